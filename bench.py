@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the BEV-projection hot path (BASELINE.json metric: BEV pool fwd+bwd frames/s
+and fraction of HBM peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One *step* = one pass of the camera pooling path over one batch of synthetic frames on each
+GPU: plan build (cell index + stable sort) -> fused voxel-pool forward -> fused backward into
+the depth and context gradients.  The workload is BASELINE.json configs[1] (CFG-2: aiMotive
+4-cam rig, D=112, 16x44 feature map, C=80, fp32, BEV grid 512x64).  The path shards by sample:
+every rank processes its own frames, there is no collective on the data path ("weak" scaling).
+
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for the byte accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mm_training_b200 import synthetic                      # noqa: E402
+from mm_training_b200.configs import CFG_2, CFG_AIM          # noqa: E402
+
+METRIC = 'bev_pool_fwd_bwd_frames_per_s'
+UNIT = 'frames/s'
+
+
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(cfg, kept_per_frame: float, s: int = 4):
+    """compulsory traffic of the fused op per frame."""
+    P = cfg.points_per_frame
+    h, w = cfg.feat_hw
+    S = cfg.num_cams * h * w
+    C = cfg.output_channels
+    x, y, _ = cfg.voxel_num
+    G = x * y
+    K = kept_per_frame
+    fwd_kernel = s * K + 4 * K + 4 * G + s * C * S + s * C * G       # depth+ids of kept, CSR, ctx, out
+    bwd_kernel = s * C * G + s * P + 4 * P + s * C * S + s * P + s * C * S
+    step = 16 * P + 3 * s * P + 3 * s * C * S + 2 * s * C * G       # formula of section 8(d)
+    return dict(fused_forward=fwd_kernel, fused_backward=bwd_kernel, step=step)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def time_cuda(fn, iters, warmup):
+    """median / min ms of ``fn`` with CUDA events on the current stream."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts), min(ts)
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_pipeline_fwd_bwd(geom, depth, ctx, go, vn):
+    """CPU path = the oracle port: materialised outer product + index_add_ forward, autograd
+    backward to depth/context (pure torch; this is the ONE place bench.py executes oracle/)."""
+    from oracle import voxel_pool_ref as vp
+    d = depth.detach().requires_grad_(True)
+    c = ctx.detach().requires_grad_(True)
+    B, N = geom.shape[0], geom.shape[1]
+    X, Y, Z = vn
+    C = c.shape[1]
+    feats = vp.materialise_features_ref(d, c, B, N).reshape(-1, C)
+    kept, lin, _ = vp.cell_index_ref(geom, vn)
+    k = kept.reshape(-1)
+    out = torch.zeros(B * Y * X, C).index_add(0, lin.reshape(-1)[k], feats[k])
+    out = out.view(B, Y, X, C).permute(0, 3, 1, 2)
+    out.backward(go)
+    return out.detach(), d.grad, c.grad
+
+
+def run_cpu_baseline(cfg, frames: int, iters: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    geom, vn = synthetic.camera_rig(cfg, frames, yaw_jitter_deg=5.0)
+    depth, ctx, go = synthetic.camera_features(cfg, frames)
+    vn = vn.tolist()
+    cpu_pipeline_fwd_bwd(geom, depth, ctx, go, vn)                      # warm-up
+    ts = []
+    for _ in range(iters):
+        t = time.perf_counter()
+        cpu_pipeline_fwd_bwd(geom, depth, ctx, go, vn)
+        ts.append(time.perf_counter() - t)
+    best = statistics.median(ts)
+    return {'value': frames / best, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{frames} frames of {cfg.name} x {iters} iterations (median), pure-torch '
+                      f'materialise + index_add_ forward + autograd backward', 'ms_per_frame': best / frames * 1e3}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'aim'])
+    ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--no-extras', action='store_true', help='skip e2e / cpu / reference-CUDA side measurements')
+    args = ap.parse_args()
+    cfg = CFG_2 if args.workload == 'cfg2' else CFG_AIM
+    if args.workload == 'aim' and args.batch == 32:
+        args.batch = 4
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+
+    workload = dict(workload=cfg.name, frames_per_gpu_per_step=args.batch, op='plan_build+fused_forward+fused_backward',
+                    points_per_frame=cfg.points_per_frame, channels=cfg.output_channels,
+                    voxel_num=list(cfg.voxel_num), sharding='by sample, no collective',
+                    cache='inputs+outputs per step exceed the 126 MB L2 (no flush needed)')
+
+    if args.impl == 'reference':
+        # CPU arm: the reference's path on the host cores (pure-torch scatter-add port), rank 0 only
+        if rank != 0:
+            return
+        frames = 2
+        t0 = time.perf_counter()
+        vals = []
+        res = None
+        for _ in range(max(1, min(args.steps, 5))):
+            res = run_cpu_baseline(cfg, frames, 1)
+            vals.append(res['value'])
+            if time.perf_counter() - t0 > 120:
+                break
+        v = statistics.median(vals)
+        res['value'] = v
+        line = {'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(vals),
+                'warmup': 1, 'ms_per_step': frames / v * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+                'config': dict(workload, frames_per_gpu_per_step=frames, device='cpu'),
+                'cpu_baseline': res,
+                'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ---------------------------------------------------------------- native arm
+    import torch.distributed as dist
+    from mm_training_b200 import _lib
+    from mm_training_b200.ops.voxel_pooling import (build_plan, fused_backward, fused_forward,
+                                                    voxel_pooling_fused)
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.lib()
+
+    B = args.batch
+    geom, vn_t = synthetic.camera_rig(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=1 + rank)
+    vn = tuple(int(v) for v in vn_t.tolist())
+    depth, ctx, go = synthetic.camera_features(cfg, B, device=dev, seed=1 + rank)
+
+    def step():
+        plan = build_plan(geom, vn)
+        out = fused_forward(plan, depth, ctx)
+        gd, gc = fused_backward(plan, go, depth, ctx)
+        return plan, out, gd, gc
+
+    plan, out, gd, gc = step()
+    torch.cuda.synchronize()
+    kept_per_frame = int(plan.cell_start[-1].item()) / B
+    bytes_ = algorithmic_bytes(cfg, kept_per_frame)
+
+    l0 = _lib.launch_count()
+    step()
+    launches_per_step = _lib.launch_count() - l0
+
+    use_graph = not args.no_graph
+    graph = None
+    if use_graph:
+        try:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+            torch.cuda.current_stream().wait_stream(s)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                keep = step()                                   # noqa: F841  (outputs stay alive in the pool)
+            run = graph.replay
+        except Exception as e:                                  # pragma: no cover
+            print(f'[bench] CUDA graph capture failed ({e}); launching eagerly', file=sys.stderr)
+            graph, run = None, step
+    else:
+        run = step
+
+    for _ in range(max(3, args.warmup)):
+        run()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            run()
+        ev1.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
+
+    # ---- per-kernel timing (CUDA events on the launching stream), same inputs, warm
+    stages = {}
+    stages['plan_build'] = time_cuda(lambda: build_plan(geom, vn), 20, 3)
+    stages['fused_forward(+ctx transpose)'] = time_cuda(lambda: fused_forward(plan, depth, ctx), 20, 3)
+    stages['fused_backward(+grad transpose)'] = time_cuda(lambda: fused_backward(plan, go, depth, ctx), 20, 3)
+    ctx_nhwc = ctx.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    go_nhwc = go.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    k_fwd = time_cuda(lambda: fused_forward(plan, depth, ctx_nhwc), 20, 3)
+    k_bwd = time_cuda(lambda: fused_backward(plan, go_nhwc, depth, ctx), 20, 3)
+    stages['fused_forward_kernel'] = k_fwd
+    stages['fused_backward_kernel'] = k_bwd
+    dom_name, dom = ('fused_backward', k_bwd) if k_bwd[0] >= k_fwd[0] else ('fused_forward', k_fwd)
+    achieved = bytes_[dom_name] * B / (dom[0] * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': dom_name + '_kernel', 'achieved': achieved, 'peak': peak_gbs,
+                'unit': 'GB/s', 'frac': achieved / peak_gbs, 'peak_source': peak_src, 'traffic': None,
+                'algorithmic_bytes_per_frame': bytes_[dom_name], 'kernel_ms': dom[0],
+                'frac_of_nominal_8TBps': achieved / 8000.0}
+    step_gbs = bytes_['step'] * B / (ms_per_step * 1e-3) / 1e9
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload, launch='cuda_graph_replay' if graph is not None else 'eager',
+                           kept_points_per_frame=kept_per_frame),
+            'roofline': roofline,
+            'step_roofline': {'algorithmic_bytes_per_frame': bytes_['step'], 'achieved': step_gbs, 'unit': 'GB/s',
+                              'frac': step_gbs / peak_gbs, 'frac_of_nominal_8TBps': step_gbs / 8000.0},
+            'stages_ms': {k: {'median': v[0], 'min': v[1]} for k, v in stages.items()},
+            'gpu_launches': launches_per_step * args.steps,
+            'clocks': clocks.summary()}
+
+    if not args.no_extras and world == 1:
+        # ---- e2e: public autograd API, HOST pinned inputs, H2D + D2H inside the timed region
+        h_geom, h_depth, h_ctx, h_go = (t.cpu().pin_memory() for t in (geom, depth, ctx, go))
+        d_geom, d_depth, d_ctx, d_go = (torch.empty_like(t) for t in (geom, depth, ctx, go))
+        X, Y, _ = vn
+        h_out = torch.empty(B, cfg.output_channels, Y, X).pin_memory()
+        h_gd, h_gc = torch.empty_like(h_depth).pin_memory(), torch.empty_like(h_ctx).pin_memory()
+
+        def e2e_step():
+            d_geom.copy_(h_geom, non_blocking=True)
+            d_depth.copy_(h_depth, non_blocking=True)
+            d_ctx.copy_(h_ctx, non_blocking=True)
+            d_go.copy_(h_go, non_blocking=True)
+            dd = d_depth.detach().requires_grad_(True)
+            cc = d_ctx.detach().requires_grad_(True)
+            o = voxel_pooling_fused(d_geom, dd, cc, vn)
+            o.backward(d_go)
+            h_out.copy_(o.detach(), non_blocking=True)
+            h_gd.copy_(dd.grad, non_blocking=True)
+            h_gc.copy_(cc.grad, non_blocking=True)
+        e2e_iters = max(5, min(args.steps, 20))
+        for _ in range(3):
+            e2e_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_iters):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        e2e_ms = a.elapsed_time(b) / e2e_iters
+        h2d = sum(t.numel() * t.element_size() for t in (h_geom, h_depth, h_ctx, h_go))
+        d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gd, h_gc))
+        line['e2e'] = {'value': B / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                       'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms, 'steps': e2e_iters,
+                       'api': 'voxel_pooling_fused(...).backward(...) with pinned host tensors'}
+
+        # ---- the reference's own CUDA op on the same GPU (oracle/_ref), same inputs
+        try:
+            from oracle import ref_cuda_op
+            if ref_cuda_op.available():
+                rb = min(B, 8)
+                g_r, d_r, c_r, go_r = geom[:rb], depth[:rb * cfg.num_cams], ctx[:rb * cfg.num_cams], go[:rb]
+                d_r = d_r.detach().requires_grad_(True)
+                c_r = c_r.detach().requires_grad_(True)
+
+                def ref_step():
+                    d_r.grad = None
+                    c_r.grad = None
+                    ref_cuda_op.ref_pipeline(g_r, d_r, c_r, vn).backward(go_r)
+                med, mn = time_cuda(ref_step, 5, 2)
+                line['ref_cuda'] = {'what': 'reference pipeline lss_fpn.py:441-466 with its own CUDA kernel '
+                                            '(compiled for sm_100a) + autograd backward, same GPU',
+                                    'frames_per_step': rb, 'ms_per_step': med, 'value': rb / (med * 1e-3),
+                                    'unit': UNIT}
+        except Exception as e:                                  # pragma: no cover
+            line['ref_cuda'] = {'error': repr(e)}
+
+        # ---- CPU baseline: oracle port on the host cores, bounded sample
+        line['cpu_baseline'] = run_cpu_baseline(cfg, 2, 3)
+    else:
+        line['e2e'] = None
+
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,101 @@
+/* libbevpool_sm100 -- C ABI of the B200-native BEV projection hot path.
+ *
+ * Drop-in boundary for the native side of aimotive/mm_training's voxel pooling
+ * (reference: ops/voxel_pooling/src/voxel_pooling_forward.cpp:24-37, the pybind
+ * function `voxel_pooling_forward_wrapper`, and its launcher
+ * ops/voxel_pooling/src/voxel_pooling_forward_cuda.cu:38-56) and for the
+ * third-party voxelizer / pillar scatter the reference reaches through
+ * models/bev_depth.py:181-183 (mmcv `hard_voxelize_forward`, mmdet3d
+ * `HardSimpleVFE`, `PointPillarsScatter` / `SparseConvTensor.dense()`).
+ *
+ * Conventions (same ownership rules as the reference):
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the caller owns all buffers including workspaces (sizes come from the
+ *     *_sizes queries); the library never allocates or frees device memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     uses the current device, and is CUDA-graph capturable;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative
+ *     BEVPOOL_E_* argument error.  The library never calls exit() (the
+ *     reference does: voxel_pooling_forward_cuda.cu:52-55).
+ */
+#ifndef BEVPOOL_SM100_H_
+#define BEVPOOL_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEVPOOL_ABI_VERSION 1
+
+#define BEVPOOL_OK            0
+#define BEVPOOL_E_ARG        -1   /* null pointer / non-positive size            */
+#define BEVPOOL_E_RANGE      -2   /* B*Np or B*X*Y does not fit 31 bits          */
+#define BEVPOOL_E_CHANNELS   -3   /* channel count unsupported by this build     */
+#define BEVPOOL_E_ALIGN      -4   /* pointer not 16-byte aligned                 */
+#define BEVPOOL_E_DTYPE      -5   /* unknown dtype code                          */
+
+/* element types of feature tensors (accumulation is always fp32) */
+#define BEVPOOL_F32  0
+#define BEVPOOL_F16  1
+#define BEVPOOL_BF16 2
+
+int         bevpool_abi_version(void);
+const char *bevpool_error_string(int code);
+/* number of CUDA kernels this library has launched in this process (memsets not counted) */
+int64_t     bevpool_launch_count(void);
+
+/* ---- plan: cell index + stable sort of kept points by BEV cell -------------------
+ * Replaces the per-call index work of voxel_pooling_forward_cuda.cu:19-29 (bounds
+ * test, z-collapse, pos_memo).  geom_xyz: int32 (B, Np, 3) contiguous, voxel_num
+ * = [X, Y, Z].  A plan depends only on geom_xyz and can be reused while the camera
+ * geometry is unchanged.                                                          */
+int bevpool_plan_sizes(int batch, int64_t num_points, int num_voxel_x, int num_voxel_y,
+                       size_t *plan_bytes, size_t *temp_bytes);
+int bevpool_plan_build(const int32_t *geom_xyz, int batch, int64_t num_points,
+                       int num_voxel_x, int num_voxel_y, int num_voxel_z,
+                       void *plan, void *temp, void *stream);
+/* the reference's pos_memo (voxel_pooling.py:40, .cu:27-29): int32 (B, Np, 3) = (b, y, x) or -1 */
+int bevpool_plan_pos_memo(const void *plan, int batch, int64_t num_points, int num_voxel_x,
+                          int num_voxel_y, int32_t *pos_memo, void *stream);
+/* device pointers into a built plan (for tests / diagnostics) */
+int bevpool_plan_views(const void *plan, int batch, int64_t num_points, int num_voxel_x,
+                       int num_voxel_y, const int32_t **cell_of_point,
+                       const int32_t **cell_start, const int32_t **sorted_ids);
+
+/* ---- drop-in op: voxel_pooling(geom_xyz, input_features, voxel_num) --------------
+ * forward  (voxel_pooling.py:10-55 + .cu:9-36): features (B, Np, C) -> out (B, Y, X, C),
+ *          every cell written exactly once (no pre-zeroing needed), deterministic.
+ * backward (voxel_pooling.py:58-69): grad_out given as (B, Y, X, C) rows ->
+ *          grad_features (B, Np, C), dropped points get zeros.                      */
+int bevpool_forward(const void *plan, const void *features, void *out_nhwc, int dtype,
+                    int batch, int64_t num_points, int channels, int num_voxel_x,
+                    int num_voxel_y, void *stream);
+int bevpool_backward(const void *plan, const void *grad_out_nhwc, void *grad_features,
+                     int dtype, int batch, int64_t num_points, int channels,
+                     int num_voxel_x, int num_voxel_y, void *stream);
+
+/* ---- fused op: depth (x) context outer product never materialised ----------------
+ * Replaces layers/backbones/lss_fpn.py:441-464 + the op.  Points are enumerated
+ * (b, n, d, h, w) like the reference's (B, N, D, H, W, C) tensor, Np = N*D*H*W.
+ * depth (B*N, D, H, W); context_nhwc (B*N, H, W, C); context_nchw (B*N, C, H, W).   */
+int bevpool_fused_forward(const void *plan, const void *depth, const void *context_nhwc,
+                          void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
+                          int feat_h, int feat_w, int channels, int num_voxel_x,
+                          int num_voxel_y, void *stream);
+int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const void *depth,
+                           const void *context_nchw, void *grad_depth, void *grad_context_nchw,
+                           int dtype, int batch, int num_cams, int depth_bins, int feat_h,
+                           int feat_w, int channels, int num_voxel_x, int num_voxel_y,
+                           void *stream);
+
+/* ---- layout helper: (batch, rows, cols) -> (batch, cols, rows), e.g. NCHW <-> NHWC */
+int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t rows,
+                      int64_t cols, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVPOOL_SM100_H_ */

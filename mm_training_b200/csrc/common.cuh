@@ -1,0 +1,102 @@
+// Shared helpers for libbevpool_sm100 (sm_100a only; no torch headers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/bevpool_sm100.h"
+
+#define BEVPOOL_RETURN_IF_CUDA(expr)              \
+  do {                                            \
+    cudaError_t _e = (expr);                      \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
+
+// placed after every kernel launch: counts it (bevpool_launch_count) and surfaces launch errors
+#define BEVPOOL_LAUNCH_CHECK()                    \
+  do {                                            \
+    ++::bevpool::g_kernel_launches;               \
+    cudaError_t _e = cudaPeekAtLastError();       \
+    if (_e != cudaSuccess) return (int)_e;        \
+  } while (0)
+
+#include <atomic>
+
+namespace bevpool {
+
+extern std::atomic<long long> g_kernel_launches;   // defined in plan.cu
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- 128-bit global access with cache hints --------------------------------------
+// streaming read: data touched once (feature rows of the drop-in op): do not pollute L1
+__device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+// reused read: gathers that hit L1/L2 (context rows, gradient rows)
+__device__ __forceinline__ float4 ldg_f4(const float4 *p) { return __ldg(p); }
+// streaming store: outputs written exactly once
+__device__ __forceinline__ void stg_stream_f4(float4 *p, const float4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- plan layout -------------------------------------------------------------------
+// A plan is one caller-owned buffer:
+//   header (256 B) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
+struct PlanLayout {
+  size_t off_cell_of_point, off_cell_start, off_sorted_ids, bytes;
+};
+struct PlanHeader {       // written by the device at build time
+  int32_t magic, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
+  int64_t num_points;
+  int32_t num_kept_total;  // K = cell_start[B*G]
+};
+constexpr int32_t kPlanMagic = 0x42455631;  // "BEV1"
+
+__host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points, int X, int Y) {
+  PlanLayout L;
+  const size_t P = (size_t)batch * (size_t)num_points;
+  const size_t G = (size_t)batch * (size_t)X * (size_t)Y;
+  size_t o = 256;
+  L.off_cell_of_point = o; o = align_up(o + P * 4, 256);
+  L.off_cell_start = o;    o = align_up(o + (G + 1) * 4, 256);
+  L.off_sorted_ids = o;    o = align_up(o + P * 4, 256);
+  L.bytes = o;
+  return L;
+}
+
+struct PlanView {
+  const int32_t *cell_of_point, *cell_start, *sorted_ids;
+};
+inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X, int Y) {
+  PlanLayout L = plan_layout(batch, num_points, X, Y);
+  const char *b = static_cast<const char *>(plan);
+  return PlanView{reinterpret_cast<const int32_t *>(b + L.off_cell_of_point),
+                  reinterpret_cast<const int32_t *>(b + L.off_cell_start),
+                  reinterpret_cast<const int32_t *>(b + L.off_sorted_ids)};
+}
+
+inline int check_plan_dims(int batch, int64_t num_points, int X, int Y) {
+  if (batch <= 0 || num_points <= 0 || X <= 0 || Y <= 0) return BEVPOOL_E_ARG;
+  if ((int64_t)batch * num_points >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
+  if ((int64_t)batch * X * Y >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
+  return BEVPOOL_OK;
+}
+
+}  // namespace bevpool

@@ -1,0 +1,350 @@
+// Pooling plan: per-point BEV cell index + deterministic (stable) sort of the kept
+// points by cell, giving a CSR (cell_start, sorted_ids) that every reduction kernel
+// walks in a fixed order.  Replaces the index half of the reference kernel
+// (ops/voxel_pooling/src/voxel_pooling_forward_cuda.cu:19-29) and removes the need
+// for its atomicAdd (:30-34).
+//
+// Algorithm: per-sample LSD radix sort on the in-sample cell id (y*X + x), 2 passes
+// for grids up to 2^20 cells.  Dropped points are compacted away in pass 0, so the
+// sort moves K (kept) pairs, not P.  Each pass = tile histogram -> one decoupled
+// look-back scan over [sample][digit][tile] -> stable scatter (warp match-any ranks).
+// The sort is stable, so points of one cell stay in ascending point order: the same
+// order the reference test's golden loop and torch.index_add_ visit them in.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace bevpool {
+
+std::atomic<long long> g_kernel_launches{0};
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 keys per CTA
+constexpr int kMaxPasses = 3;
+
+struct SortConfig {
+  int npass;
+  int bits[kMaxPasses];
+  int shift[kMaxPasses];
+};
+
+static SortConfig sort_config(int64_t cells_per_sample) {
+  int nbits = 1;
+  while ((1ll << nbits) < cells_per_sample) ++nbits;
+  SortConfig c;
+  c.npass = (nbits + 9) / 10;
+  const int per = (nbits + c.npass - 1) / c.npass;
+  int shift = 0;
+  for (int p = 0; p < kMaxPasses; ++p) {
+    c.bits[p] = p < c.npass ? (nbits - shift < per ? nbits - shift : per) : 0;
+    if (p < c.npass && c.bits[p] < 1) c.bits[p] = 1;
+    c.shift[p] = shift;
+    shift += c.bits[p];
+  }
+  return c;
+}
+
+struct TempLayout {
+  size_t off_scan[kMaxPasses + 1];  // scan workspaces: one per pass + cell counts
+  size_t off_hist[kMaxPasses];      // tile histograms [sample][digit][tile] (+1 total)
+  size_t zero_bytes;                // everything above is memset to 0 per build
+  size_t off_keys[2], off_ids[2];   // ping-pong buffers for passes before the last
+  size_t bytes;
+  int64_t hist_n[kMaxPasses];
+  int tiles_per_sample;
+};
+
+static TempLayout temp_layout(int batch, int64_t num_points, int X, int Y) {
+  const SortConfig sc = sort_config((int64_t)X * Y);
+  TempLayout L{};
+  L.tiles_per_sample = (int)ceil_div64(num_points, kSortTile);
+  size_t o = 0;
+  for (int p = 0; p < kMaxPasses; ++p) {
+    L.hist_n[p] = p < sc.npass ? (int64_t)batch * (1ll << sc.bits[p]) * L.tiles_per_sample + 1 : 0;
+  }
+  for (int p = 0; p < sc.npass; ++p) {
+    L.off_scan[p] = o;
+    o += scan_workspace_bytes(L.hist_n[p]);
+  }
+  L.off_scan[kMaxPasses] = o;
+  o += scan_workspace_bytes((int64_t)batch * X * Y + 1);
+  for (int p = 0; p < sc.npass; ++p) {
+    L.off_hist[p] = o;
+    o = align_up(o + (size_t)L.hist_n[p] * 4, 256);
+  }
+  L.zero_bytes = o;
+  const size_t P = (size_t)batch * (size_t)num_points;
+  const int nbuf = sc.npass >= 3 ? 2 : (sc.npass == 2 ? 1 : 0);
+  for (int i = 0; i < 2; ++i) {
+    L.off_keys[i] = o;
+    if (i < nbuf) o = align_up(o + P * 4, 256);
+    L.off_ids[i] = o;
+    if (i < nbuf) o = align_up(o + P * 4, 256);
+  }
+  L.bytes = o > 256 ? o : 256;
+  return L;
+}
+
+// ---- kernel 1: cell index, per-cell counts, pass-0 tile histogram --------------------
+__global__ void __launch_bounds__(kSortThreads)
+plan_key_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
+                int32_t *__restrict__ cell_of_point, uint32_t *__restrict__ cell_count,
+                uint32_t *__restrict__ hist, int bins, int tiles_per_sample) {
+  extern __shared__ uint32_t s_hist[];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const int64_t sample_base = (int64_t)b * num_points;
+  const int64_t cells = (int64_t)X * Y;
+  const int64_t tile_base = (int64_t)tile * kSortTile;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t p = tile_base + i * kSortThreads + threadIdx.x;
+    if (p < num_points) {
+      const int64_t gp = sample_base + p;
+      const int x = __ldg(geom + gp * 3 + 0);
+      const int y = __ldg(geom + gp * 3 + 1);
+      const int z = __ldg(geom + gp * 3 + 2);
+      // reference bounds test, voxel_pooling_forward_cuda.cu:24; z gates only (:32-33)
+      const bool kept = x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z;
+      const int cell = kept ? y * X + x : -1;
+      cell_of_point[gp] = cell;
+      if (kept) {
+        atomicAdd(cell_count + (int64_t)b * cells + cell, 1u);
+        atomicAdd(s_hist + (cell & (bins - 1)), 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += kSortThreads)
+    hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
+}
+
+// ---- tile histogram of a later pass (input already compacted per sample) ---------------
+__global__ void __launch_bounds__(kSortThreads)
+sort_hist_kernel(const int32_t *__restrict__ keys, const uint32_t *__restrict__ scanned0, int bins0,
+                 int shift, int bins, int tiles_per_sample, uint32_t *__restrict__ hist) {
+  extern __shared__ uint32_t s_hist[];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  const int64_t seg_begin = scanned0[(int64_t)b * bins0 * tiles_per_sample];
+  const int64_t seg_end = scanned0[(int64_t)(b + 1) * bins0 * tiles_per_sample];
+  const int64_t tile_begin = seg_begin + (int64_t)tile * kSortTile;
+  if (tile_begin >= seg_end) return;
+  for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t idx = tile_begin + i * kSortThreads + threadIdx.x;
+    if (idx < seg_end) atomicAdd(s_hist + ((keys[idx] >> shift) & (bins - 1)), 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += kSortThreads)
+    hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
+}
+
+// ---- stable scatter of one radix pass ---------------------------------------------------
+// Element order inside a CTA is (warp, round, lane) == ascending input index, so ranks
+// handed out in that order keep the sort stable.
+template <bool kFirst>
+__global__ void __launch_bounds__(kSortThreads)
+sort_scatter_kernel(const int32_t *__restrict__ in_keys, const int32_t *__restrict__ in_ids,
+                    int32_t *__restrict__ out_keys, int32_t *__restrict__ out_ids,
+                    const uint32_t *__restrict__ scanned, const uint32_t *__restrict__ scanned0,
+                    int bins0, int64_t num_points, int shift, int bins, int tiles_per_sample) {
+  extern __shared__ uint32_t s_cnt[];  // [kSortWarps][bins]
+  const int b = blockIdx.y, tile = blockIdx.x;
+  int64_t seg_begin, seg_end;
+  if (kFirst) {
+    seg_begin = (int64_t)b * num_points;
+    seg_end = seg_begin + num_points;
+  } else {
+    seg_begin = scanned0[(int64_t)b * bins0 * tiles_per_sample];
+    seg_end = scanned0[(int64_t)(b + 1) * bins0 * tiles_per_sample];
+  }
+  const int64_t tile_begin = seg_begin + (int64_t)tile * kSortTile;
+  if (tile_begin >= seg_end) return;
+
+  for (int i = threadIdx.x; i < kSortWarps * bins; i += kSortThreads) s_cnt[i] = 0u;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *cnt = s_cnt + warp * bins;
+  const int64_t warp_begin = tile_begin + warp * (kSortItems * 32);
+  int32_t key[kSortItems], id[kSortItems];
+  uint32_t rank[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const int64_t idx = warp_begin + r * 32 + lane;
+    const bool in_range = idx < seg_end;
+    key[r] = in_range ? in_keys[idx] : -1;
+    id[r] = kFirst ? (int32_t)idx : (in_range ? in_ids[idx] : -1);
+  }
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const bool valid = key[r] >= 0;
+    const uint32_t digit = valid ? (uint32_t)((key[r] >> shift) & (bins - 1)) : (uint32_t)bins;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) {
+      base = cnt[digit];
+      cnt[digit] = base + __popc(peers);
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    rank[r] = base + __popc(peers & ((1u << lane) - 1u));
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int bin = threadIdx.x; bin < bins; bin += kSortThreads) {
+    uint32_t run = scanned[((int64_t)b * bins + bin) * tiles_per_sample + tile];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t t = s_cnt[w * bins + bin];
+      s_cnt[w * bins + bin] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    if (key[r] >= 0) {
+      const uint32_t digit = (uint32_t)((key[r] >> shift) & (bins - 1));
+      const uint32_t pos = cnt[digit] + rank[r];
+      out_ids[pos] = id[r];
+      if (out_keys) out_keys[pos] = key[r];
+    }
+  }
+}
+
+__global__ void pos_memo_kernel(const int32_t *__restrict__ cell_of_point, int64_t num_points,
+                                int64_t total, int X, int32_t *__restrict__ pos_memo) {
+  const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= total) return;
+  const int cell = cell_of_point[gp];
+  int b = -1, y = -1, x = -1;
+  if (cell >= 0) {
+    b = (int)(gp / num_points);
+    y = cell / X;
+    x = cell - y * X;
+  }
+  pos_memo[gp * 3 + 0] = b;
+  pos_memo[gp * 3 + 1] = y;
+  pos_memo[gp * 3 + 2] = x;
+}
+
+}  // namespace bevpool
+
+using namespace bevpool;
+
+extern "C" int bevpool_plan_sizes(int batch, int64_t num_points, int X, int Y, size_t *plan_bytes,
+                                  size_t *temp_bytes) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
+  *plan_bytes = plan_layout(batch, num_points, X, Y).bytes;
+  *temp_bytes = temp_layout(batch, num_points, X, Y).bytes;
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_points, int X, int Y,
+                                  int Z, void *plan, void *temp, void *stream_) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!geom || !plan || !temp || Z <= 0) return BEVPOOL_E_ARG;
+  if (!aligned16(plan) || !aligned16(temp)) return BEVPOOL_E_ALIGN;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t cells = (int64_t)X * Y;
+  const SortConfig sc = sort_config(cells);
+  const PlanLayout PL = plan_layout(batch, num_points, X, Y);
+  const TempLayout TL = temp_layout(batch, num_points, X, Y);
+  char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
+  int32_t *cell_of_point = reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point);
+  uint32_t *cell_start = reinterpret_cast<uint32_t *>(pb + PL.off_cell_start);
+  int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
+  uint32_t *hist[kMaxPasses];
+  for (int p = 0; p < sc.npass; ++p) hist[p] = reinterpret_cast<uint32_t *>(tb + TL.off_hist[p]);
+  int32_t *keys[2] = {reinterpret_cast<int32_t *>(tb + TL.off_keys[0]),
+                      reinterpret_cast<int32_t *>(tb + TL.off_keys[1])};
+  int32_t *ids[2] = {reinterpret_cast<int32_t *>(tb + TL.off_ids[0]),
+                     reinterpret_cast<int32_t *>(tb + TL.off_ids[1])};
+  const int T = TL.tiles_per_sample;
+  const dim3 grid(T, batch);
+
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(pb, 0, PL.off_cell_of_point, stream));
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(cell_start, 0, ((size_t)batch * cells + 1) * 4, stream));
+
+  const int bins0 = 1 << sc.bits[0];
+  plan_key_kernel<<<grid, kSortThreads, bins0 * 4, stream>>>(
+      geom, num_points, X, Y, Z, cell_of_point, cell_start, hist[0], bins0, T);
+  BEVPOOL_LAUNCH_CHECK();
+  rc = launch_scan_exclusive(hist[0], hist[0], TL.hist_n[0], tb + TL.off_scan[0], stream);
+  if (rc) return rc;
+  {
+    const bool last = sc.npass == 1;
+    sort_scatter_kernel<true><<<grid, kSortThreads, kSortWarps * bins0 * 4, stream>>>(
+        cell_of_point, nullptr, last ? nullptr : keys[0], last ? sorted_ids : ids[0], hist[0],
+        hist[0], bins0, num_points, sc.shift[0], bins0, T);
+    BEVPOOL_LAUNCH_CHECK();
+  }
+  for (int p = 1; p < sc.npass; ++p) {
+    const int bins = 1 << sc.bits[p];
+    const bool last = p == sc.npass - 1;
+    const int src = (p - 1) & 1, dst = p & 1;
+    sort_hist_kernel<<<grid, kSortThreads, bins * 4, stream>>>(keys[src], hist[0], bins0,
+                                                               sc.shift[p], bins, T, hist[p]);
+    BEVPOOL_LAUNCH_CHECK();
+    rc = launch_scan_exclusive(hist[p], hist[p], TL.hist_n[p], tb + TL.off_scan[p], stream);
+    if (rc) return rc;
+    sort_scatter_kernel<false><<<grid, kSortThreads, kSortWarps * bins * 4, stream>>>(
+        keys[src], ids[src], last ? nullptr : keys[dst], last ? sorted_ids : ids[dst], hist[p],
+        hist[0], bins0, num_points, sc.shift[p], bins, T);
+    BEVPOOL_LAUNCH_CHECK();
+  }
+  rc = launch_scan_exclusive(cell_start, cell_start, (int64_t)batch * cells + 1,
+                             tb + TL.off_scan[kMaxPasses], stream);
+  return rc;
+}
+
+extern "C" int bevpool_plan_pos_memo(const void *plan, int batch, int64_t num_points, int X, int Y,
+                                     int32_t *pos_memo, void *stream_) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan || !pos_memo) return BEVPOOL_E_ARG;
+  const PlanView v = plan_view(plan, batch, num_points, X, Y);
+  const int64_t total = (int64_t)batch * num_points;
+  pos_memo_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      v.cell_of_point, num_points, total, X, pos_memo);
+  BEVPOOL_LAUNCH_CHECK();
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_plan_views(const void *plan, int batch, int64_t num_points, int X, int Y,
+                                  const int32_t **cell_of_point, const int32_t **cell_start,
+                                  const int32_t **sorted_ids) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan) return BEVPOOL_E_ARG;
+  const PlanView v = plan_view(plan, batch, num_points, X, Y);
+  if (cell_of_point) *cell_of_point = v.cell_of_point;
+  if (cell_start) *cell_start = v.cell_start;
+  if (sorted_ids) *sorted_ids = v.sorted_ids;
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_abi_version(void) { return BEVPOOL_ABI_VERSION; }
+
+extern "C" int64_t bevpool_launch_count(void) { return (int64_t)g_kernel_launches.load(); }
+
+extern "C" const char *bevpool_error_string(int code) {
+  switch (code) {
+    case BEVPOOL_OK: return "ok";
+    case BEVPOOL_E_ARG: return "invalid argument (null pointer or non-positive size)";
+    case BEVPOOL_E_RANGE: return "problem too large for 32-bit point/cell indices";
+    case BEVPOOL_E_CHANNELS: return "unsupported channel count";
+    case BEVPOOL_E_ALIGN: return "pointer must be 16-byte aligned";
+    case BEVPOOL_E_DTYPE: return "unknown dtype code";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}

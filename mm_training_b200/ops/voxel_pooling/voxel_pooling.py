@@ -1,0 +1,269 @@
+"""Drop-in ``voxel_pooling`` autograd op and its fused sibling, on libbevpool_sm100.
+
+Mirrors ``ops/voxel_pooling/voxel_pooling.py`` of the reference:
+
+* ``voxel_pooling(geom_xyz, input_features, voxel_num) -> (B, C, Y, X)`` --
+  ``VoxelPooling.forward`` :10-55 / ``.backward`` :58-69 / ``voxel_pooling = VoxelPooling.apply`` :72.
+  Same asserts (contiguous inputs, matching point counts), same output (a permuted view of a
+  (B, Y, X, C) buffer), gradient only w.r.t. ``input_features`` in the caller's shape.
+* ``voxel_pooling_fused(geom_xyz, depth, context, voxel_num)`` replaces the materialised outer
+  product of ``layers/backbones/lss_fpn.py:441-464``: ``depth`` (B*N, D, H, W), ``context``
+  (B*N, C, H, W); gradients flow to both.
+
+Differences, all deliberate: fp16/bf16 are accepted (fp32 accumulation);
+``voxel_num`` may be a tensor on any device or a python sequence; the backward allocates a fresh
+gradient instead of mutating a tensor saved in forward; errors raise instead of ``exit(-1)``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+from torch.autograd import Function
+
+from ... import _lib
+
+VoxelNum = Union[torch.Tensor, Sequence[int]]
+_voxel_num_cache = {}
+
+
+def _voxel_num_ints(voxel_num: VoxelNum) -> Tuple[int, int, int]:
+    """[X, Y, Z] as python ints.  A CUDA tensor costs one D2H sync the first time it is seen
+    (the reference pays >= 5 per call, voxel_pooling.py:37-38,45-47)."""
+    if isinstance(voxel_num, torch.Tensor):
+        key = (voxel_num.data_ptr(), voxel_num._version, voxel_num.device)
+        hit = _voxel_num_cache.get(key)
+        if hit is None:
+            hit = tuple(int(v) for v in voxel_num.tolist())
+            if len(_voxel_num_cache) > 64:
+                _voxel_num_cache.clear()
+            _voxel_num_cache[key] = hit
+        voxel_num = hit
+    x, y, z = (int(v) for v in voxel_num)
+    return x, y, z
+
+
+class PoolingPlan:
+    """Cell index of every point + kept points sorted by BEV cell (CSR).  Depends only on
+    ``geom_xyz`` and ``voxel_num``: reuse it while the camera geometry is unchanged."""
+
+    def __init__(self, geom_xyz: torch.Tensor, voxel_num: VoxelNum):
+        _lib.require_cuda(geom_xyz)
+        if geom_xyz.dtype != torch.int32:
+            raise TypeError(f'geom_xyz must be int32 (got {geom_xyz.dtype})')
+        assert geom_xyz.is_contiguous()
+        assert geom_xyz.shape[-1] == 3
+        self.voxel_num = _voxel_num_ints(voxel_num)
+        self.batch = int(geom_xyz.shape[0])
+        self.num_points = int(geom_xyz.numel() // (3 * self.batch))
+        self.device = geom_xyz.device
+        X, Y, Z = self.voxel_num
+        L = _lib.lib()
+        pb, tb = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(L.bevpool_plan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
+                   'bevpool_plan_sizes')
+        with torch.cuda.device(self.device):
+            self.buffer = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
+            temp = torch.empty(tb.value, dtype=torch.uint8, device=self.device)
+            _lib.check(L.bevpool_plan_build(geom_xyz.data_ptr(), self.batch, self.num_points, X, Y, Z,
+                                            self.buffer.data_ptr(), temp.data_ptr(),
+                                            _lib.stream_ptr(self.device)), 'bevpool_plan_build')
+        # temp is released to the caching allocator here; stream-ordered reuse keeps this safe
+
+    @property
+    def ptr(self) -> int:
+        return self.buffer.data_ptr()
+
+    def _views(self):
+        X, Y, _ = self.voxel_num
+        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(_lib.lib().bevpool_plan_views(self.ptr, self.batch, self.num_points, X, Y,
+                                                 ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+                   'bevpool_plan_views')
+        base = self.ptr
+        as_i32 = self.buffer.view(torch.int32)
+        P, G = self.batch * self.num_points, self.batch * X * Y
+        o = lambda p: (p.value - base) // 4
+        return (as_i32[o(a):o(a) + P], as_i32[o(b):o(b) + G + 1], as_i32[o(c):o(c) + P])
+
+    @property
+    def cell_of_point(self) -> torch.Tensor:
+        """int32 (B, Np): in-sample cell id y*X + x, or -1 for dropped points."""
+        return self._views()[0].view(self.batch, self.num_points)
+
+    @property
+    def cell_start(self) -> torch.Tensor:
+        """int32 (B*Y*X + 1,): CSR offsets into ``sorted_ids``."""
+        return self._views()[1]
+
+    @property
+    def sorted_ids(self) -> torch.Tensor:
+        """int32 (K,): global point ids (b*Np + p) of kept points, grouped by cell, ascending inside a cell."""
+        ids = self._views()[2]
+        return ids[:int(self.cell_start[-1].item())]
+
+    def pos_memo(self) -> torch.Tensor:
+        """The reference's ``pos_memo`` (voxel_pooling.py:40): int32 (B, Np, 3) = (b, y, x) or -1."""
+        X, Y, _ = self.voxel_num
+        out = torch.empty(self.batch, self.num_points, 3, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bevpool_plan_pos_memo(self.ptr, self.batch, self.num_points, X, Y,
+                                                        out.data_ptr(), _lib.stream_ptr(self.device)),
+                       'bevpool_plan_pos_memo')
+        return out
+
+
+def build_plan(geom_xyz: torch.Tensor, voxel_num: VoxelNum) -> PoolingPlan:
+    return PoolingPlan(geom_xyz, voxel_num)
+
+
+def _transpose(x: torch.Tensor, batch: int, rows: int, cols: int) -> torch.Tensor:
+    """(batch, rows, cols) -> (batch, cols, rows) with the library's tiled transpose."""
+    out = torch.empty(batch, cols, rows, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().bevpool_transpose(x.data_ptr(), out.data_ptr(), _lib.dtype_code(x), batch, rows, cols,
+                                            _lib.stream_ptr(x.device)), 'bevpool_transpose')
+    return out
+
+
+def _grad_rows_nhwc(grad_out: torch.Tensor) -> torch.Tensor:
+    """grad_out arrives as (B, C, Y, X) with arbitrary strides; the kernels want (B, Y, X, C) rows.
+    Zero-copy when it already is a permuted NHWC buffer (what autograd hands back for the
+    permuted view we return), one tiled transpose when it is NCHW-contiguous."""
+    B, C, Y, X = grad_out.shape
+    nhwc = grad_out.permute(0, 2, 3, 1)
+    if nhwc.is_contiguous():
+        return nhwc
+    if not grad_out.is_contiguous():
+        grad_out = grad_out.contiguous()
+    return _transpose(grad_out, B, C, Y * X).view(B, Y, X, C)
+
+
+def pool_forward(plan: PoolingPlan, input_features: torch.Tensor) -> torch.Tensor:
+    """features (B, ..., C) -> (B, Y, X, C); every cell written once, no pre-zeroing."""
+    X, Y, _ = plan.voxel_num
+    B, C = plan.batch, input_features.shape[-1]
+    out = torch.empty(B, Y, X, C, dtype=input_features.dtype, device=input_features.device)
+    _lib.check(_lib.lib().bevpool_forward(plan.ptr, input_features.data_ptr(), out.data_ptr(),
+                                          _lib.dtype_code(input_features), B, plan.num_points, C, X, Y,
+                                          _lib.stream_ptr(out.device)), 'bevpool_forward')
+    return out
+
+
+def pool_backward(plan: PoolingPlan, grad_output: torch.Tensor, input_shape) -> torch.Tensor:
+    """grad_output (B, C, Y, X), any strides -> grad_features in ``input_shape``."""
+    X, Y, _ = plan.voxel_num
+    B, C = grad_output.shape[0], grad_output.shape[1]
+    rows = _grad_rows_nhwc(grad_output)
+    grad_in = torch.empty(input_shape, dtype=rows.dtype, device=rows.device)
+    _lib.check(_lib.lib().bevpool_backward(plan.ptr, rows.data_ptr(), grad_in.data_ptr(),
+                                           _lib.dtype_code(rows), B, plan.num_points, C, X, Y,
+                                           _lib.stream_ptr(rows.device)), 'bevpool_backward')
+    return grad_in
+
+
+def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+    """depth (B*N, D, H, W), context (B*N, C, H, W) NCHW or channels_last -> (B, Y, X, C)."""
+    BN, D, H, W = depth.shape
+    C = context.shape[1]
+    X, Y, _ = plan.voxel_num
+    B = plan.batch
+    N = BN // B
+    assert context.shape == (BN, C, H, W) and depth.dtype == context.dtype
+    assert B * N == BN and plan.num_points == N * D * H * W
+    ctx_nhwc = context.permute(0, 2, 3, 1)
+    if not ctx_nhwc.is_contiguous():          # NCHW in: one small tiled transpose (C*H*W per image)
+        ctx_nhwc = _transpose(context.contiguous(), BN, C, H * W)
+    out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
+    _lib.check(_lib.lib().bevpool_fused_forward(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
+                                                out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
+                                                C, X, Y, _lib.stream_ptr(depth.device)),
+               'bevpool_fused_forward')
+    return out
+
+
+def fused_backward(plan: PoolingPlan, grad_output: torch.Tensor, depth: torch.Tensor,
+                   context: torch.Tensor):
+    """grad_output (B, C, Y, X), any strides -> (grad_depth, grad_context (NCHW-contiguous))."""
+    BN, D, H, W = depth.shape
+    C = context.shape[1]
+    X, Y, _ = plan.voxel_num
+    B = plan.batch
+    N = BN // B
+    rows = _grad_rows_nhwc(grad_output)
+    context_nchw = context.contiguous()
+    grad_depth = torch.empty_like(depth)
+    grad_context = torch.empty_like(context_nchw)
+    _lib.check(_lib.lib().bevpool_fused_backward(
+        plan.ptr, rows.data_ptr(), depth.data_ptr(), context_nchw.data_ptr(), grad_depth.data_ptr(),
+        grad_context.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+        _lib.stream_ptr(depth.device)), 'bevpool_fused_backward')
+    return grad_depth, grad_context
+
+
+class VoxelPooling(Function):
+    @staticmethod
+    def forward(ctx, geom_xyz: torch.Tensor, input_features: torch.Tensor, voxel_num: VoxelNum,
+                plan: Optional[PoolingPlan] = None) -> torch.Tensor:
+        _lib.require_cuda(geom_xyz, input_features)
+        assert geom_xyz.is_contiguous()
+        assert input_features.is_contiguous()
+        B, C = input_features.shape[0], input_features.shape[-1]
+        num_points = input_features.numel() // (B * C)
+        assert geom_xyz.numel() // (3 * geom_xyz.shape[0]) == num_points and geom_xyz.shape[0] == B
+        X, Y, Z = _voxel_num_ints(voxel_num)
+        with torch.cuda.device(input_features.device):
+            if plan is None:
+                plan = PoolingPlan(geom_xyz, (X, Y, Z))
+            else:
+                assert (plan.batch, plan.num_points, plan.voxel_num) == (B, num_points, (X, Y, Z))
+            out = pool_forward(plan, input_features)
+        ctx.plan = plan
+        ctx.input_shape = input_features.shape
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_output_features: torch.Tensor):
+        with torch.cuda.device(grad_output_features.device):
+            grad_in = pool_backward(ctx.plan, grad_output_features, ctx.input_shape)
+        return None, grad_in, None, None
+
+
+def voxel_pooling(geom_xyz: torch.Tensor, input_features: torch.Tensor, voxel_num: VoxelNum,
+                  plan: Optional[PoolingPlan] = None) -> torch.Tensor:
+    """Scatter-sum per-point C-vectors into the BEV grid; returns (B, C, Y, X)."""
+    return VoxelPooling.apply(geom_xyz, input_features, voxel_num, plan)
+
+
+class VoxelPoolingFused(Function):
+    @staticmethod
+    def forward(ctx, geom_xyz, depth, context, voxel_num, plan):
+        _lib.require_cuda(depth, context)
+        assert depth.is_contiguous()
+        X, Y, Z = _voxel_num_ints(voxel_num)
+        with torch.cuda.device(depth.device):
+            if plan is None:
+                assert geom_xyz.is_contiguous()
+                plan = PoolingPlan(geom_xyz, (X, Y, Z))
+            assert plan.voxel_num == (X, Y, Z)
+            out = fused_forward(plan, depth, context)
+        ctx.plan = plan
+        ctx.save_for_backward(depth, context)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        depth, context = ctx.saved_tensors
+        with torch.cuda.device(grad_out.device):
+            grad_depth, grad_context = fused_backward(ctx.plan, grad_out, depth, context)
+        return None, grad_depth, grad_context, None, None
+
+
+def voxel_pooling_fused(geom_xyz: Optional[torch.Tensor], depth: torch.Tensor, context: torch.Tensor,
+                        voxel_num: VoxelNum, plan: Optional[PoolingPlan] = None) -> torch.Tensor:
+    """Lift-splat pooling without materialising depth (x) context.
+
+    geom_xyz: int32 (B, N, D, H, W, 3) (ignored when ``plan`` is given); depth (B*N, D, H, W)
+    softmax probabilities; context (B*N, C, H, W), NCHW or channels_last.  Returns (B, C, Y, X)
+    as a permuted view of a (B, Y, X, C) buffer, like the reference op."""
+    return VoxelPoolingFused.apply(geom_xyz, depth, context, voxel_num, plan)
