@@ -25,21 +25,12 @@ from torch.autograd import Function
 from ... import _lib
 
 VoxelNum = Union[torch.Tensor, Sequence[int]]
-_voxel_num_cache = {}
-
 
 def _voxel_num_ints(voxel_num: VoxelNum) -> Tuple[int, int, int]:
-    """[X, Y, Z] as python ints.  A CUDA tensor costs one D2H sync the first time it is seen
-    (the reference pays >= 5 per call, voxel_pooling.py:37-38,45-47)."""
+    """[X, Y, Z] as python ints.  A CUDA tensor costs one D2H sync per call (the reference pays
+    >= 5, voxel_pooling.py:37-38,45-47); pass python ints or a CPU tensor to avoid it."""
     if isinstance(voxel_num, torch.Tensor):
-        key = (voxel_num.data_ptr(), voxel_num._version, voxel_num.device)
-        hit = _voxel_num_cache.get(key)
-        if hit is None:
-            hit = tuple(int(v) for v in voxel_num.tolist())
-            if len(_voxel_num_cache) > 64:
-                _voxel_num_cache.clear()
-            _voxel_num_cache[key] = hit
-        voxel_num = hit
+        voxel_num = voxel_num.tolist()
     x, y, z = (int(v) for v in voxel_num)
     return x, y, z
 
