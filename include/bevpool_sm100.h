@@ -91,6 +91,13 @@ int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const vo
                            int feat_w, int channels, int num_voxel_x, int num_voxel_y,
                            void *stream);
 
+/* ---- gradient layout: grad_out (B, C, Y, X) contiguous -> rows (B, Y, X, C) --------------
+ * Only rows of cells that received a point are written (the backward kernels read no
+ * others); the rest of `rows_nhwc` is left untouched.                                 */
+int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nhwc, int dtype,
+                      int batch, int64_t num_points, int channels, int num_voxel_x,
+                      int num_voxel_y, void *stream);
+
 /* ---- layout helper: (batch, rows, cols) -> (batch, cols, rows), e.g. NCHW <-> NHWC */
 int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t rows,
                       int64_t cols, void *stream);

@@ -12,8 +12,18 @@
 // element is written exactly once by exactly one thread, in a fixed order, so results
 // are bit-stable run to run (the reference's are not).
 #include "common.cuh"
+#include "pool_g8.cuh"
+
+#include <cstdlib>
+#include <type_traits>
 
 namespace bevpool {
+
+// BEVPOOL_DISABLE_G8=1 forces the generic float4-per-lane kernels (used by the tests to cover both paths)
+static bool g8_enabled() {
+  const char *e = std::getenv("BEVPOOL_DISABLE_G8");
+  return !(e && e[0] == '1');
+}
 
 // ---- element access: 4 consecutive channels <-> float4 -------------------------------
 template <typename T> struct Vec4;
@@ -63,87 +73,106 @@ template <> struct Vec4<__nv_bfloat16> {
 
 constexpr int kPoolThreads = 256;
 constexpr int kPoolWarps = kPoolThreads / 32;
-constexpr int kUnroll = 8;  // feature rows in flight per warp
+constexpr int kUnroll = 8;     // feature rows in flight per warp
+constexpr int kFwdTile = 32;   // BEV cells per CTA (contiguous rows of the NHWC output)
 
-// ---- forward: one warp per BEV cell, lanes own float4 channel chunks -----------------
+// ---- forward: CTA = 32 consecutive BEV cells, warps pull cells from a shared counter ----
 // kFused = false: rows = feature rows (B*Np, C), streamed from HBM once.
 // kFused = true : rows = context rows (B*N*H*W, C) (L1/L2 resident), scaled by depth[p].
-// The cell's points are visited in ascending point order (stable plan), with separate
-// multiply and add (no FMA contraction), so the fp32 result is bit-identical to a
-// sequential scatter-add over the materialised tensor.
+// A cell's points are visited in ascending point order (stable plan) with separate multiply
+// and add (no FMA contraction), so the fp32 result is bit-identical to a sequential
+// scatter-add over the materialised tensor.  Empty tiles are zero-filled with coalesced stores.
+template <typename T, int CPL, bool kFused, bool kGuard>
+__device__ __forceinline__ void accum_batch(float4 (&acc)[CPL], const T *__restrict__ rows, int my_row,
+                                            float my_d, int j, int n, int lane, int C, int C4) {
+  float4 v[kUnroll][CPL];
+  float d[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const int row = __shfl_sync(0xffffffffu, my_row, j + u);
+    d[u] = __shfl_sync(0xffffffffu, my_d, j + u);
+    if (!kGuard || j + u < n) {
+      const T *rp = rows + (int64_t)row * C;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int ch = lane + 32 * k;
+        if (ch < C4) v[u][k] = kFused ? Vec4<T>::load(rp + ch * 4) : Vec4<T>::load_stream(rp + ch * 4);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    if (!kGuard || j + u < n) {
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (kFused) {
+          acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(d[u], v[u][k].x));
+          acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(d[u], v[u][k].y));
+          acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(d[u], v[u][k].z));
+          acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(d[u], v[u][k].w));
+        } else {
+          acc[k].x += v[u][k].x;
+          acc[k].y += v[u][k].y;
+          acc[k].z += v[u][k].z;
+          acc[k].w += v[u][k].w;
+        }
+      }
+    }
+  }
+}
+
 template <typename T, int CPL, bool kFused>
 __global__ void __launch_bounds__(kPoolThreads)
 pool_forward_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_ids,
                     const T *__restrict__ rows, const T *__restrict__ depth, T *__restrict__ out,
                     int64_t total_cells, int C, int dhw, int hw) {
-  const int lane = threadIdx.x & 31;
-  const int64_t cell = (int64_t)blockIdx.x * kPoolWarps + (threadIdx.x >> 5);
-  if (cell >= total_cells) return;
+  __shared__ int s_start[kFwdTile + 1];
+  __shared__ int s_next;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile0 = (int64_t)blockIdx.x * kFwdTile;
+  const int ncell = (int)min((int64_t)kFwdTile, total_cells - tile0);
   const int C4 = C >> 2;
-  const int start = cell_start[cell], end = cell_start[cell + 1];
-
-  float4 acc[CPL];
-#pragma unroll
-  for (int k = 0; k < CPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  for (int base = start; base < end; base += 32) {
-    const int n = min(32, end - base);
-    int my_row = 0;
-    float my_d = 1.f;
-    if (lane < n) {
-      const int gp = sorted_ids[base + lane];
-      if (kFused) {
-        my_d = Vec4<T>::to_float(depth[gp]);
-        my_row = (gp / dhw) * hw + gp % hw;   // pixel row: (b*N+n)*H*W + h*W + w
-      } else {
-        my_row = gp;
-      }
-    }
-    for (int j = 0; j < n; j += kUnroll) {
-      float4 v[kUnroll][CPL];
-      float d[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int src = (j + u) & 31;
-        const int row = __shfl_sync(0xffffffffu, my_row, src);
-        d[u] = __shfl_sync(0xffffffffu, my_d, src);
-        if (j + u < n) {
-          const T *rp = rows + (int64_t)row * C;
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            const int ch = lane + 32 * k;
-            if (ch < C4) v[u][k] = kFused ? Vec4<T>::load(rp + ch * 4) : Vec4<T>::load_stream(rp + ch * 4);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (j + u < n) {
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) {
-            if (lane + 32 * k < C4) {
-              if (kFused) {
-                acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(d[u], v[u][k].x));
-                acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(d[u], v[u][k].y));
-                acc[k].z = __fadd_rn(acc[k].z, __fmul_rn(d[u], v[u][k].z));
-                acc[k].w = __fadd_rn(acc[k].w, __fmul_rn(d[u], v[u][k].w));
-              } else {
-                acc[k].x += v[u][k].x;
-                acc[k].y += v[u][k].y;
-                acc[k].z += v[u][k].z;
-                acc[k].w += v[u][k].w;
-              }
-            }
-          }
-        }
-      }
-    }
+  if (threadIdx.x <= ncell) s_start[threadIdx.x] = cell_start[tile0 + threadIdx.x];
+  if (threadIdx.x == 0) s_next = kPoolWarps;
+  __syncthreads();
+  T *tile_out = out + tile0 * C;
+  if (s_start[ncell] == s_start[0]) {   // nothing lands in this tile
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < ncell * C4; i += kPoolThreads) Vec4<T>::store(tile_out + i * 4, z);
+    return;
   }
-  T *op = out + cell * C;
+  int c = warp;                          // first cell is static, later ones come from the counter
+  while (c < ncell) {
+    const int start = s_start[c], end = s_start[c + 1];
+    float4 acc[CPL];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) {
-    const int ch = lane + 32 * k;
-    if (ch < C4) Vec4<T>::store(op + ch * 4, acc[k]);
+    for (int k = 0; k < CPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int base = start; base < end; base += 32) {
+      const int n = min(32, end - base);
+      int my_row = 0;
+      float my_d = 0.f;
+      if (lane < n) {
+        const int gp = sorted_ids[base + lane];
+        if (kFused) {
+          my_d = Vec4<T>::to_float(depth[gp]);
+          my_row = (gp / dhw) * hw + gp % hw;   // pixel row: (b*N+n)*H*W + h*W + w
+        } else {
+          my_row = gp;
+        }
+      }
+      int j = 0;
+      for (; j + kUnroll <= n; j += kUnroll)
+        accum_batch<T, CPL, kFused, false>(acc, rows, my_row, my_d, j, n, lane, C, C4);
+      if (j < n) accum_batch<T, CPL, kFused, true>(acc, rows, my_row, my_d, j, n, lane, C, C4);
+    }
+    T *op = tile_out + (int64_t)c * C;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < C4) Vec4<T>::store(op + ch * 4, acc[k]);
+    }
+    if (lane == 0) c = atomicAdd(&s_next, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
   }
 }
 
@@ -180,114 +209,168 @@ pool_backward_kernel(const int32_t *__restrict__ cell_of_point, const T *__restr
 }
 
 // ---- backward of the fused op: pixel-centric, no atomics, no sort ----------------------
-// One CTA = kPixTile consecutive pixels of one camera image, one warp per pixel.  The warp
-// keeps its context row in registers and walks the D depth bins of its ray:
+// One warp owns one pixel (camera image bn, row h, column w) at a time and walks its ray:
 //   grad_depth[d, pix]  = <grad_out[cell(d, pix), :], context[pix, :]>
 //   grad_context[pix,:] = sum_d depth[d, pix] * grad_out[cell(d, pix), :]
-// depth / cell / grad_depth columns and the NCHW context rows are staged through shared
-// memory so that every global access is a full 32-byte sector.
-constexpr int kPixTile = 8;
+// The warps of a CTA are the rows h of the same image columns: all rows of a column project
+// to (nearly) the same BEV cells, so the CTA's warps gather the same gradient rows and all
+// but the first hit L1.  Depth bins are taken 32 at a time (lane = bin); dropped bins are
+// skipped; the 32 per-bin partial dot products are reduced with one lane-transposing butterfly
+// (31 shuffles per 32 bins instead of 5 per bin).
+constexpr int kBwdTileW = 4;     // image columns per CTA
+constexpr int kBwdMaxWarps = 8;  // image rows per CTA
+
+__device__ __forceinline__ float transpose_reduce32(float (&p)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = hi ? p[i] : p[i + w];
+      const float keep = hi ? p[i + w] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return p[0];   // lane l now holds the sum over lanes of the original p[l]
+}
+
 template <typename T, int CPL>
-__global__ void __launch_bounds__(kPixTile * 32)
+__global__ void __launch_bounds__(kBwdMaxWarps * 32)
 fused_backward_kernel(const int32_t *__restrict__ cell_of_point, const T *__restrict__ grad_nhwc,
                       const T *__restrict__ depth, const T *__restrict__ ctx_nchw,
                       T *__restrict__ grad_depth, T *__restrict__ grad_ctx_nchw, int num_cams, int D,
-                      int HW, int C, int64_t cells_per_sample) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t *s_cell = reinterpret_cast<int32_t *>(smem_raw);             // [D][kPixTile]
-  float *s_depth = reinterpret_cast<float *>(s_cell + D * kPixTile);   // [D][kPixTile]
-  float *s_gd = s_depth + D * kPixTile;                                // [D][kPixTile]
-  float *s_ctx = s_gd + D * kPixTile;                                  // [C][kPixTile] (in: ctx, out: grad)
-  const int bn = blockIdx.y;
-  const int hw0 = blockIdx.x * kPixTile;
-  const int npix = min(kPixTile, HW - hw0);
-  const int lane = threadIdx.x & 31, pix = threadIdx.x >> 5;
-  const int C4 = C >> 2;
-  const int64_t img_base = (int64_t)bn * D * HW;   // == first global point id of this image
-
-  for (int i = threadIdx.x; i < D * kPixTile; i += kPixTile * 32) {
-    const int d = i / kPixTile, j = i - d * kPixTile;
-    int cell = -1;
-    float dv = 0.f;
-    if (j < npix) {
-      const int64_t gp = img_base + (int64_t)d * HW + hw0 + j;
-      cell = cell_of_point[gp];
-      dv = Vec4<T>::to_float(depth[gp]);
-    }
-    s_cell[i] = cell;
-    s_depth[i] = dv;
-  }
-  for (int i = threadIdx.x; i < C * kPixTile; i += kPixTile * 32) {
-    const int c = i / kPixTile, j = i - c * kPixTile;
-    s_ctx[i] = j < npix ? Vec4<T>::to_float(ctx_nchw[((int64_t)bn * C + c) * HW + hw0 + j]) : 0.f;
-  }
-  __syncthreads();
-
-  float4 cx[CPL], gacc[CPL];
-#pragma unroll
-  for (int k = 0; k < CPL; ++k) {
-    const int ch = lane + 32 * k;
-    gacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    cx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ch < C4) {
-      cx[k].x = s_ctx[(ch * 4 + 0) * kPixTile + pix];
-      cx[k].y = s_ctx[(ch * 4 + 1) * kPixTile + pix];
-      cx[k].z = s_ctx[(ch * 4 + 2) * kPixTile + pix];
-      cx[k].w = s_ctx[(ch * 4 + 3) * kPixTile + pix];
-    }
-  }
+                      int H, int W, int C, int64_t cells_per_sample) {
+  const int lane = threadIdx.x & 31;
+  const int bn = blockIdx.z;
+  const int h = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (h >= H) return;
+  const int HW = H * W, C4 = C >> 2;
+  const int64_t img_base = (int64_t)bn * D * HW;   // first global point id of this image
   const T *gbase = grad_nhwc + (int64_t)(bn / num_cams) * cells_per_sample * C;
-  constexpr int U = 4;
-  for (int d0 = 0; d0 < D; d0 += U) {
-    float4 g[U][CPL];
-    int cell[U];
+  const int w_end = min(W, (int)(blockIdx.x + 1) * kBwdTileW);
+
+  for (int w = blockIdx.x * kBwdTileW; w < w_end; ++w) {
+    const int hw = h * W + w;
+    float4 cx[CPL], gacc[CPL];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      cell[u] = d0 + u < D ? s_cell[(d0 + u) * kPixTile + pix] : -1;
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const int ch = lane + 32 * k;
-        g[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cell[u] >= 0 && ch < C4) g[u][k] = Vec4<T>::load(gbase + (int64_t)cell[u] * C + ch * 4);
+    for (int k = 0; k < CPL; ++k) {
+      const int ch = lane + 32 * k;
+      gacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ch < C4) {
+        const T *cp = ctx_nchw + ((int64_t)bn * C + ch * 4) * HW + hw;
+        cx[k].x = Vec4<T>::to_float(__ldg(cp));
+        cx[k].y = Vec4<T>::to_float(__ldg(cp + HW));
+        cx[k].z = Vec4<T>::to_float(__ldg(cp + 2 * HW));
+        cx[k].w = Vec4<T>::to_float(__ldg(cp + 3 * HW));
       }
     }
+    for (int d0 = 0; d0 < D; d0 += 32) {
+      const int d = d0 + lane;
+      const int64_t gp = img_base + (int64_t)d * HW + hw;
+      int cell = -1;
+      float dv = 0.f;
+      if (d < D) {
+        cell = __ldg(cell_of_point + gp);
+        dv = Vec4<T>::to_float(__ldg(depth + gp));
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, cell >= 0);
+      float result = 0.f;
+      if (mask) {
+        float part[32];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (d0 + u < D) {
-        float dot = 0.f;
-        const float dv = s_depth[(d0 + u) * kPixTile + pix];
+        for (int i = 0; i < 32; ++i) part[i] = 0.f;
+        unsigned m = mask;
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) {
-          dot += g[u][k].x * cx[k].x + g[u][k].y * cx[k].y + g[u][k].z * cx[k].z + g[u][k].w * cx[k].w;
-          gacc[k].x += dv * g[u][k].x;
-          gacc[k].y += dv * g[u][k].y;
-          gacc[k].z += dv * g[u][k].z;
-          gacc[k].w += dv * g[u][k].w;
+        for (int j0 = 0; j0 < 32; j0 += 4) {
+          if (m == 0) break;
+          float4 g[4][CPL];
+          float dvu[4];
+          bool on[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            on[q] = m != 0;
+            const int u = on[q] ? __ffs(m) - 1 : 0;
+            m &= m - 1;
+            const int cu = __shfl_sync(0xffffffffu, cell, u);
+            dvu[q] = __shfl_sync(0xffffffffu, dv, u);
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) {
+              const int ch = lane + 32 * k;
+              g[q][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (on[q] && ch < C4) g[q][k] = Vec4<T>::load(gbase + (int64_t)cu * C + ch * 4);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (on[q]) {
+              float dot = 0.f;
+#pragma unroll
+              for (int k = 0; k < CPL; ++k) {
+                dot += g[q][k].x * cx[k].x + g[q][k].y * cx[k].y + g[q][k].z * cx[k].z + g[q][k].w * cx[k].w;
+                gacc[k].x += dvu[q] * g[q][k].x;
+                gacc[k].y += dvu[q] * g[q][k].y;
+                gacc[k].z += dvu[q] * g[q][k].z;
+                gacc[k].w += dvu[q] * g[q][k].w;
+              }
+              part[j0 + q] = dot;
+            }
+          }
         }
-        if (cell[u] >= 0) dot = warp_sum(dot);     // warp-uniform branch
-        if (lane == 0) s_gd[(d0 + u) * kPixTile + pix] = dot;
+        // lane r holds the dot product of the r-th kept bin; route it to the lane owning that bin
+        const float red = transpose_reduce32(part, lane);
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        result = __shfl_sync(0xffffffffu, red, rank);
+        if (cell < 0) result = 0.f;
+      }
+      if (d < D) grad_depth[gp] = Vec4<T>::from_float(result);
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < C4) {
+        T *cp = grad_ctx_nchw + ((int64_t)bn * C + ch * 4) * HW + hw;
+        cp[0] = Vec4<T>::from_float(gacc[k].x);
+        cp[HW] = Vec4<T>::from_float(gacc[k].y);
+        cp[2 * HW] = Vec4<T>::from_float(gacc[k].z);
+        cp[3 * HW] = Vec4<T>::from_float(gacc[k].w);
       }
     }
   }
-  __syncthreads();   // everyone is done reading s_ctx as input
-#pragma unroll
-  for (int k = 0; k < CPL; ++k) {
-    const int ch = lane + 32 * k;
-    if (ch < C4) {
-      s_ctx[(ch * 4 + 0) * kPixTile + pix] = gacc[k].x;
-      s_ctx[(ch * 4 + 1) * kPixTile + pix] = gacc[k].y;
-      s_ctx[(ch * 4 + 2) * kPixTile + pix] = gacc[k].z;
-      s_ctx[(ch * 4 + 3) * kPixTile + pix] = gacc[k].w;
-    }
+}
+
+// ---- gradient rows: NCHW grad_out -> (B, Y, X, C) rows, occupied cells only ---------------
+// The backward kernels only ever read the rows of cells that received at least one point, so
+// tiles of 32 cells with no kept point are skipped entirely (about 80 % of the aiMotive grid)
+// and inside a tile only occupied rows are written.  E = raw element type (uint32_t / uint16_t).
+template <typename E>
+__global__ void __launch_bounds__(256)
+grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ grad_nchw,
+                 E *__restrict__ rows, int64_t G, int C) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  E *tile = reinterpret_cast<E *>(smem_raw);   // [32][C + 1]
+  __shared__ unsigned s_occ;
+  const int b = blockIdx.y;
+  const int64_t cell0 = (int64_t)blockIdx.x * 32;
+  const int ncell = (int)min((int64_t)32, G - cell0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    const int64_t gc = (int64_t)b * G + cell0 + lane;
+    const bool occ = lane < ncell && cell_start[gc + 1] > cell_start[gc];
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) s_occ = m;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < D * kPixTile; i += kPixTile * 32) {
-    const int d = i / kPixTile, j = i - d * kPixTile;
-    if (j < npix) grad_depth[img_base + (int64_t)d * HW + hw0 + j] = Vec4<T>::from_float(s_gd[i]);
-  }
-  for (int i = threadIdx.x; i < C * kPixTile; i += kPixTile * 32) {
-    const int c = i / kPixTile, j = i - c * kPixTile;
-    if (j < npix) grad_ctx_nchw[((int64_t)bn * C + c) * HW + hw0 + j] = Vec4<T>::from_float(s_ctx[i]);
+  const unsigned occ = s_occ;
+  if (occ == 0) return;
+  const int ld = C + 1;
+  for (int c = warp; c < C; c += 8)
+    if (lane < ncell) tile[lane * ld + c] = grad_nchw[((int64_t)b * C + c) * G + cell0 + lane];
+  __syncthreads();
+  for (int j = warp; j < ncell; j += 8) {
+    if (!((occ >> j) & 1u)) continue;
+    E *rp = rows + ((int64_t)b * G + cell0 + j) * C;
+    for (int c = lane; c < C; c += 32) rp[c] = tile[j * ld + c];
   }
 }
 
@@ -316,8 +399,16 @@ transpose_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t R, int64
 template <typename T, bool kFused>
 static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *out,
                           int64_t total_cells, int C, int dhw, int hw, cudaStream_t s) {
-  const unsigned grid = (unsigned)ceil_div64(total_cells, kPoolWarps);
+  const unsigned grid = (unsigned)ceil_div64(total_cells, kFwdTile);
   const int C4 = C >> 2;
+  if constexpr (std::is_same<T, float>::value) {
+    if (g8_supported(C) && g8_enabled()) {
+      BEVPOOL_G8_DISPATCH(C, (pool_forward_g8_kernel<NV2, kFused><<<grid, kG8Threads, 0, s>>>(
+                                 pv.cell_start, pv.sorted_ids, rows, depth, out, total_cells, dhw, hw)));
+      BEVPOOL_LAUNCH_CHECK();
+      return BEVPOOL_OK;
+    }
+  }
   if (C4 <= 32)
     pool_forward_kernel<T, 1, kFused><<<grid, kPoolThreads, 0, s>>>(pv.cell_start, pv.sorted_ids, rows, depth, out, total_cells, C, dhw, hw);
   else if (C4 <= 64)
@@ -330,16 +421,13 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
 
 template <typename T, int CPL>
 static int launch_fused_backward_cpl(const PlanView &pv, const T *grad, const T *depth, const T *ctx,
-                                     T *gdepth, T *gctx, int batch, int N, int D, int HW, int C,
+                                     T *gdepth, T *gctx, int batch, int N, int D, int H, int W, int C,
                                      int64_t cells, cudaStream_t s) {
-  const size_t smem = (size_t)D * kPixTile * 12 + (size_t)C * kPixTile * 4;
-  if (smem > 48 * 1024) {
-    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_kernel<T, CPL>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
-  const dim3 grid((unsigned)ceil_div64(HW, kPixTile), (unsigned)(batch * N));
-  fused_backward_kernel<T, CPL><<<grid, kPixTile * 32, smem, s>>>(pv.cell_of_point, grad, depth, ctx,
-                                                                gdepth, gctx, N, D, HW, C, cells);
+  const int warps = H < kBwdMaxWarps ? H : kBwdMaxWarps;
+  if ((int64_t)batch * N > 65535 || ceil_div64(H, warps) > 65535) return BEVPOOL_E_RANGE;
+  const dim3 grid((unsigned)ceil_div64(W, kBwdTileW), (unsigned)ceil_div64(H, warps), (unsigned)(batch * N));
+  fused_backward_kernel<T, CPL><<<grid, warps * 32, 0, s>>>(pv.cell_of_point, grad, depth, ctx, gdepth, gctx,
+                                                          N, D, H, W, C, cells);
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -385,9 +473,20 @@ static int fused_backward_t(const void *plan, const void *grad, const void *dept
   const T *g = static_cast<const T *>(grad), *dp = static_cast<const T *>(depth), *cx = static_cast<const T *>(ctx);
   T *gd = static_cast<T *>(gdepth), *gc = static_cast<T *>(gctx);
   const int64_t cells = (int64_t)X * Y;
-  if (C4 <= 32) return launch_fused_backward_cpl<T, 1>(pv, g, dp, cx, gd, gc, B, N, D, H * W, C, cells, s);
-  if (C4 <= 64) return launch_fused_backward_cpl<T, 2>(pv, g, dp, cx, gd, gc, B, N, D, H * W, C, cells, s);
-  return launch_fused_backward_cpl<T, 4>(pv, g, dp, cx, gd, gc, B, N, D, H * W, C, cells, s);
+  if constexpr (std::is_same<T, float>::value) {
+    if (g8_supported(C) && g8_enabled()) {
+      const int warps = H < kG8BwdWarps ? H : kG8BwdWarps;
+      if ((int64_t)B * N > 65535 || ceil_div64(H, warps) > 65535) return BEVPOOL_E_RANGE;
+      const dim3 grid((unsigned)ceil_div64(W, kG8BwdTileW), (unsigned)ceil_div64(H, warps), (unsigned)(B * N));
+      BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2><<<grid, warps * 32, 0, s>>>(
+                                 pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells)));
+      BEVPOOL_LAUNCH_CHECK();
+      return BEVPOOL_OK;
+    }
+  }
+  if (C4 <= 32) return launch_fused_backward_cpl<T, 1>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
+  if (C4 <= 64) return launch_fused_backward_cpl<T, 2>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
+  return launch_fused_backward_cpl<T, 4>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
 }
 
 }  // namespace bevpool
@@ -452,6 +551,33 @@ extern "C" int bevpool_fused_backward(const void *plan, const void *grad_out_nhw
   if (!aligned16(grad_out_nhwc)) return BEVPOOL_E_ALIGN;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   BEVPOOL_DISPATCH_DTYPE(dtype, (fused_backward_t<T>(plan, grad_out_nhwc, depth, context_nchw, grad_depth, grad_context_nchw, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
+}
+
+extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nhwc, int dtype,
+                                 int batch, int64_t num_points, int channels, int X, int Y, void *stream) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan || !grad_out_nchw || !rows_nhwc || channels <= 0) return BEVPOOL_E_ARG;
+  if (batch > 65535) return BEVPOOL_E_RANGE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const PlanView pv = plan_view(plan, batch, num_points, X, Y);
+  const int64_t G = (int64_t)X * Y;
+  const dim3 grid((unsigned)ceil_div64(G, 32), (unsigned)batch);
+  if (dtype == BEVPOOL_F32) {
+    const size_t smem = (size_t)32 * (channels + 1) * 4;
+    if (smem > 48 * 1024)
+      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(grad_rows_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    grad_rows_kernel<uint32_t><<<grid, 256, smem, s>>>(pv.cell_start, static_cast<const uint32_t *>(grad_out_nchw),
+                                                      static_cast<uint32_t *>(rows_nhwc), G, channels);
+  } else if (dtype == BEVPOOL_F16 || dtype == BEVPOOL_BF16) {
+    const size_t smem = (size_t)32 * (channels + 1) * 2;
+    grad_rows_kernel<uint16_t><<<grid, 256, smem, s>>>(pv.cell_start, static_cast<const uint16_t *>(grad_out_nchw),
+                                                      static_cast<uint16_t *>(rows_nhwc), G, channels);
+  } else {
+    return BEVPOOL_E_DTYPE;
+  }
+  BEVPOOL_LAUNCH_CHECK();
+  return BEVPOOL_OK;
 }
 
 extern "C" int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t rows,

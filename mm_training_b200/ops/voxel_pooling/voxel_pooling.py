@@ -117,17 +117,23 @@ def _transpose(x: torch.Tensor, batch: int, rows: int, cols: int) -> torch.Tenso
     return out
 
 
-def _grad_rows_nhwc(grad_out: torch.Tensor) -> torch.Tensor:
+def _grad_rows_nhwc(grad_out: torch.Tensor, plan: PoolingPlan) -> torch.Tensor:
     """grad_out arrives as (B, C, Y, X) with arbitrary strides; the kernels want (B, Y, X, C) rows.
     Zero-copy when it already is a permuted NHWC buffer (what autograd hands back for the
-    permuted view we return), one tiled transpose when it is NCHW-contiguous."""
+    permuted view we return).  Otherwise one pass that transposes only the tiles holding an
+    occupied cell -- rows of empty cells are never read by the backward kernels and stay
+    uninitialised."""
     B, C, Y, X = grad_out.shape
     nhwc = grad_out.permute(0, 2, 3, 1)
     if nhwc.is_contiguous():
         return nhwc
     if not grad_out.is_contiguous():
         grad_out = grad_out.contiguous()
-    return _transpose(grad_out, B, C, Y * X).view(B, Y, X, C)
+    rows = torch.empty(B, Y, X, C, dtype=grad_out.dtype, device=grad_out.device)
+    _lib.check(_lib.lib().bevpool_grad_rows(plan.ptr, grad_out.data_ptr(), rows.data_ptr(),
+                                            _lib.dtype_code(grad_out), B, plan.num_points, C, X, Y,
+                                            _lib.stream_ptr(grad_out.device)), 'bevpool_grad_rows')
+    return rows
 
 
 def pool_forward(plan: PoolingPlan, input_features: torch.Tensor) -> torch.Tensor:
@@ -145,7 +151,7 @@ def pool_backward(plan: PoolingPlan, grad_output: torch.Tensor, input_shape) -> 
     """grad_output (B, C, Y, X), any strides -> grad_features in ``input_shape``."""
     X, Y, _ = plan.voxel_num
     B, C = grad_output.shape[0], grad_output.shape[1]
-    rows = _grad_rows_nhwc(grad_output)
+    rows = _grad_rows_nhwc(grad_output, plan)
     grad_in = torch.empty(input_shape, dtype=rows.dtype, device=rows.device)
     _lib.check(_lib.lib().bevpool_backward(plan.ptr, rows.data_ptr(), grad_in.data_ptr(),
                                            _lib.dtype_code(rows), B, plan.num_points, C, X, Y,
@@ -181,7 +187,7 @@ def fused_backward(plan: PoolingPlan, grad_output: torch.Tensor, depth: torch.Te
     X, Y, _ = plan.voxel_num
     B = plan.batch
     N = BN // B
-    rows = _grad_rows_nhwc(grad_output)
+    rows = _grad_rows_nhwc(grad_output, plan)
     context_nchw = context.contiguous()
     grad_depth = torch.empty_like(depth)
     grad_context = torch.empty_like(context_nchw)

@@ -17,6 +17,15 @@ from oracle import ref_cuda_op
 from oracle import voxel_pool_ref as vp
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=['g8', 'generic'])
+def kernel_path(request, monkeypatch):
+    """Every test runs twice: with the fp32 8-lanes-per-row fast path (default) and with the
+    generic float4-per-lane kernels forced (the library reads BEVPOOL_DISABLE_G8 per call)."""
+    monkeypatch.setenv('BEVPOOL_DISABLE_G8', '1' if request.param == 'generic' else '0')
+    return request.param
+
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 DEV = 'cuda'
 
