@@ -403,7 +403,8 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
   const int C4 = C >> 2;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
-      BEVPOOL_G8_DISPATCH(C, (pool_forward_g8_kernel<NV2, kFused><<<grid, kG8Threads, 0, s>>>(
+      const unsigned g8grid = (unsigned)ceil_div64(total_cells, kG8FwdCellsPerCta);
+      BEVPOOL_G8_DISPATCH(C, (pool_forward_g8_kernel<NV2, kFused><<<g8grid, kG8FwdWarps * 32, 0, s>>>(
                                  pv.cell_start, pv.sorted_ids, rows, depth, out, total_cells, dhw, hw)));
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;

@@ -13,8 +13,7 @@
 
 namespace bevpool {
 
-constexpr int kG8Threads = 256;
-constexpr int kG8Chunk = 1024;   // points of a tile staged in shared memory at a time
+constexpr int kG8Chunk = 256;   // points of a warp's 4 cells staged in shared memory at a time
 
 __device__ __forceinline__ float4 ld_stream_or_cached_f4(const char *p, bool stream) {
   return stream ? ldg_stream_f4(reinterpret_cast<const float4 *>(p)) : __ldg(reinterpret_cast<const float4 *>(p));
@@ -53,36 +52,44 @@ __device__ __forceinline__ int g8_channel(int r, int l8) {
 }
 
 // ---- forward ---------------------------------------------------------------------------------
-// CTA = 32 consecutive BEV cells (one 8-lane group per cell).  The tile's points are contiguous
-// in the plan's sorted list; the whole CTA stages (row index, depth) for up to kG8Chunk of
-// them in shared memory with coalesced / independent loads (2 dependent round trips per tile
-// instead of 3 per cell), then every group walks its own cell's interval.
+// Warp-autonomous: every warp owns 4 consecutive BEV cells (one 8-lane group per cell) and never
+// synchronises with the rest of its CTA, so the SM's warp scheduler hides the dependent
+// cell_start -> sorted ids -> depth -> context-row latencies across ~24 independent warps.
+// The 4 cells' points are contiguous in the plan's sorted list; the warp stages (row index,
+// depth) for up to kG8Chunk of them in its private shared-memory slice with coalesced loads,
+// then every group walks its own cell's interval in order.
+constexpr int kG8FwdWarps = 4;
+constexpr int kG8FwdCellsPerCta = 4 * kG8FwdWarps;
+
 template <int NV2, bool kFused>
-__global__ void __launch_bounds__(kG8Threads, 3)
+__global__ void __launch_bounds__(kG8FwdWarps * 32, 6)
 pool_forward_g8_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_ids,
                        const float *__restrict__ rows, const float *__restrict__ depth,
                        float *__restrict__ out, int64_t total_cells, int dhw, int hw) {
   constexpr int C = 16 * NV2, NREG = 2 * NV2, U = 4;
-  __shared__ int s_start[33];
-  __shared__ uint2 s_pts[kG8Chunk];
-  const int tid = threadIdx.x, lane = tid & 31, l8 = lane & 7, grp = tid >> 3;
-  const int64_t tile0 = (int64_t)blockIdx.x * 32;
-  const int ncell = (int)min((int64_t)32, total_cells - tile0);
-  if (tid <= ncell) s_start[tid] = cell_start[tile0 + tid];
-  __syncthreads();
-  const int tstart = s_start[0], tend = s_start[ncell];
+  __shared__ uint2 s_pts_all[kG8FwdWarps][kG8Chunk];
+  const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3, warp = threadIdx.x >> 5;
+  uint2 *s_pts = s_pts_all[warp];
+  const int64_t cell0 = ((int64_t)blockIdx.x * kG8FwdWarps + warp) * 4;
+  if (cell0 >= total_cells) return;
+  const int ncell = (int)min((int64_t)4, total_cells - cell0);
+  int cs = 0;
+  if (lane <= ncell) cs = __ldg(cell_start + cell0 + lane);
+  const int wstart = __shfl_sync(0xffffffffu, cs, 0), wend = __shfl_sync(0xffffffffu, cs, ncell);
   const bool mine = grp < ncell;
-  const int my_start = mine ? s_start[grp] : tend, my_end = mine ? s_start[grp + 1] : tend;
+  int my_start = __shfl_sync(0xffffffffu, cs, min(grp, ncell));
+  int my_end = __shfl_sync(0xffffffffu, cs, min(grp + 1, ncell));
+  if (!mine) my_start = my_end = wend;
 
   float acc[NREG];
 #pragma unroll
   for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
   const char *rows_b = reinterpret_cast<const char *>(rows);
 
-  for (int lo = tstart; lo < tend; lo += kG8Chunk) {
-    const int hi = min(lo + kG8Chunk, tend);
-    if (lo != tstart) __syncthreads();
-    for (int i = tid; i < hi - lo; i += kG8Threads) {
+  for (int lo = wstart; lo < wend; lo += kG8Chunk) {
+    const int hi = min(lo + kG8Chunk, wend);
+    if (lo != wstart) __syncwarp();
+    for (int i = lane; i < hi - lo; i += 32) {
       const int gp = __ldg(sorted_ids + lo + i);
       uint2 e;
       if (kFused) {
@@ -94,7 +101,7 @@ pool_forward_g8_kernel(const int32_t *__restrict__ cell_start, const int32_t *__
       }
       s_pts[i] = e;
     }
-    __syncthreads();
+    __syncwarp();
     const int a = max(my_start, lo), b = min(my_end, hi);
     int trips = max(b - a, 0);
     trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, 8));
@@ -123,7 +130,7 @@ pool_forward_g8_kernel(const int32_t *__restrict__ cell_start, const int32_t *__
       }
     }
   }
-  if (mine) g8_store_row<NV2>(reinterpret_cast<char *>(out + (tile0 + grp) * C), l8, acc);
+  if (mine) g8_store_row<NV2>(reinterpret_cast<char *>(out + (cell0 + grp) * C), l8, acc);
 }
 
 // ---- fused backward ---------------------------------------------------------------------------
