@@ -102,6 +102,47 @@ int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nh
 int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t rows,
                       int64_t cols, void *stream);
 
+/* ==== LiDAR / radar branch ==========================================================
+ * Replaces what the reference reaches through models/bev_depth.py:181-183:
+ *   mmcv `hard_voxelize_forward` (via mmdet3d `MVXTwoStageDetector.voxelize`), mmdet3d
+ *   `HardSimpleVFE`, and the scatter-to-dense step of `PointPillarsScatter` /
+ *   `SparseConvTensor.dense()`.  Semantics: SURVEY.md Appendix A (mmcv-full 1.7.0).
+ *
+ * bevvox_hard_voxelize -- a whole batch in one call.
+ *   points          (total_points, F) float32, the samples' clouds concatenated in order
+ *   sample_offsets  device int32[batch + 1], row offsets of each sample in `points`
+ *   max_sample_points  largest per-sample point count (host value, sizes the launch)
+ *   voxel_size_host[3], range_host[6] = [xmin,ymin,zmin,xmax,ymax,zmax], grid_host[3] = [gx,gy,gz]
+ *   outputs are packed like mmdet3d's concatenation: rows of sample b start at voxel_base[b]
+ *     voxels     (batch*max_voxels, max_points, F) float32   rows >= voxel_base[batch] untouched
+ *     coors      (batch*max_voxels, 4) int32 [b, z, y, x]
+ *     num_points (batch*max_voxels) int32
+ *     voxel_base device int32[batch + 1] (written): row offsets; [batch] = total voxel count M
+ *     voxel_mean optional (batch*max_voxels, mean_features) float32 = HardSimpleVFE, or NULL
+ *   temp: bevvox_temp_bytes() bytes of scratch.                                          */
+int bevvox_temp_bytes(int batch, int64_t total_points, int max_voxels, int max_points,
+                      size_t *temp_bytes);
+int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int batch,
+                         int64_t total_points, int64_t max_sample_points, int num_features,
+                         const float *voxel_size_host, const float *range_host,
+                         const int *grid_host, int max_points, int max_voxels, float *voxels,
+                         int32_t *coors, int32_t *num_points, int32_t *voxel_base,
+                         float *voxel_mean, int mean_features, void *temp, void *stream);
+/* mmcv dynamic voxelization: coors (num_points, 3) int32 [z, y, x], -1 for out-of-range points */
+int bevvox_dynamic_voxelize(const float *points, int64_t num_points, int num_features,
+                            const float *voxel_size_host, const float *range_host,
+                            const int *grid_host, int32_t *coors, void *stream);
+
+/* pillar scatter: voxel_features (M, C), coors (M, 4) [b, z, y, x] -> canvas (B, C, nz, ny, nx)
+ * (== (B, C*nz, ny, nx)); every canvas element is written exactly once (no pre-zeroing).
+ * index_map: scratch int32 (B*nz*ny*nx).  backward = gather of grad_canvas at coors.        */
+int pillar_scatter_forward(const void *voxel_features, const int32_t *coors, int64_t num_voxels,
+                           int channels, int dtype, int batch, int nz, int ny, int nx,
+                           void *canvas, int32_t *index_map, void *stream);
+int pillar_scatter_backward(const void *grad_canvas, const int32_t *coors, int64_t num_voxels,
+                            int channels, int dtype, int batch, int nz, int ny, int nx,
+                            void *grad_voxel_features, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

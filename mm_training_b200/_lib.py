@@ -24,6 +24,8 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _szp = ctypes.POINTER(ctypes.c_size_t)
+_fp = ctypes.POINTER(ctypes.c_float)
+_ip = ctypes.POINTER(ctypes.c_int)
 
 # name -> argtypes; every function returns int (0 = ok) except the two noted below
 _SIGNATURES = {
@@ -37,6 +39,11 @@ _SIGNATURES = {
     'bevpool_fused_backward': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     'bevpool_grad_rows': [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _vp],
     'bevpool_transpose': [_vp, _vp, _i, _i, _i64, _i64, _vp],
+    'bevvox_temp_bytes': [_i, _i64, _i, _i, _szp],
+    'bevvox_hard_voxelize': [_vp, _vp, _i, _i64, _i64, _i, _fp, _fp, _ip, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
+    'bevvox_dynamic_voxelize': [_vp, _i64, _i, _fp, _fp, _ip, _vp, _vp],
+    'pillar_scatter_forward': [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    'pillar_scatter_backward': [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
 EXPORTED_SYMBOLS = ['bevpool_abi_version', 'bevpool_error_string', 'bevpool_launch_count', *_SIGNATURES]
 

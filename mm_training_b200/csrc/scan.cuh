@@ -29,7 +29,7 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned 
 constexpr unsigned long long kScanAggregate = 1ull << 32;
 constexpr unsigned long long kScanPrefix = 2ull << 32;
 
-__global__ void __launch_bounds__(kScanThreads)
+static __global__ void __launch_bounds__(kScanThreads)
 scan_exclusive_kernel(const uint32_t *in, uint32_t *out, int64_t n,
                       unsigned long long *status /* [tiles] then ticket */) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
@@ -126,7 +126,7 @@ scan_exclusive_kernel(const uint32_t *in, uint32_t *out, int64_t n,
 }
 
 // `workspace` must be zeroed (scan_workspace_bytes(n)); in/out 16-byte aligned; in == out allowed.
-inline int launch_scan_exclusive(const uint32_t *in, uint32_t *out, int64_t n, void *workspace,
+static inline int launch_scan_exclusive(const uint32_t *in, uint32_t *out, int64_t n, void *workspace,
                                  cudaStream_t stream) {
   if (n <= 0) return BEVPOOL_OK;
   const int64_t tiles = scan_num_tiles(n);
