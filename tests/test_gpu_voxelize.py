@@ -147,7 +147,7 @@ def test_pillar_scatter_forward_backward(dtype, nz, C):
     canvas = pillar_scatter(f, torch.from_numpy(coors).to(DEV), B, (nz, ny, nx))
     ref = vz.pillar_scatter_ref(feats.float().numpy(), coors, B, (nz, ny, nx))
     assert canvas.shape == (B, C * nz, ny, nx) and canvas.dtype == dtype
-    assert np.array_equal(canvas.float().cpu().numpy(), ref)                        # a copy: exact in any dtype
+    assert np.array_equal(canvas.detach().float().cpu().numpy(), ref)                        # a copy: exact in any dtype
     g = torch.randn(B, C * nz, ny, nx).to(dtype)
     canvas.backward(g.to(DEV))
     gref = vz.pillar_scatter_backward_ref(g.float().numpy(), coors, (nz, ny, nx))
