@@ -42,6 +42,22 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ int4 ldg_stream_i4(const int4 *p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ldg_stream_i32(const int *p) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ldg_stream_f32(const float *p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
 // reused read: gathers that hit L1/L2 (context rows, gradient rows)
 __device__ __forceinline__ float4 ldg_f4(const float4 *p) { return __ldg(p); }
 // streaming store: outputs written exactly once

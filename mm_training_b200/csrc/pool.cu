@@ -404,8 +404,9 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
       const unsigned g8grid = (unsigned)ceil_div64(total_cells, kG8FwdCellsPerCta);
+      const FastDiv fd_dhw = make_fastdiv((uint32_t)dhw), fd_hw = make_fastdiv((uint32_t)hw);
       BEVPOOL_G8_DISPATCH(C, (pool_forward_g8_kernel<NV2, kFused><<<g8grid, kG8FwdWarps * 32, 0, s>>>(
-                                 pv.cell_start, pv.sorted_ids, rows, depth, out, total_cells, dhw, hw)));
+                                 pv.cell_start, pv.sorted_ids, rows, depth, out, total_cells, fd_dhw, fd_hw, C)));
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
@@ -476,11 +477,17 @@ static int fused_backward_t(const void *plan, const void *grad, const void *dept
   const int64_t cells = (int64_t)X * Y;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
-      const int warps = H < kG8BwdWarps ? H : kG8BwdWarps;
-      if ((int64_t)B * N > 65535 || ceil_div64(H, warps) > 65535) return BEVPOOL_E_RANGE;
-      const dim3 grid((unsigned)ceil_div64(W, kG8BwdTileW), (unsigned)ceil_div64(H, warps), (unsigned)(B * N));
-      BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2><<<grid, warps * 32, 0, s>>>(
-                                 pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells)));
+      const int64_t tiles_h = ceil_div64(H, 4 * kBwHG), tiles_w = ceil_div64(W, kBwTW);
+      const int64_t ctas = (int64_t)B * N * tiles_h * tiles_w;
+      if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
+      const bool vec = (W % 4 == 0) && aligned16(dp) && aligned16(gd);
+      if (vec) {
+        BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, kBwHG, true><<<(unsigned)ctas, 128 * kBwHG, 0, s>>>(
+                                   pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w)));
+      } else {
+        BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, kBwHG, false><<<(unsigned)ctas, 128 * kBwHG, 0, s>>>(
+                                   pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w)));
+      }
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
