@@ -68,11 +68,14 @@ int bevpool_plan_views(const void *plan, int batch, int64_t num_points, int num_
 /* ---- drop-in op: voxel_pooling(geom_xyz, input_features, voxel_num) --------------
  * forward  (voxel_pooling.py:10-55 + .cu:9-36): features (B, Np, C) -> out (B, Y, X, C),
  *          every cell written exactly once (no pre-zeroing needed), deterministic.
+ *          `workspace`: bevpool_forward_workspace_bytes() bytes of scratch (partial sums of
+ *          cells cut by the even-share partition of the point list); contents are don't-care.
  * backward (voxel_pooling.py:58-69): grad_out given as (B, Y, X, C) rows ->
  *          grad_features (B, Np, C), dropped points get zeros.                      */
+int bevpool_forward_workspace_bytes(int channels, size_t *bytes);   /* for both forward entry points */
 int bevpool_forward(const void *plan, const void *features, void *out_nhwc, int dtype,
                     int batch, int64_t num_points, int channels, int num_voxel_x,
-                    int num_voxel_y, void *stream);
+                    int num_voxel_y, void *workspace, void *stream);
 int bevpool_backward(const void *plan, const void *grad_out_nhwc, void *grad_features,
                      int dtype, int batch, int64_t num_points, int channels,
                      int num_voxel_x, int num_voxel_y, void *stream);
@@ -84,7 +87,7 @@ int bevpool_backward(const void *plan, const void *grad_out_nhwc, void *grad_fea
 int bevpool_fused_forward(const void *plan, const void *depth, const void *context_nhwc,
                           void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
                           int feat_h, int feat_w, int channels, int num_voxel_x,
-                          int num_voxel_y, void *stream);
+                          int num_voxel_y, void *workspace, void *stream);
 int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const void *depth,
                            const void *context_nchw, void *grad_depth, void *grad_context_nchw,
                            int dtype, int batch, int num_cams, int depth_bins, int feat_h,

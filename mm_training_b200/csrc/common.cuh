@@ -75,8 +75,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---- plan layout -------------------------------------------------------------------
 // A plan is one caller-owned buffer:
 //   header (256 B) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
+//   | sorted_cells int32[B*Np]
+// sorted_ids[k] is the global point id of the k-th kept point in (cell, point id) order and
+// sorted_cells[k] its global output row b*G + cell; only the first K = cell_start[B*G] entries
+// of both are defined.
 struct PlanLayout {
-  size_t off_cell_of_point, off_cell_start, off_sorted_ids, bytes;
+  size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, bytes;
 };
 struct PlanHeader {       // written by the device at build time
   int32_t magic, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
@@ -93,19 +97,21 @@ __host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points,
   L.off_cell_of_point = o; o = align_up(o + P * 4, 256);
   L.off_cell_start = o;    o = align_up(o + (G + 1) * 4, 256);
   L.off_sorted_ids = o;    o = align_up(o + P * 4, 256);
+  L.off_sorted_cells = o;  o = align_up(o + P * 4 + 64, 256);   // + slack: readers prefetch a batch past K
   L.bytes = o;
   return L;
 }
 
 struct PlanView {
-  const int32_t *cell_of_point, *cell_start, *sorted_ids;
+  const int32_t *cell_of_point, *cell_start, *sorted_ids, *sorted_cells;
 };
 inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X, int Y) {
   PlanLayout L = plan_layout(batch, num_points, X, Y);
   const char *b = static_cast<const char *>(plan);
   return PlanView{reinterpret_cast<const int32_t *>(b + L.off_cell_of_point),
                   reinterpret_cast<const int32_t *>(b + L.off_cell_start),
-                  reinterpret_cast<const int32_t *>(b + L.off_sorted_ids)};
+                  reinterpret_cast<const int32_t *>(b + L.off_sorted_ids),
+                  reinterpret_cast<const int32_t *>(b + L.off_sorted_cells)};
 }
 
 inline int check_plan_dims(int batch, int64_t num_points, int X, int Y) {

@@ -150,6 +150,7 @@ template <bool kFirst>
 __global__ void __launch_bounds__(kSortThreads)
 sort_scatter_kernel(const int32_t *__restrict__ in_keys, const int32_t *__restrict__ in_ids,
                     int32_t *__restrict__ out_keys, int32_t *__restrict__ out_ids,
+                    int32_t *__restrict__ out_rows, int32_t cells_per_sample,
                     const uint32_t *__restrict__ scanned, const uint32_t *__restrict__ scanned0,
                     int bins0, int64_t num_points, int shift, int bins, int tiles_per_sample) {
   extern __shared__ uint32_t s_cnt[];  // [kSortWarps][bins]
@@ -213,6 +214,7 @@ sort_scatter_kernel(const int32_t *__restrict__ in_keys, const int32_t *__restri
       const uint32_t pos = cnt[digit] + rank[r];
       out_ids[pos] = id[r];
       if (out_keys) out_keys[pos] = key[r];
+      if (out_rows) out_rows[pos] = b * cells_per_sample + key[r];   // last pass: global output row
     }
   }
 }
@@ -262,6 +264,7 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
   int32_t *cell_of_point = reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point);
   uint32_t *cell_start = reinterpret_cast<uint32_t *>(pb + PL.off_cell_start);
   int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
+  int32_t *sorted_cells = reinterpret_cast<int32_t *>(pb + PL.off_sorted_cells);
   uint32_t *hist[kMaxPasses];
   for (int p = 0; p < sc.npass; ++p) hist[p] = reinterpret_cast<uint32_t *>(tb + TL.off_hist[p]);
   int32_t *keys[2] = {reinterpret_cast<int32_t *>(tb + TL.off_keys[0]),
@@ -284,8 +287,8 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
   {
     const bool last = sc.npass == 1;
     sort_scatter_kernel<true><<<grid, kSortThreads, kSortWarps * bins0 * 4, stream>>>(
-        cell_of_point, nullptr, last ? nullptr : keys[0], last ? sorted_ids : ids[0], hist[0],
-        hist[0], bins0, num_points, sc.shift[0], bins0, T);
+        cell_of_point, nullptr, last ? nullptr : keys[0], last ? sorted_ids : ids[0],
+        last ? sorted_cells : nullptr, (int32_t)cells, hist[0], hist[0], bins0, num_points, sc.shift[0], bins0, T);
     BEVPOOL_LAUNCH_CHECK();
   }
   for (int p = 1; p < sc.npass; ++p) {
@@ -298,8 +301,8 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
     rc = launch_scan_exclusive(hist[p], hist[p], TL.hist_n[p], tb + TL.off_scan[p], stream);
     if (rc) return rc;
     sort_scatter_kernel<false><<<grid, kSortThreads, kSortWarps * bins * 4, stream>>>(
-        keys[src], ids[src], last ? nullptr : keys[dst], last ? sorted_ids : ids[dst], hist[p],
-        hist[0], bins0, num_points, sc.shift[p], bins, T);
+        keys[src], ids[src], last ? nullptr : keys[dst], last ? sorted_ids : ids[dst],
+        last ? sorted_cells : nullptr, (int32_t)cells, hist[p], hist[0], bins0, num_points, sc.shift[p], bins, T);
     BEVPOOL_LAUNCH_CHECK();
   }
   rc = launch_scan_exclusive(cell_start, cell_start, (int64_t)batch * cells + 1,

@@ -19,6 +19,11 @@
 
 namespace bevpool {
 
+static int env_int(const char *name, int dflt) {   // tuning knobs for experiments
+  const char *e = std::getenv(name);
+  return e && e[0] ? std::atoi(e) : dflt;
+}
+
 // BEVPOOL_DISABLE_G8=1 forces the generic float4-per-lane kernels (used by the tests to cover both paths)
 static bool g8_enabled() {
   const char *e = std::getenv("BEVPOOL_DISABLE_G8");
@@ -396,17 +401,52 @@ transpose_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t R, int64
 }
 
 // ---- launchers ----------------------------------------------------------------------------
+static int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = kSMs;
+  }
+  return cached;
+}
+static size_t forward_workspace_bytes(int C) {
+  // head + tail partial rows of every slice of the largest grid the forward may launch
+  return (size_t)2 * 4 * kFwWarpsPerCta * kFwMaxCtasPerSm * sm_count() * (size_t)C * sizeof(float);
+}
+
 template <typename T, bool kFused>
-static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *out,
+static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *out, void *workspace,
                           int64_t total_cells, int C, int dhw, int hw, cudaStream_t s) {
   const unsigned grid = (unsigned)ceil_div64(total_cells, kFwdTile);
   const int C4 = C >> 2;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
-      const unsigned g8grid = (unsigned)ceil_div64(total_cells, kG8FwdCellsPerCta);
+      if (!workspace) return BEVPOOL_E_ARG;
+      if (!aligned16(workspace)) return BEVPOOL_E_ALIGN;
       const FastDiv fd_dhw = make_fastdiv((uint32_t)dhw), fd_hw = make_fastdiv((uint32_t)hw);
-      BEVPOOL_G8_DISPATCH(C, (pool_forward_g8_kernel<NV2, kFused><<<g8grid, kG8FwdWarps * 32, 0, s>>>(
-                                 pv.cell_start, pv.sorted_ids, rows, depth, out, total_cells, fd_dhw, fd_hw, C)));
+      int cps = env_int("BEVPOOL_FW_CPS", 5);
+      cps = cps < 1 ? 1 : (cps > kFwMaxCtasPerSm ? kFwMaxCtasPerSm : cps);
+      const int u = env_int("BEVPOOL_FW_U", 4);
+      const unsigned ctas = (unsigned)(sm_count() * cps);
+      const int slices = (int)ctas * kFwWarpsPerCta * 4;
+      float *ws_head = static_cast<float *>(workspace);
+      float *ws_tail = ws_head + (size_t)slices * C;
+      if (u == 2) {
+        BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 2><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
+                                   pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
+                                   total_cells, fd_dhw, fd_hw)));
+      } else {
+        BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 4><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
+                                   pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
+                                   total_cells, fd_dhw, fd_hw)));
+      }
+      BEVPOOL_LAUNCH_CHECK();
+      BEVPOOL_G8_DISPATCH(C, (pool_forward_fixup_kernel<NV2><<<(unsigned)ceil_div64((int64_t)slices * 8, 128), 128, 0, s>>>(
+                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, total_cells, slices)));
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
@@ -440,10 +480,10 @@ static int check_channels(int C) {
 }
 
 template <typename T>
-static int forward_t(const void *plan, const void *feats, void *out, int B, int64_t Np, int C, int X,
+static int forward_t(const void *plan, const void *feats, void *out, void *ws, int B, int64_t Np, int C, int X,
                      int Y, cudaStream_t s) {
   const PlanView pv = plan_view(plan, B, Np, X, Y);
-  return launch_forward<T, false>(pv, static_cast<const T *>(feats), nullptr, static_cast<T *>(out),
+  return launch_forward<T, false>(pv, static_cast<const T *>(feats), nullptr, static_cast<T *>(out), ws,
                                   (int64_t)B * X * Y, C, 1, 1, s);
 }
 template <typename T>
@@ -458,12 +498,12 @@ static int backward_t(const void *plan, const void *grad, void *gfeats, int B, i
   return BEVPOOL_OK;
 }
 template <typename T>
-static int fused_forward_t(const void *plan, const void *depth, const void *ctx, void *out, int B, int N,
+static int fused_forward_t(const void *plan, const void *depth, const void *ctx, void *out, void *ws, int B, int N,
                            int D, int H, int W, int C, int X, int Y, cudaStream_t s) {
   const int64_t Np = (int64_t)N * D * H * W;
   const PlanView pv = plan_view(plan, B, Np, X, Y);
   return launch_forward<T, true>(pv, static_cast<const T *>(ctx), static_cast<const T *>(depth),
-                                 static_cast<T *>(out), (int64_t)B * X * Y, C, D * H * W, H * W, s);
+                                 static_cast<T *>(out), ws, (int64_t)B * X * Y, C, D * H * W, H * W, s);
 }
 template <typename T>
 static int fused_backward_t(const void *plan, const void *grad, const void *depth, const void *ctx,
@@ -477,17 +517,21 @@ static int fused_backward_t(const void *plan, const void *grad, const void *dept
   const int64_t cells = (int64_t)X * Y;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
-      const int64_t tiles_h = ceil_div64(H, 4 * kBwHG), tiles_w = ceil_div64(W, kBwTW);
+      const int hg = env_int("BEVPOOL_BW_HG", 2) == 1 ? 1 : 2;
+      const int64_t tiles_h = ceil_div64(H, 4 * hg), tiles_w = ceil_div64(W, kBwTW);
       const int64_t ctas = (int64_t)B * N * tiles_h * tiles_w;
       if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
       const bool vec = (W % 4 == 0) && aligned16(dp) && aligned16(gd);
-      if (vec) {
-        BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, kBwHG, true><<<(unsigned)ctas, 128 * kBwHG, 0, s>>>(
-                                   pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w)));
-      } else {
-        BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, kBwHG, false><<<(unsigned)ctas, 128 * kBwHG, 0, s>>>(
-                                   pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w)));
-      }
+#define BEVPOOL_BW_LAUNCH(HG, VEC, U)                                                                      \
+  BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, HG, VEC, U><<<(unsigned)ctas, 128 * HG, 0, s>>>(   \
+                             pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w)))
+      const int bu = env_int("BEVPOOL_BW_U", 2);
+      if (!vec) { if (hg == 1) { BEVPOOL_BW_LAUNCH(1, false, 2); } else { BEVPOOL_BW_LAUNCH(2, false, 2); } }
+      else if (hg == 1 && bu == 4) { BEVPOOL_BW_LAUNCH(1, true, 4); }
+      else if (hg == 1) { BEVPOOL_BW_LAUNCH(1, true, 2); }
+      else if (bu == 4) { BEVPOOL_BW_LAUNCH(2, true, 4); }
+      else { BEVPOOL_BW_LAUNCH(2, true, 2); }
+#undef BEVPOOL_BW_LAUNCH
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
@@ -509,15 +553,22 @@ using namespace bevpool;
     default: return BEVPOOL_E_DTYPE;                               \
   }
 
+extern "C" int bevpool_forward_workspace_bytes(int channels, size_t *bytes) {
+  if (!bytes || channels <= 0) return BEVPOOL_E_ARG;
+  *bytes = forward_workspace_bytes(channels);
+  return BEVPOOL_OK;
+}
+
 extern "C" int bevpool_forward(const void *plan, const void *features, void *out_nhwc, int dtype,
-                               int batch, int64_t num_points, int channels, int X, int Y, void *stream) {
+                               int batch, int64_t num_points, int channels, int X, int Y, void *workspace,
+                               void *stream) {
   int rc = check_plan_dims(batch, num_points, X, Y);
   if (rc) return rc;
   if ((rc = check_channels(channels))) return rc;
   if (!plan || !features || !out_nhwc) return BEVPOOL_E_ARG;
   if (!aligned16(features) || !aligned16(out_nhwc)) return BEVPOOL_E_ALIGN;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  BEVPOOL_DISPATCH_DTYPE(dtype, (forward_t<T>(plan, features, out_nhwc, batch, num_points, channels, X, Y, s)));
+  BEVPOOL_DISPATCH_DTYPE(dtype, (forward_t<T>(plan, features, out_nhwc, workspace, batch, num_points, channels, X, Y, s)));
 }
 
 extern "C" int bevpool_backward(const void *plan, const void *grad_out_nhwc, void *grad_features,
@@ -534,7 +585,8 @@ extern "C" int bevpool_backward(const void *plan, const void *grad_out_nhwc, voi
 
 extern "C" int bevpool_fused_forward(const void *plan, const void *depth, const void *context_nhwc,
                                      void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
-                                     int feat_h, int feat_w, int channels, int X, int Y, void *stream) {
+                                     int feat_h, int feat_w, int channels, int X, int Y, void *workspace,
+                                     void *stream) {
   if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
   const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
   int rc = check_plan_dims(batch, np, X, Y);
@@ -543,7 +595,7 @@ extern "C" int bevpool_fused_forward(const void *plan, const void *depth, const 
   if (!plan || !depth || !context_nhwc || !out_nhwc) return BEVPOOL_E_ARG;
   if (!aligned16(context_nhwc) || !aligned16(out_nhwc)) return BEVPOOL_E_ALIGN;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  BEVPOOL_DISPATCH_DTYPE(dtype, (fused_forward_t<T>(plan, depth, context_nhwc, out_nhwc, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
+  BEVPOOL_DISPATCH_DTYPE(dtype, (fused_forward_t<T>(plan, depth, context_nhwc, out_nhwc, workspace, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
 }
 
 extern "C" int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const void *depth,

@@ -18,6 +18,18 @@ __device__ __forceinline__ float4 ld_stream_or_cached_f4(const char *p, bool str
   return stream ? ldg_stream_f4(reinterpret_cast<const float4 *>(p)) : __ldg(reinterpret_cast<const float4 *>(p));
 }
 
+// Row addressing: base pointer made opaque to the optimiser (otherwise it folds the per-sample
+// offset back into every row address as a 64-bit multiply chain) + one IMAD.WIDE.U32 per row.
+__device__ __forceinline__ const char *opaque_ptr(const void *p) {
+  unsigned long long v = reinterpret_cast<unsigned long long>(p);
+  asm volatile("" : "+l"(v));
+  return reinterpret_cast<const char *>(v);
+}
+template <int kRowBytes>
+__device__ __forceinline__ const char *row_ptr(const char *base, unsigned row) {
+  return base + (unsigned long long)row * (unsigned)kRowBytes;
+}
+
 // loads the NREG floats of one row for lane l8; `row` points at the row's first byte
 template <int NV2, bool kStream>
 __device__ __forceinline__ void g8_load_row(const char *row, int l8, float (&v)[2 * NV2]) {
@@ -50,22 +62,26 @@ __device__ __forceinline__ int g8_channel(int r, int l8) {
   return r < 4 * NF4 ? 32 * (r >> 2) + 4 * l8 + (r & 3) : 32 * NF4 + 2 * l8 + (r - 4 * NF4);
 }
 
-// ---- forward ---------------------------------------------------------------------------------
-// Warp-autonomous: every warp owns 32 consecutive BEV cells and never synchronises with the rest
-// of its CTA, so the SM's warp scheduler hides the dependent cell_start -> sorted ids -> depth ->
-// context-row latencies across independent warps.
-//  * empty cells are zero-filled with coalesced 16-byte stores (every output element is written
-//    exactly once, no memset);
-//  * the points of the 32 cells are contiguous in the plan's sorted list; the range is cut into 4
-//    equal slices (point granularity, NOT cell granularity: near-camera cells hold 100x the median)
-//    and each 8-lane group reduces one slice, 8 list entries per batch (ids + depth prefetched one
-//    batch ahead, 4 context rows in flight);
-//  * a cell that straddles a slice boundary is finished by a fixed-order in-warp fix-up
-//    (head partial of slice g+1 added to the open tail of slice g), so the result is a pure
-//    function of the plan: bit-stable run to run.
-constexpr int kG8FwdWarps = 4;
-constexpr int kG8FwdCellsPerWarp = 32;
-constexpr int kG8FwdCellsPerCta = kG8FwdCellsPerWarp * kG8FwdWarps;
+// ---- packed fp32 math (Blackwell FFMA2 / FADD2: two fp32 lanes per instruction) ---------------
+template <int NREG>
+__device__ __forceinline__ void axpy_row(float (&acc)[NREG], float a, const float (&v)[NREG]) {
+  const float2 a2 = make_float2(a, a);
+#pragma unroll
+  for (int r = 0; r < NREG; r += 2) {
+    const float2 t = __ffma2_rn(a2, make_float2(v[r], v[r + 1]), make_float2(acc[r], acc[r + 1]));
+    acc[r] = t.x;
+    acc[r + 1] = t.y;
+  }
+}
+template <int NREG>
+__device__ __forceinline__ void add_row(float (&acc)[NREG], const float (&v)[NREG]) {
+#pragma unroll
+  for (int r = 0; r < NREG; r += 2) {
+    const float2 t = __fadd2_rn(make_float2(acc[r], acc[r + 1]), make_float2(v[r], v[r + 1]));
+    acc[r] = t.x;
+    acc[r + 1] = t.y;
+  }
+}
 
 struct FastDiv {          // exact n / d for 0 <= n < 2^31 (round-up magic, 64-bit product)
   uint32_t mul, shift, div;
@@ -83,62 +99,75 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
   return (uint32_t)(((uint64_t)n * f.mul) >> f.shift);
 }
 
-template <int NV2, bool kFused>
-__global__ void __launch_bounds__(kG8FwdWarps * 32)
-pool_forward_g8_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_ids,
-                       const float *__restrict__ rows, const float *__restrict__ depth,
-                       float *__restrict__ out, int64_t total_cells, FastDiv div_dhw, FastDiv div_hw,
-                       int row_pitch) {
-  constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4, U = 4;
-  constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3, warp = threadIdx.x >> 5;
-  const int64_t cell0 = ((int64_t)blockIdx.x * kG8FwdWarps + warp) * kG8FwdCellsPerWarp;
-  if (cell0 >= total_cells) return;
-  const int ncell = (int)min((int64_t)kG8FwdCellsPerWarp, total_cells - cell0);
-  const int cs = __ldg(cell_start + cell0 + min(lane, ncell));
-  const int ce = __ldg(cell_start + cell0 + min(lane + 1, ncell));
-  const unsigned occ = __ballot_sync(kFull, ce > cs);
-  float *out_w = out + cell0 * C;
-  {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int i = lane; i < ncell * C4; i += 32)
-      if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(reinterpret_cast<float4 *>(out_w) + i, z);
-  }
-  if (occ == 0u) return;
-  const int wstart = __shfl_sync(kFull, cs, 0), wend = __shfl_sync(kFull, ce, 31);
-  const int n = wend - wstart;
+// ---- forward: even-share segmented reduction over the plan's sorted point list ----------------
+// The K kept points, sorted by (cell, point id), are cut into S equal slices (S = 4 x the number
+// of warps of a grid that is exactly resident: no scheduling rounds, no tail, and near-camera
+// cells that hold 100x the median cannot unbalance anything).  An 8-lane group walks one slice,
+// 8 list entries per batch: point id and output row are prefetched two batches ahead, the depth
+// gather (whose address needs the id) one batch ahead, 4 context rows are in flight per group.
+// A cell whose points all lie inside the slice is stored directly; the partial sums of the (at
+// most two) cells cut by the slice's ends go to a workspace and are combined, in slice order,
+// by pool_forward_fixup_kernel.  The partition is a pure function of the plan, so the result is
+// bit-stable run to run.  Empty cells are zero-filled by the same warps (even share of the grid,
+// coalesced 16-byte stores): every output element is written exactly once, no memset.
+constexpr int kFwWarpsPerCta = 4;
+constexpr int kFwMaxCtasPerSm = 8;
 
-  // my slice of the warp's point range, and the cell its first point belongs to
-  int lo = wstart, hi = wstart, cur = 0;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int glo = wstart + (int)(((int64_t)n * g) >> 2);
-    const unsigned m = __ballot_sync(kFull, ce > cs && cs <= glo && glo < ce);
-    if (g == grp) {
-      lo = glo;
-      hi = wstart + (int)(((int64_t)n * (g + 1)) >> 2);
-      cur = m ? __ffs(m) - 1 : 31;
+__host__ __device__ __forceinline__ int fwd_slice_len(int K, int num_slices) {
+  int L = (int)(((int64_t)K + num_slices - 1) / num_slices);
+  L = (L + 7) & ~7;
+  return L < 8 ? 8 : L;
+}
+
+template <int NV2, bool kFused, int U>
+__global__ void __launch_bounds__(kFwWarpsPerCta * 32)
+pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_ids,
+                          const int32_t *__restrict__ sorted_cells, const float *__restrict__ rows,
+                          const float *__restrict__ depth, float *__restrict__ out,
+                          float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t total_cells,
+                          FastDiv div_dhw, FastDiv div_hw) {
+  constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3;
+  const int wglobal = blockIdx.x * kFwWarpsPerCta + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * kFwWarpsPerCta;
+
+  // ---- my share of the empty cells
+  {
+    const int64_t per_warp = ((total_cells + nwarps - 1) / nwarps + 31) & ~(int64_t)31;
+    const int64_t c_end = min(total_cells, (wglobal + 1) * per_warp);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t c0 = wglobal * per_warp; c0 < c_end; c0 += 32) {
+      const int ncell = (int)min((int64_t)32, c_end - c0);
+      const int cs = __ldg(cell_start + c0 + min(lane, ncell));
+      const int ce = __ldg(cell_start + c0 + min(lane + 1, ncell));
+      const unsigned occ = __ballot_sync(kFull, ce > cs);
+      if (occ == kFull) continue;
+      float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
+#pragma unroll 4
+      for (int i = lane; i < ncell * C4; i += 32)
+        if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(o4 + i, z);
     }
   }
-  int cur_end = __shfl_sync(kFull, ce, cur);
-  const int cur_begin = __shfl_sync(kFull, cs, cur);     // (all lanes: no short-circuit around a shuffle)
-  const bool starts_mid = hi > lo && lo > cur_begin;
-  bool in_head = starts_mid, had_boundary = false, open = false;
 
-  // head partial of a slice that starts inside a cell: parked in shared memory (rarely touched)
-  __shared__ float s_head[kG8FwdWarps][4][NREG][8];
-  float acc[NREG];
-#pragma unroll
-  for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
-  const char *rows_b = reinterpret_cast<const char *>(rows);
-  const size_t pitch_b = (size_t)row_pitch * 4;
+  // ---- my slice of the sorted point list
+  const int K = __ldg(cell_start + total_cells);
+  const int L = fwd_slice_len(K, nwarps * 4);
+  const int s = wglobal * 4 + grp;
+  const int lo = (int)min((int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
+  const int n0 = __shfl_sync(kFull, hi - lo, 0);            // group 0 has the warp's longest slice
+  if (n0 <= 0) return;
+  const bool guard = __any_sync(kFull, hi - lo != L);       // only the warp(s) at the very end of the list
+  const int nb = (n0 + 7) >> 3;
 
-  auto load_entry = [&](int idx, unsigned &erow, float &ed) {
+  const char *rows_b = opaque_ptr(rows);
+  auto load_id = [&](int idx) -> int { return idx < K ? ldg_stream_i32(sorted_ids + idx) : -1; };
+  auto load_key = [&](int idx) -> int { return idx < K ? ldg_stream_i32(sorted_cells + idx) : -1; };
+  auto finish_entry = [&](int id, unsigned &erow, float &ed) {
     erow = 0u;
     ed = 0.f;
-    if (idx < hi) {
-      const unsigned gp = (unsigned)ldg_stream_i32(sorted_ids + idx);
+    if (id >= 0) {
+      const unsigned gp = (unsigned)id;
       if (kFused) {
         const unsigned img = fastdiv(gp, div_dhw);                  // b*N + n
         const unsigned rem = gp - fastdiv(gp, div_hw) * div_hw.div; // h*W + w
@@ -150,96 +179,100 @@ pool_forward_g8_kernel(const int32_t *__restrict__ cell_start, const int32_t *__
     }
   };
 
-  unsigned e_row, n_row;
-  float e_d, n_d;
-  load_entry(lo + l8, e_row, e_d);
-  const int maxlen = (n + 3) >> 2;
-  for (int t = 0; t < maxlen; t += 8) {
-    const int pos = lo + t;
-    load_entry(pos + 8 + l8, n_row, n_d);     // next batch: in flight while this one is reduced
+  float acc[NREG];
+#pragma unroll
+  for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
+
+  unsigned row_c, row_n;
+  float d_c, d_n;
+  int key_c = load_key(lo + l8), key_n = load_key(lo + 8 + l8), key_nn;
+  int id_n = load_id(lo + 8 + l8), id_nn;
+  finish_entry(load_id(lo + l8), row_c, d_c);
+  const int prev_key = lo > 0 ? __ldg(sorted_cells + lo - 1) : -1;
+  const int first_key = __shfl_sync(kFull, key_c, 0, 8);   // (all lanes: never short-circuit around a shuffle)
+  bool in_head = hi > lo && prev_key == first_key;         // slice starts inside a cell
+  unsigned last_gm = 0u;
+  float *head_row = ws_head + (size_t)s * C, *tail_row = ws_tail + (size_t)s * C;
+
+  for (int b = 0; b < nb; ++b) {
+    const int pos = lo + 8 * b;
+    finish_entry(id_n, row_n, d_n);            // batch b+1: its id arrived during batch b-1
+    id_nn = load_id(pos + 16 + l8);            // batch b+2
+    key_nn = load_key(pos + 16 + l8);
+    // entry j closes its cell when the next list entry belongs to another cell
+    int nk = __shfl_down_sync(kFull, key_c, 1, 8);
+    const int k0n = __shfl_sync(kFull, key_n, 0, 8);
+    if (l8 == 7) nk = k0n;
+    const bool fl = key_c != nk && (!guard || pos + l8 < hi);
+    const unsigned gm = (__ballot_sync(kFull, fl) >> (8 * grp)) & 0xffu;
+    if (pos < hi) last_gm = gm;
 #pragma unroll
     for (int j0 = 0; j0 < 8; j0 += U) {
       float v[U][NREG];
       float d[U];
-      bool on[U];
+      int kk[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const unsigned row = __shfl_sync(kFull, e_row, j0 + u, 8);
-        d[u] = __shfl_sync(kFull, e_d, j0 + u, 8);
-        on[u] = pos + j0 + u < hi;
-        if (on[u]) g8_load_row<NV2, !kFused>(rows_b + (size_t)row * pitch_b, l8, v[u]);
+        const unsigned row = __shfl_sync(kFull, row_c, j0 + u, 8);
+        d[u] = __shfl_sync(kFull, d_c, j0 + u, 8);
+        kk[u] = __shfl_sync(kFull, key_c, j0 + u, 8);
+        if (!guard || pos + j0 + u < hi) {
+          g8_load_row<NV2, !kFused>(row_ptr<C * 4>(rows_b, row), l8, v[u]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < NREG; ++r) v[u][r] = 0.f;
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (on[u]) {
-#pragma unroll
-          for (int r = 0; r < NREG; ++r)
-            acc[r] = kFused ? __fadd_rn(acc[r], __fmul_rn(d[u], v[u][r])) : acc[r] + v[u][r];
-          open = true;
-        }
-        const bool flush = on[u] && (pos + j0 + u + 1 == cur_end);
-        if (__any_sync(kFull, flush)) {
-          if (flush) {
-            if (in_head) {
-#pragma unroll
-              for (int r = 0; r < NREG; ++r) s_head[warp][grp][r][l8] = acc[r];
-              in_head = false;
-            } else {
-              g8_store_row<NV2>(reinterpret_cast<char *>(out_w + (size_t)cur * C), l8, acc);
-            }
-#pragma unroll
-            for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
-            had_boundary = true;
-            open = false;
-            const unsigned rest = cur < 31 ? occ & ~((2u << cur) - 1u) : 0u;
-            cur = rest ? __ffs(rest) - 1 : 31;
+        if (kFused) axpy_row<NREG>(acc, d[u], v[u]); else add_row<NREG>(acc, v[u]);
+        if ((gm >> (j0 + u)) & 1u) {
+          if (in_head) {
+            g8_store_row<NV2>(reinterpret_cast<char *>(head_row), l8, acc);
+            in_head = false;
+          } else {
+            g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)kk[u] * C), l8, acc);
           }
-          const int nce = __shfl_sync(kFull, ce, cur);
-          if (flush) cur_end = nce;
+#pragma unroll
+          for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
         }
       }
     }
-    e_row = n_row;
-    e_d = n_d;
+    row_c = row_n; d_c = d_n; key_c = key_n;
+    id_n = id_nn; key_n = key_nn;
   }
-  if (in_head) {          // the whole slice lies inside one cell that started in an earlier slice
-#pragma unroll
-    for (int r = 0; r < NREG; ++r) { s_head[warp][grp][r][l8] = acc[r]; acc[r] = 0.f; }
-    open = false;
-  }
-  __syncwarp();
+  // the last cell continues in the next slice: park the partial sum
+  if (hi > lo && !((last_gm >> ((hi - lo - 1) & 7)) & 1u))
+    g8_store_row<NV2>(reinterpret_cast<char *>(in_head ? head_row : tail_row), l8, acc);
+}
 
-  // fixed-order fix-up of cells that straddle slice boundaries
-  float carry[NREG];
+// Combines the partial sums of cells cut by slice boundaries: the slice where such a cell
+// begins owns it and adds, in slice order, the head partials of the slices it continues into.
+template <int NV2>
+__global__ void __launch_bounds__(128)
+pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_cells,
+                          const float *__restrict__ ws_head, const float *__restrict__ ws_tail,
+                          float *__restrict__ out, int64_t total_cells, int num_slices) {
+  constexpr int C = 16 * NV2, NREG = 2 * NV2;
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l8 = threadIdx.x & 7;
+  if (s >= num_slices) return;
+  const int K = __ldg(cell_start + total_cells);
+  const int L = fwd_slice_len(K, num_slices);
+  const int lo = (int)min((int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
+  if (hi <= lo || hi >= K) return;
+  const int key = __ldg(sorted_cells + hi - 1);
+  if (key != __ldg(sorted_cells + hi)) return;                      // slice ends on a cell boundary
+  if (lo > 0 && __ldg(sorted_cells + lo - 1) == key) return;        // cell began in an earlier slice
+  float acc[NREG], v[NREG];
+  g8_load_row<NV2, false>(reinterpret_cast<const char *>(ws_tail + (size_t)s * C), l8, acc);
+  for (int t = s + 1; t < num_slices; ++t) {
+    const int tlo = t * L, thi = min(tlo + L, K);                   // tlo < K because slice t-1 ended mid-cell
+    g8_load_row<NV2, false>(reinterpret_cast<const char *>(ws_head + (size_t)t * C), l8, v);
 #pragma unroll
-  for (int r = 0; r < NREG; ++r) carry[r] = 0.f;
-  int carry_cell = 0;
-  bool carry_open = false;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const int src = g * 8;
-    const bool g_nonempty = __shfl_sync(kFull, (int)(hi > lo), src) != 0;
-    const bool g_mid = __shfl_sync(kFull, (int)starts_mid, src) != 0;
-    const bool g_bound = __shfl_sync(kFull, (int)had_boundary, src) != 0;
-    const bool g_open = __shfl_sync(kFull, (int)open, src) != 0;
-    const int g_cur = __shfl_sync(kFull, cur, src);
-    if (!g_nonempty) continue;
-    if (g_mid) {
-#pragma unroll
-      for (int r = 0; r < NREG; ++r) carry[r] += s_head[warp][g][r][l8];
-      if (g_bound) {
-        if (grp == 0) g8_store_row<NV2>(reinterpret_cast<char *>(out_w + (size_t)carry_cell * C), l8, carry);
-        carry_open = false;
-      }
-    }
-    if (g_open) {
-#pragma unroll
-      for (int r = 0; r < NREG; ++r) carry[r] = __shfl_sync(kFull, acc[r], src + l8);
-      carry_cell = g_cur;
-      carry_open = true;
-    }
+    for (int r = 0; r < NREG; ++r) acc[r] += v[r];
+    if (!(thi < K && __ldg(sorted_cells + thi - 1) == key && __ldg(sorted_cells + thi) == key)) break;
   }
-  if (carry_open && grp == 0) g8_store_row<NV2>(reinterpret_cast<char *>(out_w + (size_t)carry_cell * C), l8, carry);
+  g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)key * C), l8, acc);
 }
 
 // ---- fused backward ---------------------------------------------------------------------------
@@ -260,9 +293,8 @@ pool_forward_g8_kernel(const int32_t *__restrict__ cell_start, const int32_t *__
 constexpr int kBwTW = 4;     // image columns per CTA = one 16-byte segment
 constexpr int kBwDC = 32;    // depth bins per staged chunk
 constexpr int kBwHG = 2;     // row groups (of 4 rows) per CTA
-constexpr int kBwU = 2;      // depth bins in flight per warp
 
-template <int NV2, int HG, bool kVec>
+template <int NV2, int HG, bool kVec, int kBwU /* depth bins in flight per warp */>
 __global__ void __launch_bounds__(128 * HG)
 fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float *__restrict__ grad_rows,
                          const float *__restrict__ depth, const float *__restrict__ ctx_nchw,
@@ -279,7 +311,7 @@ fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float 
   const int h0 = th * TH, w0 = tw * kBwTW;
   const int HW = H * W;
   const int64_t img_base = (int64_t)bn * D * HW;
-  const char *gbase = reinterpret_cast<const char *>(grad_rows + (int64_t)(bn / num_cams) * cells_per_sample * C);
+  const char *gbase = opaque_ptr(grad_rows + (int64_t)(bn / num_cams) * cells_per_sample * C);
 
   // staging role: thread = (bin sd of the chunk, row sh of the tile), 4 columns
   const int sd = lane, sh = warp;
@@ -351,18 +383,19 @@ fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float 
         dmask &= dmask - 1u;
         e[q] = s_cd[wl][hl][dq[q]];
         on[q] = on[q] && (int)e[q].x >= 0;
-        if (on[q]) g8_load_row<NV2, false>(gbase + (size_t)e[q].x * (C * 4), l8, g[q]);
+        if (on[q]) g8_load_row<NV2, false>(row_ptr<C * 4>(gbase, e[q].x), l8, g[q]);
       }
 #pragma unroll
       for (int q = 0; q < kBwU; ++q) {
         float dot = 0.f;
         if (on[q]) {
           const float dv = __uint_as_float(e[q].y);
+          float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int r = 0; r < NREG; ++r) {
-            dot = fmaf(g[q][r], cx[r], dot);
-            gacc[r] = fmaf(dv, g[q][r], gacc[r]);
-          }
+          for (int r = 0; r < NREG; r += 2)
+            dot2 = __ffma2_rn(make_float2(g[q][r], g[q][r + 1]), make_float2(cx[r], cx[r + 1]), dot2);
+          dot = dot2.x + dot2.y;
+          axpy_row<NREG>(gacc, dv, g[q]);
         }
         dot += __shfl_xor_sync(0xffffffffu, dot, 4);
         dot += __shfl_xor_sync(0xffffffffu, dot, 2);

@@ -136,14 +136,23 @@ def _grad_rows_nhwc(grad_out: torch.Tensor, plan: PoolingPlan) -> torch.Tensor:
     return rows
 
 
+def _forward_workspace(channels: int, device) -> torch.Tensor:
+    """Scratch for the forward kernels (partial sums of cells cut by the even-share partition)."""
+    nbytes = ctypes.c_size_t()
+    _lib.check(_lib.lib().bevpool_forward_workspace_bytes(channels, ctypes.byref(nbytes)),
+               'bevpool_forward_workspace_bytes')
+    return torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+
+
 def pool_forward(plan: PoolingPlan, input_features: torch.Tensor) -> torch.Tensor:
     """features (B, ..., C) -> (B, Y, X, C); every cell written once, no pre-zeroing."""
     X, Y, _ = plan.voxel_num
     B, C = plan.batch, input_features.shape[-1]
     out = torch.empty(B, Y, X, C, dtype=input_features.dtype, device=input_features.device)
+    ws = _forward_workspace(C, out.device)
     _lib.check(_lib.lib().bevpool_forward(plan.ptr, input_features.data_ptr(), out.data_ptr(),
                                           _lib.dtype_code(input_features), B, plan.num_points, C, X, Y,
-                                          _lib.stream_ptr(out.device)), 'bevpool_forward')
+                                          ws.data_ptr(), _lib.stream_ptr(out.device)), 'bevpool_forward')
     return out
 
 
@@ -172,9 +181,10 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor)
     if not ctx_nhwc.is_contiguous():          # NCHW in: one small tiled transpose (C*H*W per image)
         ctx_nhwc = _transpose(context.contiguous(), BN, C, H * W)
     out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
+    ws = _forward_workspace(C, out.device)
     _lib.check(_lib.lib().bevpool_fused_forward(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
                                                 out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
-                                                C, X, Y, _lib.stream_ptr(depth.device)),
+                                                C, X, Y, ws.data_ptr(), _lib.stream_ptr(depth.device)),
                'bevpool_fused_forward')
     return out
 

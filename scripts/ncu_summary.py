@@ -90,3 +90,25 @@ if __name__ == '__main__' and '--hot' in sys.argv:
     for p in sys.argv[1:]:
         if p.endswith('.ncu-rep'):
             hot(p)
+
+
+def loop(path, frac=0.5):
+    """SASS of the hot region: every instruction executed at least `frac` x the most-executed count"""
+    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    his = [i for i, r in enumerate(rows) if 'Source' in r and 'Instructions Executed' in r]
+    hi = his[-1]
+    hdr = rows[hi]
+    si, ii, st = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Warp Stall Sampling (All Samples)')
+    body = [r for r in rows[hi + 1:] if len(r) > ii and r[0].startswith('0x')]
+    mx = max(int(r[ii]) for r in body)
+    tot = sum(int(r[st]) for r in body)
+    for i, r in enumerate(body):
+        if int(r[ii]) >= frac * mx:
+            print(f'    #{i:4d} exec={int(r[ii]):9d} stall={100 * int(r[st]) / tot:4.1f}%  {r[si].strip()[:100]}')
+
+
+if __name__ == '__main__' and '--loop' in sys.argv:
+    for p in sys.argv[1:]:
+        if p.endswith('.ncu-rep'):
+            loop(p)

@@ -45,8 +45,8 @@ def test_argument_errors_are_codes_not_crashes(L):
     assert L.bevpool_plan_sizes(2, 6000, 128, 128, ctypes.byref(pb), ctypes.byref(tb)) == 0
     assert pb.value > 2 * 6000 * 8 and tb.value > 0
     # null pointers / bad channel counts are rejected before any launch
-    assert L.bevpool_forward(None, None, None, 0, 2, 6000, 80, 128, 128, None) == -1
-    assert L.bevpool_forward(None, None, None, 0, 2, 6000, 81, 128, 128, None) == -3
+    assert L.bevpool_forward(None, None, None, 0, 2, 6000, 80, 128, 128, None, None) == -1
+    assert L.bevpool_forward(None, None, None, 0, 2, 6000, 81, 128, 128, None, None) == -3
     assert L.bevpool_transpose(None, None, 0, 1, 4, 4, None) == -1
 
 

@@ -249,9 +249,14 @@ def test_fused_on_camera_rig(cfg, B, kernel_path):
     geom, vn = synthetic.camera_rig(cfg, B, yaw_jitter_deg=5.0)
     depth, ctx, go = synthetic.camera_features(cfg, B)
     out = _check_fused(geom, depth, ctx, go, vn.tolist(), False, kernel_path)
-    # the materialised drop-in path gives the same bits
+    # the materialised drop-in path: same bits with the generic kernels (separate multiply and add in
+    # point order); the fast path contracts multiply-add (FFMA2), so it agrees to rounding
     feats = vp.materialise_features_ref(depth, ctx, B, cfg.num_cams).cuda()
-    assert torch.equal(voxel_pooling(geom.cuda(), feats, vn.cuda()), out)
+    mat = voxel_pooling(geom.cuda(), feats, vn.cuda())
+    if kernel_path == 'generic':
+        assert torch.equal(mat, out)
+    else:
+        assert torch.allclose(mat, out, rtol=1e-5, atol=1e-6)
 
 
 def test_fused_full_size_aim_properties():
