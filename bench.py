@@ -205,8 +205,8 @@ def main():
     # ---------------------------------------------------------------- native arm
     import torch.distributed as dist
     from mm_training_b200 import _lib
-    from mm_training_b200.ops.voxel_pooling import (build_plan, fused_backward, fused_forward,
-                                                    voxel_pooling_fused)
+    from mm_training_b200.ops.voxel_pooling import (build_plan, context_rows_nhwc, fused_backward,
+                                                    fused_forward, voxel_pooling_fused)
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -221,8 +221,9 @@ def main():
 
     def step():
         plan = build_plan(geom, vn)
-        out = fused_forward(plan, depth, ctx)
-        gd, gc = fused_backward(plan, go, depth, ctx)
+        rows = context_rows_nhwc(ctx)                  # NCHW context -> pixel rows, shared by fwd and bwd
+        out = fused_forward(plan, depth, ctx, rows)
+        gd, gc = fused_backward(plan, go, depth, ctx, rows)   # grad_context comes back NCHW like ctx
         return plan, out, gd, gc
 
     plan, out, gd, gc = step()
@@ -297,7 +298,7 @@ def main():
     ctx_nhwc = ctx.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
     go_nhwc = go.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
     k_fwd = time_cuda(lambda: fused_forward(plan, depth, ctx_nhwc), 20, 3)
-    k_bwd = time_cuda(lambda: fused_backward(plan, go_nhwc, depth, ctx), 20, 3)
+    k_bwd = time_cuda(lambda: fused_backward(plan, go_nhwc, depth, ctx_nhwc), 20, 3)
     stages['fused_forward_kernel'] = k_fwd
     stages['fused_backward_kernel'] = k_bwd
     dom_name, dom = ('fused_backward', k_bwd) if k_bwd[0] >= k_fwd[0] else ('fused_forward', k_fwd)

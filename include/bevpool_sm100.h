@@ -83,13 +83,14 @@ int bevpool_backward(const void *plan, const void *grad_out_nhwc, void *grad_fea
 /* ---- fused op: depth (x) context outer product never materialised ----------------
  * Replaces layers/backbones/lss_fpn.py:441-464 + the op.  Points are enumerated
  * (b, n, d, h, w) like the reference's (B, N, D, H, W, C) tensor, Np = N*D*H*W.
- * depth (B*N, D, H, W); context_nhwc (B*N, H, W, C); context_nchw (B*N, C, H, W).   */
+ * depth (B*N, D, H, W); context_nhwc / grad_context_nhwc (B*N, H, W, C): pixel rows of C
+ * contiguous channels (channels_last); bevpool_transpose converts from / to (B*N, C, H, W).   */
 int bevpool_fused_forward(const void *plan, const void *depth, const void *context_nhwc,
                           void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
                           int feat_h, int feat_w, int channels, int num_voxel_x,
                           int num_voxel_y, void *workspace, void *stream);
 int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const void *depth,
-                           const void *context_nchw, void *grad_depth, void *grad_context_nchw,
+                           const void *context_nhwc, void *grad_depth, void *grad_context_nhwc,
                            int dtype, int batch, int num_cams, int depth_bins, int feat_h,
                            int feat_w, int channels, int num_voxel_x, int num_voxel_y,
                            void *stream);

@@ -242,8 +242,8 @@ __device__ __forceinline__ float transpose_reduce32(float (&p)[32], int lane) {
 template <typename T, int CPL>
 __global__ void __launch_bounds__(kBwdMaxWarps * 32)
 fused_backward_kernel(const int32_t *__restrict__ cell_of_point, const T *__restrict__ grad_nhwc,
-                      const T *__restrict__ depth, const T *__restrict__ ctx_nchw,
-                      T *__restrict__ grad_depth, T *__restrict__ grad_ctx_nchw, int num_cams, int D,
+                      const T *__restrict__ depth, const T *__restrict__ ctx_nhwc,
+                      T *__restrict__ grad_depth, T *__restrict__ grad_ctx_nhwc, int num_cams, int D,
                       int H, int W, int C, int64_t cells_per_sample) {
   const int lane = threadIdx.x & 31;
   const int bn = blockIdx.z;
@@ -262,13 +262,7 @@ fused_backward_kernel(const int32_t *__restrict__ cell_of_point, const T *__rest
       const int ch = lane + 32 * k;
       gacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       cx[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ch < C4) {
-        const T *cp = ctx_nchw + ((int64_t)bn * C + ch * 4) * HW + hw;
-        cx[k].x = Vec4<T>::to_float(__ldg(cp));
-        cx[k].y = Vec4<T>::to_float(__ldg(cp + HW));
-        cx[k].z = Vec4<T>::to_float(__ldg(cp + 2 * HW));
-        cx[k].w = Vec4<T>::to_float(__ldg(cp + 3 * HW));
-      }
+      if (ch < C4) cx[k] = Vec4<T>::load(ctx_nhwc + ((int64_t)bn * HW + hw) * C + ch * 4);
     }
     for (int d0 = 0; d0 < D; d0 += 32) {
       const int d = d0 + lane;
@@ -333,13 +327,7 @@ fused_backward_kernel(const int32_t *__restrict__ cell_of_point, const T *__rest
 #pragma unroll
     for (int k = 0; k < CPL; ++k) {
       const int ch = lane + 32 * k;
-      if (ch < C4) {
-        T *cp = grad_ctx_nchw + ((int64_t)bn * C + ch * 4) * HW + hw;
-        cp[0] = Vec4<T>::from_float(gacc[k].x);
-        cp[HW] = Vec4<T>::from_float(gacc[k].y);
-        cp[2 * HW] = Vec4<T>::from_float(gacc[k].z);
-        cp[3 * HW] = Vec4<T>::from_float(gacc[k].w);
-      }
+      if (ch < C4) Vec4<T>::store(grad_ctx_nhwc + ((int64_t)bn * HW + hw) * C + ch * 4, gacc[k]);
     }
   }
 }
@@ -428,21 +416,21 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
       if (!workspace) return BEVPOOL_E_ARG;
       if (!aligned16(workspace)) return BEVPOOL_E_ALIGN;
       const FastDiv fd_dhw = make_fastdiv((uint32_t)dhw), fd_hw = make_fastdiv((uint32_t)hw);
-      int cps = env_int("BEVPOOL_FW_CPS", 5);
-      cps = cps < 1 ? 1 : (cps > kFwMaxCtasPerSm ? kFwMaxCtasPerSm : cps);
+      int cps = env_int("BEVPOOL_FW_CPS", 6);          // CTAs per SM: cps-1 reduce + 1 zero-fill
+      cps = cps < 2 ? 2 : (cps > kFwMaxCtasPerSm ? kFwMaxCtasPerSm : cps);
       const int u = env_int("BEVPOOL_FW_U", 4);
       const unsigned ctas = (unsigned)(sm_count() * cps);
-      const int slices = (int)ctas * kFwWarpsPerCta * 4;
+      const int slices = (int)(ctas - ctas / cps) * kFwWarpsPerCta * 4;
       float *ws_head = static_cast<float *>(workspace);
       float *ws_tail = ws_head + (size_t)slices * C;
       if (u == 2) {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 2><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   total_cells, fd_dhw, fd_hw)));
+                                   total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
       } else {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 4><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   total_cells, fd_dhw, fd_hw)));
+                                   total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
       }
       BEVPOOL_LAUNCH_CHECK();
       BEVPOOL_G8_DISPATCH(C, (pool_forward_fixup_kernel<NV2><<<(unsigned)ceil_div64((int64_t)slices * 8, 128), 128, 0, s>>>(
@@ -524,7 +512,7 @@ static int fused_backward_t(const void *plan, const void *grad, const void *dept
       const bool vec = (W % 4 == 0) && aligned16(dp) && aligned16(gd);
 #define BEVPOOL_BW_LAUNCH(HG, VEC, U)                                                                      \
   BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, HG, VEC, U><<<(unsigned)ctas, 128 * HG, 0, s>>>(   \
-                             pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w)))
+                             pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))))
       const int bu = env_int("BEVPOOL_BW_U", 2);
       if (!vec) { if (hg == 1) { BEVPOOL_BW_LAUNCH(1, false, 2); } else { BEVPOOL_BW_LAUNCH(2, false, 2); } }
       else if (hg == 1 && bu == 4) { BEVPOOL_BW_LAUNCH(1, true, 4); }
@@ -599,7 +587,7 @@ extern "C" int bevpool_fused_forward(const void *plan, const void *depth, const 
 }
 
 extern "C" int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const void *depth,
-                                      const void *context_nchw, void *grad_depth, void *grad_context_nchw,
+                                      const void *context_nhwc, void *grad_depth, void *grad_context_nhwc,
                                       int dtype, int batch, int num_cams, int depth_bins, int feat_h,
                                       int feat_w, int channels, int X, int Y, void *stream) {
   if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
@@ -607,10 +595,10 @@ extern "C" int bevpool_fused_backward(const void *plan, const void *grad_out_nhw
   int rc = check_plan_dims(batch, np, X, Y);
   if (rc) return rc;
   if ((rc = check_channels(channels))) return rc;
-  if (!plan || !grad_out_nhwc || !depth || !context_nchw || !grad_depth || !grad_context_nchw) return BEVPOOL_E_ARG;
-  if (!aligned16(grad_out_nhwc)) return BEVPOOL_E_ALIGN;
+  if (!plan || !grad_out_nhwc || !depth || !context_nhwc || !grad_depth || !grad_context_nhwc) return BEVPOOL_E_ARG;
+  if (!aligned16(grad_out_nhwc) || !aligned16(context_nhwc) || !aligned16(grad_context_nhwc)) return BEVPOOL_E_ALIGN;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  BEVPOOL_DISPATCH_DTYPE(dtype, (fused_backward_t<T>(plan, grad_out_nhwc, depth, context_nchw, grad_depth, grad_context_nchw, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
+  BEVPOOL_DISPATCH_DTYPE(dtype, (fused_backward_t<T>(plan, grad_out_nhwc, depth, context_nhwc, grad_depth, grad_context_nhwc, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
 }
 
 extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nhwc, int dtype,

@@ -125,32 +125,51 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
                           const int32_t *__restrict__ sorted_cells, const float *__restrict__ rows,
                           const float *__restrict__ depth, float *__restrict__ out,
                           float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t total_cells,
-                          FastDiv div_dhw, FastDiv div_hw) {
+                          FastDiv div_dhw, FastDiv div_hw, int fill_period, int exp_mask, int exp_flags) {
   constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4;
   constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3;
-  const int wglobal = blockIdx.x * kFwWarpsPerCta + (threadIdx.x >> 5);
-  const int nwarps = gridDim.x * kFwWarpsPerCta;
-
-  // ---- my share of the empty cells
-  {
-    const int64_t per_warp = ((total_cells + nwarps - 1) / nwarps + 31) & ~(int64_t)31;
-    const int64_t c_end = min(total_cells, (wglobal + 1) * per_warp);
+  const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3, warp = threadIdx.x >> 5;
+  // Roles: every `fill_period`-th CTA zero-fills the empty cells of the grid (DRAM-write bound) while
+  // the other CTAs, co-resident on the same SMs, run the latency-bound reduction.
+  const int bid = blockIdx.x;
+  if (bid % fill_period == fill_period - 1) {
+    if (exp_flags & 1) return;
+    const int fwarp = (bid / fill_period) * kFwWarpsPerCta + warp;
+    const int nfw = (gridDim.x / fill_period) * kFwWarpsPerCta;
+    const int64_t per_warp = ((total_cells + nfw - 1) / nfw + 31) & ~(int64_t)31;
+    const int64_t c_begin = fwarp * per_warp, c_end = min(total_cells, c_begin + per_warp);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t c0 = wglobal * per_warp; c0 < c_end; c0 += 32) {
+    auto load_cs = [&](int64_t c0, int &cs, int &ce) {
+      cs = ce = 0;
+      if (c0 < c_end) {
+        const int ncell = (int)min((int64_t)32, c_end - c0);
+        cs = __ldg(cell_start + c0 + min(lane, ncell));
+        ce = __ldg(cell_start + c0 + min(lane + 1, ncell));
+      }
+    };
+    int cs, ce, cs_n, ce_n;
+    load_cs(c_begin, cs, ce);
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += 32) {
+      load_cs(c0 + 32, cs_n, ce_n);            // next block's offsets: in flight behind this block's stores
       const int ncell = (int)min((int64_t)32, c_end - c0);
-      const int cs = __ldg(cell_start + c0 + min(lane, ncell));
-      const int ce = __ldg(cell_start + c0 + min(lane + 1, ncell));
       const unsigned occ = __ballot_sync(kFull, ce > cs);
-      if (occ == kFull) continue;
-      float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
+      if (occ != kFull) {
+        float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
 #pragma unroll 4
-      for (int i = lane; i < ncell * C4; i += 32)
-        if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(o4 + i, z);
+        for (int i = lane; i < ncell * C4; i += 32)
+          if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(o4 + i, z);
+      }
+      cs = cs_n;
+      ce = ce_n;
     }
+    return;
   }
+  const int rid = bid - bid / fill_period;
+  const int wglobal = rid * kFwWarpsPerCta + warp;
+  const int nwarps = (gridDim.x - gridDim.x / fill_period) * kFwWarpsPerCta;
 
   // ---- my slice of the sorted point list
+  if (exp_flags & 2) return;
   const int K = __ldg(cell_start + total_cells);
   const int L = fwd_slice_len(K, nwarps * 4);
   const int s = wglobal * 4 + grp;
@@ -213,7 +232,7 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
       int kk[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const unsigned row = __shfl_sync(kFull, row_c, j0 + u, 8);
+        const unsigned row = __shfl_sync(kFull, row_c, j0 + u, 8) & (unsigned)exp_mask;
         d[u] = __shfl_sync(kFull, d_c, j0 + u, 8);
         kk[u] = __shfl_sync(kFull, key_c, j0 + u, 8);
         if (!guard || pos + j0 + u < hi) {
@@ -297,9 +316,10 @@ constexpr int kBwHG = 2;     // row groups (of 4 rows) per CTA
 template <int NV2, int HG, bool kVec, int kBwU /* depth bins in flight per warp */>
 __global__ void __launch_bounds__(128 * HG)
 fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float *__restrict__ grad_rows,
-                         const float *__restrict__ depth, const float *__restrict__ ctx_nchw,
-                         float *__restrict__ grad_depth, float *__restrict__ grad_ctx_nchw, int num_cams,
-                         int D, int H, int W, int64_t cells_per_sample, int tiles_h, int tiles_w) {
+                         const float *__restrict__ depth, const float *__restrict__ ctx_nhwc,
+                         float *__restrict__ grad_depth, float *__restrict__ grad_ctx_nhwc, int num_cams,
+                         int D, int H, int W, int64_t cells_per_sample, int tiles_h, int tiles_w, int exp_mask,
+                         int exp_flags) {
   constexpr int C = 16 * NV2, NREG = 2 * NV2, TH = 4 * HG, LD = kBwDC + 1;
   __shared__ uint2 s_cd[kBwTW][TH][LD];    // (cell, depth bits) of the chunk, [column][row][bin]
   __shared__ float s_res[kBwTW][TH][LD];   // grad_depth of the chunk
@@ -323,14 +343,10 @@ fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float 
   const int hw = (h0 + hl) * W + w0 + wl;
 
   float cx[NREG], gacc[NREG];
-  {
-    const float *cp = ctx_nchw + (int64_t)bn * C * HW + hw;
 #pragma unroll
-    for (int r = 0; r < NREG; ++r) {
-      cx[r] = pix_ok ? __ldg(cp + (int64_t)g8_channel<NV2>(r, l8) * HW) : 0.f;
-      gacc[r] = 0.f;
-    }
-  }
+  for (int r = 0; r < NREG; ++r) cx[r] = gacc[r] = 0.f;
+  // context row of the group's pixel: one contiguous C-float row of the (B*N, H, W, C) tensor
+  if (pix_ok) g8_load_row<NV2, true>(reinterpret_cast<const char *>(ctx_nhwc + ((int64_t)bn * HW + hw) * C), l8, cx);
 
   int4 pc = make_int4(-1, -1, -1, -1);
   float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -371,6 +387,7 @@ fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float 
       m |= m >> 8;
       dmask |= (m & 0xffu) << (8 * k);
     }
+    if (exp_flags & 1) dmask = 0u;
     while (dmask) {
       int dq[kBwU];
       uint2 e[kBwU];
@@ -383,7 +400,7 @@ fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float 
         dmask &= dmask - 1u;
         e[q] = s_cd[wl][hl][dq[q]];
         on[q] = on[q] && (int)e[q].x >= 0;
-        if (on[q]) g8_load_row<NV2, false>(row_ptr<C * 4>(gbase, e[q].x), l8, g[q]);
+        if (on[q]) g8_load_row<NV2, false>(row_ptr<C * 4>(gbase, e[q].x & (unsigned)exp_mask), l8, g[q]);
       }
 #pragma unroll
       for (int q = 0; q < kBwU; ++q) {
@@ -418,11 +435,7 @@ fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float 
       }
     }
   }
-  if (pix_ok) {
-    float *op = grad_ctx_nchw + (int64_t)bn * C * HW + hw;
-#pragma unroll
-    for (int r = 0; r < NREG; ++r) op[(int64_t)g8_channel<NV2>(r, l8) * HW] = gacc[r];
-  }
+  if (pix_ok) g8_store_row<NV2>(reinterpret_cast<char *>(grad_ctx_nhwc + ((int64_t)bn * HW + hw) * C), l8, gacc);
 }
 
 inline bool g8_supported(int C) {

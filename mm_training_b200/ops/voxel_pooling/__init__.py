@@ -1,5 +1,5 @@
 # mirrors ops/voxel_pooling/__init__.py:1-3 of the reference
 from .voxel_pooling import (voxel_pooling, voxel_pooling_fused, build_plan, PoolingPlan, pool_forward,
-                            pool_backward, fused_forward, fused_backward)
+                            pool_backward, fused_forward, fused_backward, context_rows_nhwc)
 
 __all__ = ['voxel_pooling', 'voxel_pooling_fused', 'build_plan', 'PoolingPlan']

@@ -168,7 +168,18 @@ def pool_backward(plan: PoolingPlan, grad_output: torch.Tensor, input_shape) -> 
     return grad_in
 
 
-def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor) -> torch.Tensor:
+def context_rows_nhwc(context: torch.Tensor) -> torch.Tensor:
+    """context (B*N, C, H, W), NCHW or channels_last -> (B*N, H, W, C) contiguous rows.  Zero-copy for
+    channels_last; NCHW costs one small tiled transpose (C*H*W elements per image)."""
+    BN, C, H, W = context.shape
+    rows = context.permute(0, 2, 3, 1)
+    if not rows.is_contiguous():
+        rows = _transpose(context.contiguous(), BN, C, H * W).view(BN, H, W, C)
+    return rows
+
+
+def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
+                  context_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     """depth (B*N, D, H, W), context (B*N, C, H, W) NCHW or channels_last -> (B, Y, X, C)."""
     BN, D, H, W = depth.shape
     C = context.shape[1]
@@ -177,9 +188,7 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor)
     N = BN // B
     assert context.shape == (BN, C, H, W) and depth.dtype == context.dtype
     assert B * N == BN and plan.num_points == N * D * H * W
-    ctx_nhwc = context.permute(0, 2, 3, 1)
-    if not ctx_nhwc.is_contiguous():          # NCHW in: one small tiled transpose (C*H*W per image)
-        ctx_nhwc = _transpose(context.contiguous(), BN, C, H * W)
+    ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
     out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
     ws = _forward_workspace(C, out.device)
     _lib.check(_lib.lib().bevpool_fused_forward(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
@@ -190,21 +199,28 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor)
 
 
 def fused_backward(plan: PoolingPlan, grad_output: torch.Tensor, depth: torch.Tensor,
-                   context: torch.Tensor):
-    """grad_output (B, C, Y, X), any strides -> (grad_depth, grad_context (NCHW-contiguous))."""
+                   context: torch.Tensor, context_rows: Optional[torch.Tensor] = None):
+    """grad_output (B, C, Y, X), any strides -> (grad_depth, grad_context).  grad_context has the
+    memory format of ``context``: channels_last in -> channels_last out (zero-copy), NCHW in ->
+    NCHW out (one tiled transpose)."""
     BN, D, H, W = depth.shape
     C = context.shape[1]
     X, Y, _ = plan.voxel_num
     B = plan.batch
     N = BN // B
     rows = _grad_rows_nhwc(grad_output, plan)
-    context_nchw = context.contiguous()
+    channels_last = context.permute(0, 2, 3, 1).is_contiguous()
+    ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
     grad_depth = torch.empty_like(depth)
-    grad_context = torch.empty_like(context_nchw)
+    grad_ctx_nhwc = torch.empty(BN, H, W, C, dtype=context.dtype, device=context.device)
     _lib.check(_lib.lib().bevpool_fused_backward(
-        plan.ptr, rows.data_ptr(), depth.data_ptr(), context_nchw.data_ptr(), grad_depth.data_ptr(),
-        grad_context.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+        plan.ptr, rows.data_ptr(), depth.data_ptr(), ctx_nhwc.data_ptr(), grad_depth.data_ptr(),
+        grad_ctx_nhwc.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
         _lib.stream_ptr(depth.device)), 'bevpool_fused_backward')
+    if channels_last:
+        grad_context = grad_ctx_nhwc.permute(0, 3, 1, 2)
+    else:
+        grad_context = _transpose(grad_ctx_nhwc, BN, H * W, C).view(BN, C, H, W)
     return grad_depth, grad_context
 
 
@@ -253,16 +269,17 @@ class VoxelPoolingFused(Function):
                 assert geom_xyz.is_contiguous()
                 plan = PoolingPlan(geom_xyz, (X, Y, Z))
             assert plan.voxel_num == (X, Y, Z)
-            out = fused_forward(plan, depth, context)
+            context_rows = context_rows_nhwc(context)
+            out = fused_forward(plan, depth, context, context_rows)
         ctx.plan = plan
-        ctx.save_for_backward(depth, context)
+        ctx.save_for_backward(depth, context, context_rows)   # the rows are reused by backward
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, grad_out):
-        depth, context = ctx.saved_tensors
+        depth, context, context_rows = ctx.saved_tensors
         with torch.cuda.device(grad_out.device):
-            grad_depth, grad_context = fused_backward(ctx.plan, grad_out, depth, context)
+            grad_depth, grad_context = fused_backward(ctx.plan, grad_out, depth, context, context_rows)
         return None, grad_depth, grad_context, None, None
 
 
