@@ -27,12 +27,22 @@ struct SortConfig {
   int npass;
   int bits[kMaxPasses];
   int shift[kMaxPasses];
+  bool msd;            // bits[0] = low (finished per bucket in shared memory), bits[1] = high (global pass)
 };
 
 static SortConfig sort_config(int64_t cells_per_sample) {
   int nbits = 1;
   while ((1ll << nbits) < cells_per_sample) ++nbits;
   SortConfig c;
+  c.msd = false;
+  if (nbits > 8 && nbits <= 16) {
+    c.msd = true;
+    c.npass = 2;
+    c.bits[0] = 8;          c.shift[0] = 0;
+    c.bits[1] = nbits - 8;  c.shift[1] = 8;
+    c.bits[2] = 0;          c.shift[2] = nbits;
+    return c;
+  }
   c.npass = (nbits + 9) / 10;
   const int per = (nbits + c.npass - 1) / c.npass;
   int shift = 0;
@@ -62,6 +72,10 @@ static TempLayout temp_layout(int batch, int64_t num_points, int X, int Y) {
   size_t o = 0;
   for (int p = 0; p < kMaxPasses; ++p) {
     L.hist_n[p] = p < sc.npass ? (int64_t)batch * (1ll << sc.bits[p]) * L.tiles_per_sample + 1 : 0;
+  }
+  if (sc.msd) {   // one global pass, over the HIGH bits; the low bits never get a global histogram
+    L.hist_n[0] = (int64_t)batch * (1ll << sc.bits[1]) * L.tiles_per_sample + 1;
+    L.hist_n[1] = 1;
   }
   for (int p = 0; p < sc.npass; ++p) {
     L.off_scan[p] = o;
@@ -219,6 +233,159 @@ sort_scatter_kernel(const int32_t *__restrict__ in_keys, const int32_t *__restri
   }
 }
 
+// ==== MSD fast path (grids of 2^9 .. 2^16 cells per sample) ====================================
+// pass A (plan_key_msd_kernel): cell index of every point + tile histogram of the HIGH key bits
+// pass B (sort_scatter_kernel<true>): stable scatter of the kept (cell, id) pairs into buckets of
+//         2^low consecutive cells (one look-back scan over [sample][bucket][tile] in between)
+// pass C (bucket_sort_kernel): one CTA per (sample, bucket) finishes the sort locally -- histogram of
+//         the low bits in shared memory, CSR offsets of its 2^low cells, stable placement -- so the
+//         second global histogram, its scan, the per-cell atomics and the CSR scan of the LSD path
+//         are not needed.
+// geom is read as 16-byte vectors: a thread owns 4 consecutive points = 48 bytes.
+__global__ void __launch_bounds__(kSortThreads)
+plan_key_msd_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
+                    int32_t *__restrict__ cell_of_point, uint32_t *__restrict__ hist, int low_bits,
+                    int bins, int tiles_per_sample) {
+  extern __shared__ uint32_t s_hist[];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const int64_t sample_base = (int64_t)b * num_points;
+  const int64_t tile_base = (int64_t)tile * kSortTile;
+  const bool vec = ((sample_base + tile_base) & 3) == 0;   // 16-byte alignment of the quad loads
+#pragma unroll
+  for (int q = 0; q < kSortItems / 4; ++q) {
+    const int64_t p0 = tile_base + ((int64_t)q * kSortThreads + threadIdx.x) * 4;
+    if (p0 >= num_points) continue;
+    const int64_t gp0 = sample_base + p0;
+    int c[12];
+    if (vec && p0 + 3 < num_points) {
+      const int4 *src = reinterpret_cast<const int4 *>(geom + gp0 * 3);
+      const int4 a0 = ldg_stream_i4(src), a1 = ldg_stream_i4(src + 1), a2 = ldg_stream_i4(src + 2);
+      c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y;
+      c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y; c[10] = a2.z; c[11] = a2.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 12; ++k) c[k] = (p0 + k / 3 < num_points) ? __ldg(geom + gp0 * 3 + k) : -1;
+    }
+    int cell[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x = c[3 * k], y = c[3 * k + 1], z = c[3 * k + 2];
+      // reference bounds test, voxel_pooling_forward_cuda.cu:24; z gates only (:32-33)
+      const bool kept = x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z && p0 + k < num_points;
+      cell[k] = kept ? y * X + x : -1;
+      if (kept) atomicAdd(s_hist + (cell[k] >> low_bits), 1u);
+    }
+    if (vec && p0 + 3 < num_points) {
+      *reinterpret_cast<int4 *>(cell_of_point + gp0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (p0 + k < num_points) cell_of_point[gp0 + k] = cell[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += kSortThreads)
+    hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+bucket_sort_kernel(const int32_t *__restrict__ keys, const int32_t *__restrict__ ids,
+                   const uint32_t *__restrict__ scanned, int bins_hi, int tiles_per_sample, int low_bits,
+                   int32_t cells_per_sample, int batch, int32_t *__restrict__ cell_start,
+                   int32_t *__restrict__ sorted_ids, int32_t *__restrict__ sorted_cells) {
+  __shared__ uint32_t s_run[256];                  // next output position of every low-bits bin
+  __shared__ uint32_t s_cnt[kSortWarps][256];      // per-warp counts of the current chunk
+  __shared__ uint32_t s_warp_tot[kSortWarps];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int nlow = 1 << low_bits, lmask = nlow - 1;
+  const int64_t slot = ((int64_t)b * bins_hi + h) * tiles_per_sample;
+  const uint32_t begin = scanned[slot], end = scanned[slot + tiles_per_sample];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // (i) histogram of the low bits over the whole bucket
+  s_run[threadIdx.x] = 0u;
+  __syncthreads();
+  for (uint32_t i = begin + threadIdx.x; i < end; i += kSortThreads) atomicAdd(&s_run[keys[i] & lmask], 1u);
+  __syncthreads();
+  // (ii) exclusive scan of the 256 bins (one element per thread) -> CSR offsets of the bucket's cells
+  {
+    const uint32_t v = s_run[threadIdx.x];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t base = begin;
+    for (int w = 0; w < warp; ++w) base += s_warp_tot[w];
+    const uint32_t excl = base + incl - v;
+    __syncthreads();
+    s_run[threadIdx.x] = excl;
+    const int cell = (h << low_bits) + threadIdx.x;
+    if ((int)threadIdx.x < nlow && cell < cells_per_sample) cell_start[(int64_t)b * cells_per_sample + cell] = (int32_t)excl;
+    if (h == 0 && b == 0 && threadIdx.x == 0)
+      cell_start[(int64_t)batch * cells_per_sample] = (int32_t)scanned[(int64_t)batch * bins_hi * tiles_per_sample];
+  }
+  __syncthreads();
+  // (iii) stable placement, one chunk of kSortTile elements at a time, element order (warp, round, lane)
+  for (uint32_t chunk = begin; chunk < end; chunk += kSortTile) {
+    for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0u;
+    __syncthreads();
+    uint32_t *cnt = s_cnt[warp];
+    const uint32_t warp_begin = chunk + warp * (kSortItems * 32);
+    int32_t key[kSortItems], id[kSortItems];
+    uint32_t rank[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const uint32_t idx = warp_begin + r * 32 + lane;
+      const bool in_range = idx < end;
+      key[r] = in_range ? keys[idx] : -1;
+      id[r] = in_range ? ids[idx] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const bool valid = key[r] >= 0;
+      const uint32_t digit = valid ? (uint32_t)(key[r] & lmask) : 256u;
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (valid && lane == leader) {
+        base = cnt[digit];
+        cnt[digit] = base + __popc(peers);
+      }
+      base = __shfl_sync(0xffffffffu, base, leader);
+      rank[r] = base + __popc(peers & ((1u << lane) - 1u));
+      __syncwarp();
+    }
+    __syncthreads();
+    {   // per-bin: turn the warps' counts into starting positions, advance the running offset
+      const int bin = threadIdx.x;
+      uint32_t run = s_run[bin];
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t t = s_cnt[w][bin];
+        s_cnt[w][bin] = run;
+        run += t;
+      }
+      s_run[bin] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      if (key[r] >= 0) {
+        const uint32_t pos = cnt[key[r] & lmask] + rank[r];
+        sorted_ids[pos] = id[r];
+        sorted_cells[pos] = b * cells_per_sample + key[r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void pos_memo_kernel(const int32_t *__restrict__ cell_of_point, int64_t num_points,
                                 int64_t total, int X, int32_t *__restrict__ pos_memo) {
   const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,6 +443,24 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
 
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(pb, 0, PL.off_cell_of_point, stream));
+
+  if (sc.msd) {
+    const int low = sc.bits[0], bins_hi = 1 << sc.bits[1];
+    plan_key_msd_kernel<<<grid, kSortThreads, bins_hi * 4, stream>>>(geom, num_points, X, Y, Z, cell_of_point,
+                                                                    hist[0], low, bins_hi, T);
+    BEVPOOL_LAUNCH_CHECK();
+    rc = launch_scan_exclusive(hist[0], hist[0], TL.hist_n[0], tb + TL.off_scan[0], stream);
+    if (rc) return rc;
+    sort_scatter_kernel<true><<<grid, kSortThreads, kSortWarps * bins_hi * 4, stream>>>(
+        cell_of_point, nullptr, keys[0], ids[0], nullptr, (int32_t)cells, hist[0], hist[0], bins_hi, num_points,
+        low, bins_hi, T);
+    BEVPOOL_LAUNCH_CHECK();
+    bucket_sort_kernel<<<dim3(bins_hi, batch), kSortThreads, 0, stream>>>(
+        keys[0], ids[0], hist[0], bins_hi, T, low, (int32_t)cells, batch, reinterpret_cast<int32_t *>(cell_start),
+        sorted_ids, sorted_cells);
+    BEVPOOL_LAUNCH_CHECK();
+    return BEVPOOL_OK;
+  }
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(cell_start, 0, ((size_t)batch * cells + 1) * 4, stream));
 
   const int bins0 = 1 << sc.bits[0];
