@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'aim'])
+    ap.add_argument('--e2e-chunk', type=int, default=4, help='frames per chunk of the host-buffer pipeline')
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip e2e / cpu / reference-CUDA side measurements')
     args = ap.parse_args()
@@ -269,12 +270,42 @@ def main():
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    from mm_training_b200.sharding import aggregate_throughput
+    value, total_ms, total_frames = aggregate_throughput(B * args.steps, ev0.elapsed_time(ev1), device=dev)
     ms_per_step = total_ms / args.steps
-    value = world * B * args.steps / (total_ms / 1e3)
+
+    # ---- e2e on EVERY rank (host pinned buffers in/out, PCIe inside the timed region), max over ranks
+    e2e = None
+    if not args.no_extras:
+        from mm_training_b200.ops.voxel_pooling.host_pipeline import HostPoolingPipeline
+        h_geom, h_depth, h_ctx, h_go = (t.cpu().pin_memory() for t in (geom, depth, ctx, go))
+        X, Y, _ = vn
+        h_out = torch.empty(B, cfg.output_channels, Y, X).pin_memory()
+        h_gd, h_gc = torch.empty_like(h_depth).pin_memory(), torch.empty_like(h_ctx).pin_memory()
+        pipe = HostPoolingPipeline(cfg.num_cams, geom.shape, depth.shape, ctx.shape, vn,
+                                   chunk_frames=max(1, min(args.e2e_chunk, B)), device=dev)
+        e2e_iters = max(5, min(args.steps, 20))
+        for _ in range(3):
+            pipe.run(h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc)
+        torch.cuda.synchronize()
+        assert torch.allclose(h_out.to(dev), out.permute(0, 3, 1, 2), rtol=1e-5, atol=1e-6)   # same results as the device path
+        if world > 1:
+            dist.barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(e2e_iters):
+            pipe.run(h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc)
+        eb.record()
+        torch.cuda.synchronize()
+        e2e_value, e2e_total_ms, _ = aggregate_throughput(B * e2e_iters, ea.elapsed_time(eb), device=dev)
+        h2d = sum(t.numel() * t.element_size() for t in (h_geom, h_depth, h_ctx, h_go))
+        d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gd, h_gc))
+        e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+               'ms_per_step': e2e_total_ms / e2e_iters, 'steps': e2e_iters,
+               'api': 'HostPoolingPipeline.run: voxel_pooling_fused(...).backward(...) on pinned host tensors, '
+                      f'{pipe.chunk}-frame chunks on 3 streams (H2D | plan+fwd+bwd | D2H); bytes are per GPU',
+               'pcie_gbs_per_gpu': (h2d + d2h) / (e2e_total_ms / e2e_iters * 1e-3) / 1e9}
+        del pipe, h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc
 
     if rank != 0:
         if world > 1:
@@ -303,8 +334,16 @@ def main():
     stages['fused_backward_kernel'] = k_bwd
     dom_name, dom = ('fused_backward', k_bwd) if k_bwd[0] >= k_fwd[0] else ('fused_forward', k_fwd)
     achieved = bytes_[dom_name] * B / (dom[0] * 1e-3) / 1e9
+    traffic = None                      # dram__bytes_read+write per launch of that kernel, from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        ent = tj.get(dom_name + '_kernel')
+        if ent and ent.get('frames_per_launch') == B and ent.get('workload') == cfg.name:
+            traffic = ent['dram_bytes_per_launch']
+    except (OSError, ValueError):
+        pass
     roofline = {'bound': 'hbm', 'kernel': dom_name + '_kernel', 'achieved': achieved, 'peak': peak_gbs,
-                'unit': 'GB/s', 'frac': achieved / peak_gbs, 'peak_source': peak_src, 'traffic': None,
+                'unit': 'GB/s', 'frac': achieved / peak_gbs, 'peak_source': peak_src, 'traffic': traffic,
                 'algorithmic_bytes_per_frame': bytes_[dom_name], 'kernel_ms': dom[0],
                 'frac_of_nominal_8TBps': achieved / 8000.0}
     step_gbs = bytes_['step'] * B / (ms_per_step * 1e-3) / 1e9
@@ -320,43 +359,8 @@ def main():
             'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks.summary()}
 
+    line['e2e'] = e2e
     if not args.no_extras and world == 1:
-        # ---- e2e: public autograd API, HOST pinned inputs, H2D + D2H inside the timed region
-        h_geom, h_depth, h_ctx, h_go = (t.cpu().pin_memory() for t in (geom, depth, ctx, go))
-        d_geom, d_depth, d_ctx, d_go = (torch.empty_like(t) for t in (geom, depth, ctx, go))
-        X, Y, _ = vn
-        h_out = torch.empty(B, cfg.output_channels, Y, X).pin_memory()
-        h_gd, h_gc = torch.empty_like(h_depth).pin_memory(), torch.empty_like(h_ctx).pin_memory()
-
-        def e2e_step():
-            d_geom.copy_(h_geom, non_blocking=True)
-            d_depth.copy_(h_depth, non_blocking=True)
-            d_ctx.copy_(h_ctx, non_blocking=True)
-            d_go.copy_(h_go, non_blocking=True)
-            dd = d_depth.detach().requires_grad_(True)
-            cc = d_ctx.detach().requires_grad_(True)
-            o = voxel_pooling_fused(d_geom, dd, cc, vn)
-            o.backward(d_go)
-            h_out.copy_(o.detach(), non_blocking=True)
-            h_gd.copy_(dd.grad, non_blocking=True)
-            h_gc.copy_(cc.grad, non_blocking=True)
-        e2e_iters = max(5, min(args.steps, 20))
-        for _ in range(3):
-            e2e_step()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(e2e_iters):
-            e2e_step()
-        b.record()
-        torch.cuda.synchronize()
-        e2e_ms = a.elapsed_time(b) / e2e_iters
-        h2d = sum(t.numel() * t.element_size() for t in (h_geom, h_depth, h_ctx, h_go))
-        d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gd, h_gc))
-        line['e2e'] = {'value': B / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                       'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms, 'steps': e2e_iters,
-                       'api': 'voxel_pooling_fused(...).backward(...) with pinned host tensors'}
-
         # ---- the reference's own CUDA op on the same GPU (oracle/_ref), same inputs
         try:
             from oracle import ref_cuda_op
@@ -380,8 +384,6 @@ def main():
 
         # ---- CPU baseline: oracle port on the host cores, bounded sample
         line['cpu_baseline'] = run_cpu_baseline(cfg, 2, 3)
-    else:
-        line['e2e'] = None
 
     print(json.dumps(line), flush=True)
     if world > 1:
