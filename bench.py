@@ -162,6 +162,8 @@ def main():
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
     ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'aim'])
     ap.add_argument('--e2e-chunk', type=int, default=4, help='frames per chunk of the host-buffer pipeline')
+    ap.add_argument('--plan', default='runs', choices=['runs', 'points'],
+                    help="what the plan sorts: 'runs' (vertical point runs, two-stage forward) or 'points'")
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip e2e / cpu / reference-CUDA side measurements')
     args = ap.parse_args()
@@ -220,8 +222,15 @@ def main():
     vn = tuple(int(v) for v in vn_t.tolist())
     depth, ctx, go = synthetic.camera_features(cfg, B, device=dev, seed=1 + rank)
 
+    frustum = tuple(geom.shape[1:5]) if args.plan == 'runs' else None
+    probe = build_plan(geom, vn, frustum=frustum)      # eager, once: the run count sizes the scratch rows
+    max_runs = probe.num_sorted if probe.mode == 'runs' else None
+    plan_mode = probe.mode
+    del probe
+
     def step():
-        plan = build_plan(geom, vn)
+        # cold plan every step: cell index + sort are redone from geom_xyz (no sync: max_runs is known)
+        plan = build_plan(geom, vn, frustum=frustum, max_runs=max_runs)
         rows = context_rows_nhwc(ctx)                  # NCHW context -> pixel rows, shared by fwd and bwd
         out = fused_forward(plan, depth, ctx, rows)
         gd, gc = fused_backward(plan, go, depth, ctx, rows)   # grad_context comes back NCHW like ctx
@@ -229,7 +238,7 @@ def main():
 
     plan, out, gd, gc = step()
     torch.cuda.synchronize()
-    kept_per_frame = int(plan.cell_start[-1].item()) / B
+    kept_per_frame = int((plan.cell_of_point >= 0).sum().item()) / B
     bytes_ = algorithmic_bytes(cfg, kept_per_frame)
 
     l0 = _lib.launch_count()
@@ -323,7 +332,7 @@ def main():
 
     # ---- per-kernel timing (CUDA events on the launching stream), same inputs, warm
     stages = {}
-    stages['plan_build'] = time_cuda(lambda: build_plan(geom, vn), 20, 3)
+    stages['plan_build'] = time_cuda(lambda: build_plan(geom, vn, frustum=frustum, max_runs=max_runs), 20, 3)
     stages['fused_forward(+ctx transpose)'] = time_cuda(lambda: fused_forward(plan, depth, ctx), 20, 3)
     stages['fused_backward(+grad transpose)'] = time_cuda(lambda: fused_backward(plan, go, depth, ctx), 20, 3)
     ctx_nhwc = ctx.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
@@ -351,7 +360,8 @@ def main():
             'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': dict(workload, launch='cuda_graph_replay' if graph is not None else 'eager',
-                           kept_points_per_frame=kept_per_frame),
+                           kept_points_per_frame=kept_per_frame, plan=plan_mode,
+                           sorted_entries_per_frame=(max_runs / B if max_runs else kept_per_frame)),
             'roofline': roofline,
             'step_roofline': {'algorithmic_bytes_per_frame': bytes_['step'], 'achieved': step_gbs, 'unit': 'GB/s',
                               'frac': step_gbs / peak_gbs, 'frac_of_nominal_8TBps': step_gbs / 8000.0},

@@ -95,6 +95,40 @@ int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const vo
                            int feat_w, int channels, int num_voxel_x, int num_voxel_y,
                            void *stream);
 
+/* ---- fused op on a RUN plan (fp32, channels in {32, 64, 80, 96, 128}) -------------------------
+ * Same replacement as above (lss_fpn.py:441-464 + the op), restructured around the frustum: a RUN is
+ * a set of vertically adjacent frustum points (same image, depth bin and column; consecutive rows
+ * inside one block of 16 rows) that fall into the same BEV cell -- for a level camera every kept
+ * point of a (depth bin, column) pair.  The plan sorts runs, not points (an order of magnitude fewer),
+ * and the forward never gathers context rows from global memory:
+ *   stage A  run_rows[slot] = sum over the run's rows h of depth[d,h,w] * context[h,w,:]
+ *            (context rows of a 16x4-pixel tile staged in shared memory)
+ *   stage B  out[cell]      = sum of the cell's run rows in slot order (zeros for empty cells, written
+ *            by spare CTAs of stage A while it runs)
+ * bevpool_runplan_build: geom_xyz int32 (B, N, D, H, W, 3); the plan buffer has the layout of a point
+ * plan (cell_of_point is identical; cell_start / sorted_ids / sorted_cells describe RUNS: the first
+ * point of each run, ordered by (cell, point id)) plus run_code int32[B*Np]: the run's slot for the
+ * first point of a run, -2 for its continuation points, -1 for dropped points.
+ * Returns BEVPOOL_E_RANGE when the grid has more than 2^18 or fewer than 2^9 cells per sample (use
+ * the point plan).  run_rows: caller-owned scratch of run_rows_capacity rows of `channels` floats;
+ * capacity must be >= the largest number of runs in any group of BEVPOOL_RUN_CHUNK (default 8)
+ * consecutive samples (default: all) -- the total run count cell_start[B*X*Y] always suffices.
+ * workspace: bevpool_forward_workspace_bytes(channels) bytes, as for the other forward entry points.
+ * The backward entry points above accept a run plan unchanged (they only read cell_of_point).   */
+int bevpool_runplan_sizes(int batch, int64_t num_points, int num_voxel_x, int num_voxel_y,
+                          size_t *plan_bytes, size_t *temp_bytes);
+int bevpool_runplan_build(const int32_t *geom_xyz, int batch, int num_cams, int depth_bins, int feat_h,
+                          int feat_w, int num_voxel_x, int num_voxel_y, int num_voxel_z, void *plan,
+                          void *temp, void *stream);
+int bevpool_runplan_views(const void *plan, int batch, int64_t num_points, int num_voxel_x,
+                          int num_voxel_y, const int32_t **cell_of_point, const int32_t **cell_start,
+                          const int32_t **sorted_ids, const int32_t **sorted_cells,
+                          const int32_t **run_code);
+int bevpool_fused_forward_runs(const void *plan, const void *depth, const void *context_nhwc,
+                               void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
+                               int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
+                               void *run_rows, int64_t run_rows_capacity, void *workspace, void *stream);
+
 /* ---- gradient layout: grad_out (B, C, Y, X) contiguous -> rows (B, Y, X, C) --------------
  * Only rows of cells that received a point are written (the backward kernels read no
  * others); the rest of `rows_nhwc` is left untouched.                                 */

@@ -38,6 +38,10 @@ _SIGNATURES = {
     'bevpool_backward': [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _vp],
     'bevpool_fused_forward': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp],
     'bevpool_fused_backward': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'bevpool_runplan_sizes': [_i, _i64, _i, _i, _szp, _szp],
+    'bevpool_runplan_build': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    'bevpool_runplan_views': [_vp, _i, _i64, _i, _i] + [ctypes.POINTER(_vp)] * 5,
+    'bevpool_fused_forward_runs': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp],
     'bevpool_grad_rows': [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _vp],
     'bevpool_transpose': [_vp, _vp, _i, _i, _i64, _i64, _vp],
     'bevvox_temp_bytes': [_i, _i64, _i, _i, _szp],

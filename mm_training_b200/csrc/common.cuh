@@ -72,6 +72,22 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+struct FastDiv {          // exact n / d for 0 <= n < 2^31 (round-up magic, 64-bit product)
+  uint32_t mul, shift, div;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.shift = 31 + s;
+  f.mul = (uint32_t)((1ull << f.shift) / d + 1ull);
+  f.div = d;
+  return f;
+}
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
+  return (uint32_t)(((uint64_t)n * f.mul) >> f.shift);
+}
+
 // ---- plan layout -------------------------------------------------------------------
 // A plan is one caller-owned buffer:
 //   header (256 B) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
@@ -80,7 +96,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // sorted_cells[k] its global output row b*G + cell; only the first K = cell_start[B*G] entries
 // of both are defined.
 struct PlanLayout {
-  size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, bytes;
+  size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, off_run_code, bytes;
 };
 struct PlanHeader {       // written by the device at build time
   int32_t magic, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
@@ -89,7 +105,15 @@ struct PlanHeader {       // written by the device at build time
 };
 constexpr int32_t kPlanMagic = 0x42455631;  // "BEV1"
 
-__host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points, int X, int Y) {
+// Run plan (fused op only): the sorted entries are RUNS, not points.  A run is a maximal set of
+// vertically adjacent frustum points (same image, depth bin and column, consecutive rows h inside one
+// block of kRunHB rows) that fall into the same BEV cell; for a level camera that is every kept point
+// of a (depth bin, column) pair.  run_code int32[B*Np]: slot (position in the sorted run list) for
+// the first point of a run, kRunCont for its continuation points, kRunDropped for dropped points.
+constexpr int kRunHB = 16;
+constexpr int32_t kRunDropped = -1, kRunCont = -2;
+
+__host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points, int X, int Y, bool runs = false) {
   PlanLayout L;
   const size_t P = (size_t)batch * (size_t)num_points;
   const size_t G = (size_t)batch * (size_t)X * (size_t)Y;
@@ -98,12 +122,14 @@ __host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points,
   L.off_cell_start = o;    o = align_up(o + (G + 1) * 4, 256);
   L.off_sorted_ids = o;    o = align_up(o + P * 4, 256);
   L.off_sorted_cells = o;  o = align_up(o + P * 4 + 64, 256);   // + slack: readers prefetch a batch past K
+  L.off_run_code = o;
+  if (runs) o = align_up(o + P * 4, 256);
   L.bytes = o;
   return L;
 }
 
 struct PlanView {
-  const int32_t *cell_of_point, *cell_start, *sorted_ids, *sorted_cells;
+  const int32_t *cell_of_point, *cell_start, *sorted_ids, *sorted_cells, *run_code;
 };
 inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X, int Y) {
   PlanLayout L = plan_layout(batch, num_points, X, Y);
@@ -111,8 +137,16 @@ inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X
   return PlanView{reinterpret_cast<const int32_t *>(b + L.off_cell_of_point),
                   reinterpret_cast<const int32_t *>(b + L.off_cell_start),
                   reinterpret_cast<const int32_t *>(b + L.off_sorted_ids),
-                  reinterpret_cast<const int32_t *>(b + L.off_sorted_cells)};
+                  reinterpret_cast<const int32_t *>(b + L.off_sorted_cells),
+                  reinterpret_cast<const int32_t *>(b + L.off_run_code)};
 }
+
+// pool_bwd.cu: tile kernel of the fused backward (fp32, g8 channel counts)
+int launch_fused_backward_tile(const int32_t *cell_of_point, const float *grad_rows, const float *depth,
+                               const float *ctx_nhwc, float *grad_depth, float *grad_ctx_nhwc, int batch,
+                               int num_cams, int D, int H, int W, int C, int64_t cells_per_sample,
+                               cudaStream_t s);
+bool fused_backward_tile_supported(int C);
 
 inline int check_plan_dims(int batch, int64_t num_points, int X, int Y) {
   if (batch <= 0 || num_points <= 0 || X <= 0 || Y <= 0) return BEVPOOL_E_ARG;

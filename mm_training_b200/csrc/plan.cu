@@ -35,7 +35,7 @@ static SortConfig sort_config(int64_t cells_per_sample) {
   while ((1ll << nbits) < cells_per_sample) ++nbits;
   SortConfig c;
   c.msd = false;
-  if (nbits > 8 && nbits <= 16) {
+  if (nbits > 8 && nbits <= 18) {
     c.msd = true;
     c.npass = 2;
     c.bits[0] = 8;          c.shift[0] = 0;
@@ -290,11 +290,95 @@ plan_key_msd_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X,
     hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
 }
 
+// ---- run plans: same as plan_key_msd_kernel, but only the FIRST point of every run enters the sort ----
+// Points are enumerated (n, d, h, w); the vertical predecessor of point p is p - W.  A kept point starts
+// a run when it is the first row of a kRunHB-row block or its predecessor lies in another cell (or was
+// dropped).  run_code: cell id for run heads (replaced by the run's slot once the sort has placed it),
+// kRunCont for continuation points, kRunDropped for dropped points.
+__device__ __forceinline__ int cell_of_xyz(int x, int y, int z, int X, int Y, int Z) {
+  // reference bounds test, voxel_pooling_forward_cuda.cu:24; z gates only (:32-33)
+  return (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) ? y * X + x : -1;
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+plan_key_runs_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
+                     int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code,
+                     uint32_t *__restrict__ hist, int low_bits, int bins, int tiles_per_sample,
+                     FastDiv div_w, FastDiv div_h) {
+  extern __shared__ uint32_t s_hist[];
+  const int b = blockIdx.y, tile = blockIdx.x;
+  for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const int64_t sample_base = (int64_t)b * num_points;
+  const int64_t tile_base = (int64_t)tile * kSortTile;
+  const int W = (int)div_w.div, H = (int)div_h.div;
+  const bool vec = ((sample_base + tile_base) & 3) == 0 && (W & 3) == 0;   // quads are 16-byte aligned and stay in one row
+#pragma unroll
+  for (int q = 0; q < kSortItems / 4; ++q) {
+    const int64_t p0 = tile_base + ((int64_t)q * kSortThreads + threadIdx.x) * 4;
+    if (p0 >= num_points) continue;
+    const int64_t gp0 = sample_base + p0;
+    int cell[4], code[4];
+    if (vec && p0 + 3 < num_points) {
+      const int4 *src = reinterpret_cast<const int4 *>(geom + gp0 * 3);
+      const int4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+      cell[0] = cell_of_xyz(a0.x, a0.y, a0.z, X, Y, Z);
+      cell[1] = cell_of_xyz(a0.w, a1.x, a1.y, X, Y, Z);
+      cell[2] = cell_of_xyz(a1.z, a1.w, a2.x, X, Y, Z);
+      cell[3] = cell_of_xyz(a2.y, a2.z, a2.w, X, Y, Z);
+      const uint32_t row = fastdiv((uint32_t)p0, div_w);
+      const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
+      int pcell[4] = {-1, -1, -1, -1};
+      if ((h % kRunHB) != 0 && (cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0 || cell[3] >= 0)) {
+        const int4 *ps = reinterpret_cast<const int4 *>(geom + (gp0 - W) * 3);   // the row above: an L1/L2 hit
+        const int4 b0 = __ldg(ps), b1 = __ldg(ps + 1), b2 = __ldg(ps + 2);
+        pcell[0] = cell_of_xyz(b0.x, b0.y, b0.z, X, Y, Z);
+        pcell[1] = cell_of_xyz(b0.w, b1.x, b1.y, X, Y, Z);
+        pcell[2] = cell_of_xyz(b1.z, b1.w, b2.x, X, Y, Z);
+        pcell[3] = cell_of_xyz(b2.y, b2.z, b2.w, X, Y, Z);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        code[k] = cell[k] < 0 ? kRunDropped : (pcell[k] != cell[k] ? cell[k] : kRunCont);
+      *reinterpret_cast<int4 *>(cell_of_point + gp0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
+      *reinterpret_cast<int4 *>(run_code + gp0) = make_int4(code[0], code[1], code[2], code[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cell[k] = -1;
+        code[k] = kRunDropped;
+        if (p0 + k >= num_points) continue;
+        const int32_t *g = geom + (gp0 + k) * 3;
+        cell[k] = cell_of_xyz(__ldg(g), __ldg(g + 1), __ldg(g + 2), X, Y, Z);
+        if (cell[k] >= 0) {
+          const uint32_t row = fastdiv((uint32_t)(p0 + k), div_w);
+          const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
+          int pc = -1;
+          if ((h % kRunHB) != 0) {
+            const int32_t *pg = g - (int64_t)W * 3;
+            pc = cell_of_xyz(__ldg(pg), __ldg(pg + 1), __ldg(pg + 2), X, Y, Z);
+          }
+          code[k] = pc != cell[k] ? cell[k] : kRunCont;
+        }
+        cell_of_point[gp0 + k] = cell[k];
+        run_code[gp0 + k] = code[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (code[k] >= 0) atomicAdd(s_hist + (code[k] >> low_bits), 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += kSortThreads)
+    hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
+}
+
 __global__ void __launch_bounds__(kSortThreads)
 bucket_sort_kernel(const int32_t *__restrict__ keys, const int32_t *__restrict__ ids,
                    const uint32_t *__restrict__ scanned, int bins_hi, int tiles_per_sample, int low_bits,
                    int32_t cells_per_sample, int batch, int32_t *__restrict__ cell_start,
-                   int32_t *__restrict__ sorted_ids, int32_t *__restrict__ sorted_cells) {
+                   int32_t *__restrict__ sorted_ids, int32_t *__restrict__ sorted_cells,
+                   int32_t *__restrict__ slot_of_id /* run plans: run_code[first point] = slot, else NULL */) {
   __shared__ uint32_t s_run[256];                  // next output position of every low-bits bin
   __shared__ uint32_t s_cnt[kSortWarps][256];      // per-warp counts of the current chunk
   __shared__ uint32_t s_warp_tot[kSortWarps];
@@ -380,6 +464,7 @@ bucket_sort_kernel(const int32_t *__restrict__ keys, const int32_t *__restrict__
         const uint32_t pos = cnt[key[r] & lmask] + rank[r];
         sorted_ids[pos] = id[r];
         sorted_cells[pos] = b * cells_per_sample + key[r];
+        if (slot_of_id) slot_of_id[id[r]] = (int32_t)pos;
       }
     }
     __syncthreads();
@@ -457,7 +542,7 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
     BEVPOOL_LAUNCH_CHECK();
     bucket_sort_kernel<<<dim3(bins_hi, batch), kSortThreads, 0, stream>>>(
         keys[0], ids[0], hist[0], bins_hi, T, low, (int32_t)cells, batch, reinterpret_cast<int32_t *>(cell_start),
-        sorted_ids, sorted_cells);
+        sorted_ids, sorted_cells, nullptr);
     BEVPOOL_LAUNCH_CHECK();
     return BEVPOOL_OK;
   }
@@ -518,6 +603,77 @@ extern "C" int bevpool_plan_views(const void *plan, int batch, int64_t num_point
   if (cell_of_point) *cell_of_point = v.cell_of_point;
   if (cell_start) *cell_start = v.cell_start;
   if (sorted_ids) *sorted_ids = v.sorted_ids;
+  return BEVPOOL_OK;
+}
+
+// ---- run plan (fused op): see common.cuh.  Same pipeline as the MSD point plan, on run heads only. ----
+extern "C" int bevpool_runplan_sizes(int batch, int64_t num_points, int X, int Y, size_t *plan_bytes,
+                                     size_t *temp_bytes) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
+  if (!sort_config((int64_t)X * Y).msd) return BEVPOOL_E_RANGE;   // grids of 2^9 .. 2^18 cells per sample
+  *plan_bytes = plan_layout(batch, num_points, X, Y, true).bytes;
+  *temp_bytes = temp_layout(batch, num_points, X, Y).bytes;
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cams, int depth_bins, int feat_h,
+                                     int feat_w, int X, int Y, int Z, void *plan, void *temp, void *stream_) {
+  if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  const int64_t num_points = (int64_t)num_cams * depth_bins * feat_h * feat_w;
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!geom || !plan || !temp || Z <= 0) return BEVPOOL_E_ARG;
+  if (!aligned16(plan) || !aligned16(temp) || !aligned16(geom)) return BEVPOOL_E_ALIGN;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t cells = (int64_t)X * Y;
+  const SortConfig sc = sort_config(cells);
+  if (!sc.msd) return BEVPOOL_E_RANGE;
+  const PlanLayout PL = plan_layout(batch, num_points, X, Y, true);
+  const TempLayout TL = temp_layout(batch, num_points, X, Y);
+  char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
+  int32_t *cell_of_point = reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point);
+  int32_t *cell_start = reinterpret_cast<int32_t *>(pb + PL.off_cell_start);
+  int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
+  int32_t *sorted_cells = reinterpret_cast<int32_t *>(pb + PL.off_sorted_cells);
+  int32_t *run_code = reinterpret_cast<int32_t *>(pb + PL.off_run_code);
+  uint32_t *hist = reinterpret_cast<uint32_t *>(tb + TL.off_hist[0]);
+  int32_t *keys = reinterpret_cast<int32_t *>(tb + TL.off_keys[0]);
+  int32_t *ids = reinterpret_cast<int32_t *>(tb + TL.off_ids[0]);
+  const int T = TL.tiles_per_sample;
+  const dim3 grid(T, batch);
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(pb, 0, PL.off_cell_of_point, stream));
+  const int low = sc.bits[0], bins_hi = 1 << sc.bits[1];
+  plan_key_runs_kernel<<<grid, kSortThreads, bins_hi * 4, stream>>>(
+      geom, num_points, X, Y, Z, cell_of_point, run_code, hist, low, bins_hi, T,
+      make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h));
+  BEVPOOL_LAUNCH_CHECK();
+  rc = launch_scan_exclusive(hist, hist, TL.hist_n[0], tb + TL.off_scan[0], stream);
+  if (rc) return rc;
+  sort_scatter_kernel<true><<<grid, kSortThreads, kSortWarps * bins_hi * 4, stream>>>(
+      run_code, nullptr, keys, ids, nullptr, (int32_t)cells, hist, hist, bins_hi, num_points, low, bins_hi, T);
+  BEVPOOL_LAUNCH_CHECK();
+  bucket_sort_kernel<<<dim3(bins_hi, batch), kSortThreads, 0, stream>>>(
+      keys, ids, hist, bins_hi, T, low, (int32_t)cells, batch, cell_start, sorted_ids, sorted_cells, run_code);
+  BEVPOOL_LAUNCH_CHECK();
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_runplan_views(const void *plan, int batch, int64_t num_points, int X, int Y,
+                                     const int32_t **cell_of_point, const int32_t **cell_start,
+                                     const int32_t **sorted_ids, const int32_t **sorted_cells,
+                                     const int32_t **run_code) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan) return BEVPOOL_E_ARG;
+  const PlanView v = plan_view(plan, batch, num_points, X, Y);
+  if (cell_of_point) *cell_of_point = v.cell_of_point;
+  if (cell_start) *cell_start = v.cell_start;
+  if (sorted_ids) *sorted_ids = v.sorted_ids;
+  if (sorted_cells) *sorted_cells = v.sorted_cells;
+  if (run_code) *run_code = v.run_code;
   return BEVPOOL_OK;
 }
 

@@ -426,15 +426,15 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
       if (u == 2) {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 2><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
+                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
       } else {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 4><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
+                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
       }
       BEVPOOL_LAUNCH_CHECK();
       BEVPOOL_G8_DISPATCH(C, (pool_forward_fixup_kernel<NV2><<<(unsigned)ceil_div64((int64_t)slices * 8, 128), 128, 0, s>>>(
-                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, total_cells, slices)));
+                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, (int64_t)0, total_cells, slices)));
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
@@ -505,6 +505,8 @@ static int fused_backward_t(const void *plan, const void *grad, const void *dept
   const int64_t cells = (int64_t)X * Y;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
+      if (env_int("BEVPOOL_BW_KERNEL", 1) == 1 && fused_backward_tile_supported(C))   // 1: tile kernel with staged gradient rows (pool_bwd.cu); 0: per-group gather
+        return launch_fused_backward_tile(pv.cell_of_point, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
       const int hg = env_int("BEVPOOL_BW_HG", 2) == 1 ? 1 : 2;
       const int64_t tiles_h = ceil_div64(H, 4 * hg), tiles_w = ceil_div64(W, kBwTW);
       const int64_t ctas = (int64_t)B * N * tiles_h * tiles_w;

@@ -83,22 +83,6 @@ __device__ __forceinline__ void add_row(float (&acc)[NREG], const float (&v)[NRE
   }
 }
 
-struct FastDiv {          // exact n / d for 0 <= n < 2^31 (round-up magic, 64-bit product)
-  uint32_t mul, shift, div;
-};
-inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f;
-  uint32_t s = 0;
-  while ((1ull << s) < d) ++s;
-  f.shift = 31 + s;
-  f.mul = (uint32_t)((1ull << f.shift) / d + 1ull);
-  f.div = d;
-  return f;
-}
-__device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
-  return (uint32_t)(((uint64_t)n * f.mul) >> f.shift);
-}
-
 // ---- forward: even-share segmented reduction over the plan's sorted point list ----------------
 // The K kept points, sorted by (cell, point id), are cut into S equal slices (S = 4 x the number
 // of warps of a grid that is exactly resident: no scheduling rounds, no tail, and near-camera
@@ -119,25 +103,30 @@ __host__ __device__ __forceinline__ int fwd_slice_len(int K, int num_slices) {
   return L < 8 ? 8 : L;
 }
 
-template <int NV2, bool kFused, int U>
+// kIdent (run plans, stage B): entry k of the list IS row k - e0 of `rows` (the run rows are stored in
+// slot order), so no id array is read.  The kernel works on the cells [cell_base, cell_base + total_cells)
+// and on the list entries [cell_start[cell_base], cell_start[cell_base + total_cells)); fill_period == 0
+// launches no zero-fill CTAs (the caller filled the empty cells elsewhere).
+template <int NV2, bool kFused, int U, bool kIdent = false>
 __global__ void __launch_bounds__(kFwWarpsPerCta * 32)
 pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_ids,
                           const int32_t *__restrict__ sorted_cells, const float *__restrict__ rows,
                           const float *__restrict__ depth, float *__restrict__ out,
-                          float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t total_cells,
-                          FastDiv div_dhw, FastDiv div_hw, int fill_period, int exp_mask, int exp_flags) {
+                          float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t cell_base,
+                          int64_t total_cells, FastDiv div_dhw, FastDiv div_hw, int fill_period, int exp_mask,
+                          int exp_flags) {
   constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4;
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3, warp = threadIdx.x >> 5;
   // Roles: every `fill_period`-th CTA zero-fills the empty cells of the grid (DRAM-write bound) while
   // the other CTAs, co-resident on the same SMs, run the latency-bound reduction.
   const int bid = blockIdx.x;
-  if (bid % fill_period == fill_period - 1) {
+  if (fill_period > 0 && bid % fill_period == fill_period - 1) {
     if (exp_flags & 1) return;
     const int fwarp = (bid / fill_period) * kFwWarpsPerCta + warp;
     const int nfw = (gridDim.x / fill_period) * kFwWarpsPerCta;
     const int64_t per_warp = ((total_cells + nfw - 1) / nfw + 31) & ~(int64_t)31;
-    const int64_t c_begin = fwarp * per_warp, c_end = min(total_cells, c_begin + per_warp);
+    const int64_t c_begin = cell_base + fwarp * per_warp, c_end = min(cell_base + total_cells, c_begin + per_warp);
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     auto load_cs = [&](int64_t c0, int &cs, int &ce) {
       cs = ce = 0;
@@ -164,23 +153,24 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
     }
     return;
   }
-  const int rid = bid - bid / fill_period;
+  const int rid = fill_period > 0 ? bid - bid / fill_period : bid;
   const int wglobal = rid * kFwWarpsPerCta + warp;
-  const int nwarps = (gridDim.x - gridDim.x / fill_period) * kFwWarpsPerCta;
+  const int nwarps = (fill_period > 0 ? gridDim.x - gridDim.x / fill_period : gridDim.x) * kFwWarpsPerCta;
 
-  // ---- my slice of the sorted point list
+  // ---- my slice of the sorted list (entries [e0, K) of it)
   if (exp_flags & 2) return;
-  const int K = __ldg(cell_start + total_cells);
-  const int L = fwd_slice_len(K, nwarps * 4);
+  const int e0 = __ldg(cell_start + cell_base);
+  const int K = __ldg(cell_start + cell_base + total_cells);
+  const int L = fwd_slice_len(K - e0, nwarps * 4);
   const int s = wglobal * 4 + grp;
-  const int lo = (int)min((int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
+  const int lo = (int)min((int64_t)e0 + (int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
   const int n0 = __shfl_sync(kFull, hi - lo, 0);            // group 0 has the warp's longest slice
   if (n0 <= 0) return;
   const bool guard = __any_sync(kFull, hi - lo != L);       // only the warp(s) at the very end of the list
   const int nb = (n0 + 7) >> 3;
 
   const char *rows_b = opaque_ptr(rows);
-  auto load_id = [&](int idx) -> int { return idx < K ? ldg_stream_i32(sorted_ids + idx) : -1; };
+  auto load_id = [&](int idx) -> int { return idx < K ? (kIdent ? idx - e0 : ldg_stream_i32(sorted_ids + idx)) : -1; };
   auto load_key = [&](int idx) -> int { return idx < K ? ldg_stream_i32(sorted_cells + idx) : -1; };
   auto finish_entry = [&](int id, unsigned &erow, float &ed) {
     erow = 0u;
@@ -207,7 +197,7 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
   int key_c = load_key(lo + l8), key_n = load_key(lo + 8 + l8), key_nn;
   int id_n = load_id(lo + 8 + l8), id_nn;
   finish_entry(load_id(lo + l8), row_c, d_c);
-  const int prev_key = lo > 0 ? __ldg(sorted_cells + lo - 1) : -1;
+  const int prev_key = lo > e0 ? __ldg(sorted_cells + lo - 1) : -1;
   const int first_key = __shfl_sync(kFull, key_c, 0, 8);   // (all lanes: never short-circuit around a shuffle)
   bool in_head = hi > lo && prev_key == first_key;         // slice starts inside a cell
   unsigned last_gm = 0u;
@@ -271,21 +261,22 @@ template <int NV2>
 __global__ void __launch_bounds__(128)
 pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_cells,
                           const float *__restrict__ ws_head, const float *__restrict__ ws_tail,
-                          float *__restrict__ out, int64_t total_cells, int num_slices) {
+                          float *__restrict__ out, int64_t cell_base, int64_t total_cells, int num_slices) {
   constexpr int C = 16 * NV2, NREG = 2 * NV2;
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l8 = threadIdx.x & 7;
   if (s >= num_slices) return;
-  const int K = __ldg(cell_start + total_cells);
-  const int L = fwd_slice_len(K, num_slices);
-  const int lo = (int)min((int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
+  const int e0 = __ldg(cell_start + cell_base);
+  const int K = __ldg(cell_start + cell_base + total_cells);
+  const int L = fwd_slice_len(K - e0, num_slices);
+  const int lo = (int)min((int64_t)e0 + (int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
   if (hi <= lo || hi >= K) return;
   const int key = __ldg(sorted_cells + hi - 1);
   if (key != __ldg(sorted_cells + hi)) return;                      // slice ends on a cell boundary
-  if (lo > 0 && __ldg(sorted_cells + lo - 1) == key) return;        // cell began in an earlier slice
+  if (lo > e0 && __ldg(sorted_cells + lo - 1) == key) return;       // cell began in an earlier slice
   float acc[NREG], v[NREG];
   g8_load_row<NV2, false>(reinterpret_cast<const char *>(ws_tail + (size_t)s * C), l8, acc);
   for (int t = s + 1; t < num_slices; ++t) {
-    const int tlo = t * L, thi = min(tlo + L, K);                   // tlo < K because slice t-1 ended mid-cell
+    const int tlo = e0 + t * L, thi = min(tlo + L, K);              // tlo < K because slice t-1 ended mid-cell
     g8_load_row<NV2, false>(reinterpret_cast<const char *>(ws_head + (size_t)t * C), l8, v);
 #pragma unroll
     for (int r = 0; r < NREG; ++r) acc[r] += v[r];

@@ -17,6 +17,7 @@ gradient instead of mutating a tensor saved in forward; errors raise instead of 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple, Union
 
 import torch
@@ -35,11 +36,22 @@ def _voxel_num_ints(voxel_num: VoxelNum) -> Tuple[int, int, int]:
     return x, y, z
 
 
-class PoolingPlan:
-    """Cell index of every point + kept points sorted by BEV cell (CSR).  Depends only on
-    ``geom_xyz`` and ``voxel_num``: reuse it while the camera geometry is unchanged."""
+RUN_CHANNELS = (32, 64, 80, 96, 128)     # channel counts of the fp32 run-plan kernels (csrc/pool_runs.cu)
 
-    def __init__(self, geom_xyz: torch.Tensor, voxel_num: VoxelNum):
+
+class PoolingPlan:
+    """Cell index of every point + the kept points sorted by BEV cell (CSR).  Depends only on
+    ``geom_xyz`` and ``voxel_num``: reuse it while the camera geometry is unchanged.
+
+    ``frustum=(N, D, H, W)`` asks for a RUN plan (fused op only): vertically adjacent points of one
+    (image, depth bin, column) that share a BEV cell are sorted as one entry -- 11x fewer entries at
+    the aiMotive shape -- and ``run_code`` maps every point to its run.  ``mode`` says which kind
+    was built ('runs' needs a grid of 2^9..2^18 cells per sample, else it falls back to 'points').
+    ``max_runs``: upper bound of the run count known to the caller (e.g. from an earlier plan of the
+    same rig); without it the first fused forward reads the count back (one D2H sync)."""
+
+    def __init__(self, geom_xyz: torch.Tensor, voxel_num: VoxelNum, frustum: Optional[Sequence[int]] = None,
+                 max_runs: Optional[int] = None):
         _lib.require_cuda(geom_xyz)
         if geom_xyz.dtype != torch.int32:
             raise TypeError(f'geom_xyz must be int32 (got {geom_xyz.dtype})')
@@ -49,17 +61,35 @@ class PoolingPlan:
         self.batch = int(geom_xyz.shape[0])
         self.num_points = int(geom_xyz.numel() // (3 * self.batch))
         self.device = geom_xyz.device
+        self.mode = 'points'
+        self.frustum = None
+        self._num_runs = max_runs
         X, Y, Z = self.voxel_num
         L = _lib.lib()
         pb, tb = ctypes.c_size_t(), ctypes.c_size_t()
-        _lib.check(L.bevpool_plan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
-                   'bevpool_plan_sizes')
+        if frustum is not None:
+            N, D, H, W = (int(v) for v in frustum)
+            assert N * D * H * W == self.num_points, 'frustum shape does not match geom_xyz'
+            rc = L.bevpool_runplan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb))
+            if rc == 0 and geom_xyz.data_ptr() % 16 == 0:
+                self.mode, self.frustum = 'runs', (N, D, H, W)
+            elif rc != -2:
+                _lib.check(rc, 'bevpool_runplan_sizes')
+        if self.mode == 'points':
+            _lib.check(L.bevpool_plan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
+                       'bevpool_plan_sizes')
         with torch.cuda.device(self.device):
             self.buffer = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
             temp = torch.empty(tb.value, dtype=torch.uint8, device=self.device)
-            _lib.check(L.bevpool_plan_build(geom_xyz.data_ptr(), self.batch, self.num_points, X, Y, Z,
-                                            self.buffer.data_ptr(), temp.data_ptr(),
-                                            _lib.stream_ptr(self.device)), 'bevpool_plan_build')
+            if self.mode == 'runs':
+                N, D, H, W = self.frustum
+                _lib.check(L.bevpool_runplan_build(geom_xyz.data_ptr(), self.batch, N, D, H, W, X, Y, Z,
+                                                   self.buffer.data_ptr(), temp.data_ptr(),
+                                                   _lib.stream_ptr(self.device)), 'bevpool_runplan_build')
+            else:
+                _lib.check(L.bevpool_plan_build(geom_xyz.data_ptr(), self.batch, self.num_points, X, Y, Z,
+                                                self.buffer.data_ptr(), temp.data_ptr(),
+                                                _lib.stream_ptr(self.device)), 'bevpool_plan_build')
         # temp is released to the caching allocator here; stream-ordered reuse keeps this safe
 
     @property
@@ -68,15 +98,17 @@ class PoolingPlan:
 
     def _views(self):
         X, Y, _ = self.voxel_num
-        a, b, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-        _lib.check(_lib.lib().bevpool_plan_views(self.ptr, self.batch, self.num_points, X, Y,
-                                                 ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
-                   'bevpool_plan_views')
+        ptrs = [ctypes.c_void_p() for _ in range(5)]
+        _lib.check(_lib.lib().bevpool_runplan_views(self.ptr, self.batch, self.num_points, X, Y,
+                                                    *[ctypes.byref(q) for q in ptrs]), 'bevpool_runplan_views')
         base = self.ptr
         as_i32 = self.buffer.view(torch.int32)
         P, G = self.batch * self.num_points, self.batch * X * Y
-        o = lambda p: (p.value - base) // 4
-        return (as_i32[o(a):o(a) + P], as_i32[o(b):o(b) + G + 1], as_i32[o(c):o(c) + P])
+        o = lambda q: (q.value - base) // 4
+        a, b, c, d, e = ptrs
+        views = [as_i32[o(a):o(a) + P], as_i32[o(b):o(b) + G + 1], as_i32[o(c):o(c) + P], as_i32[o(d):o(d) + P]]
+        views.append(as_i32[o(e):o(e) + P] if self.mode == 'runs' else None)
+        return views
 
     @property
     def cell_of_point(self) -> torch.Tensor:
@@ -90,9 +122,29 @@ class PoolingPlan:
 
     @property
     def sorted_ids(self) -> torch.Tensor:
-        """int32 (K,): global point ids (b*Np + p) of kept points, grouped by cell, ascending inside a cell."""
+        """int32 (K,): global point ids (b*Np + p) of kept points (run plans: of the first point of every
+        run), grouped by cell, ascending inside a cell."""
         ids = self._views()[2]
         return ids[:int(self.cell_start[-1].item())]
+
+    @property
+    def num_sorted(self) -> int:
+        """Number of sorted entries K = cell_start[-1]: kept points of a point plan, runs of a run plan.
+        Read back from the device once (a sync) unless ``max_runs`` was given."""
+        if self._num_runs is None:
+            self._num_runs = int(self.cell_start[-1].item())
+        return self._num_runs
+
+    @property
+    def sorted_cells(self) -> torch.Tensor:
+        """int32 (K,): global output row b*Y*X + cell of every sorted entry."""
+        return self._views()[3][:int(self.cell_start[-1].item())]
+
+    @property
+    def run_code(self) -> torch.Tensor:
+        """run plans: int32 (B, Np) -- slot of the run for its first point, -2 continuation, -1 dropped."""
+        assert self.mode == 'runs'
+        return self._views()[4].view(self.batch, self.num_points)
 
     def pos_memo(self) -> torch.Tensor:
         """The reference's ``pos_memo`` (voxel_pooling.py:40): int32 (B, Np, 3) = (b, y, x) or -1."""
@@ -105,8 +157,15 @@ class PoolingPlan:
         return out
 
 
-def build_plan(geom_xyz: torch.Tensor, voxel_num: VoxelNum) -> PoolingPlan:
-    return PoolingPlan(geom_xyz, voxel_num)
+def build_plan(geom_xyz: torch.Tensor, voxel_num: VoxelNum, frustum: Optional[Sequence[int]] = None,
+               max_runs: Optional[int] = None) -> PoolingPlan:
+    return PoolingPlan(geom_xyz, voxel_num, frustum, max_runs)
+
+
+def runs_supported(channels: int, dtype: torch.dtype) -> bool:
+    """fp32 fast-path channel counts; BEVPOOL_DISABLE_G8=1 (tests) forces the generic point kernels."""
+    return (dtype == torch.float32 and channels in RUN_CHANNELS
+            and os.environ.get('BEVPOOL_DISABLE_G8', '0') != '1')
 
 
 def _transpose(x: torch.Tensor, batch: int, rows: int, cols: int) -> torch.Tensor:
@@ -148,6 +207,7 @@ def pool_forward(plan: PoolingPlan, input_features: torch.Tensor) -> torch.Tenso
     """features (B, ..., C) -> (B, Y, X, C); every cell written once, no pre-zeroing."""
     X, Y, _ = plan.voxel_num
     B, C = plan.batch, input_features.shape[-1]
+    assert plan.mode == 'points', 'the drop-in op sums arbitrary per-point rows: it needs a point plan'
     out = torch.empty(B, Y, X, C, dtype=input_features.dtype, device=input_features.device)
     ws = _forward_workspace(C, out.device)
     _lib.check(_lib.lib().bevpool_forward(plan.ptr, input_features.data_ptr(), out.data_ptr(),
@@ -190,6 +250,19 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
     assert B * N == BN and plan.num_points == N * D * H * W
     ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
     out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
+    if plan.mode == 'runs':
+        if not runs_supported(C, depth.dtype):
+            raise ValueError(f'run plans need float32 and C in {RUN_CHANNELS}; build a point plan for C={C}, {depth.dtype}')
+        assert plan.frustum == (N, D, H, W)
+        cap = max(1, plan.num_sorted)
+        run_rows = torch.empty(cap, C, dtype=torch.float32, device=depth.device)
+        ws = _forward_workspace(C, out.device)
+        _lib.check(_lib.lib().bevpool_fused_forward_runs(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
+                                                         out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
+                                                         C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(),
+                                                         _lib.stream_ptr(depth.device)),
+                   'bevpool_fused_forward_runs')
+        return out
     ws = _forward_workspace(C, out.device)
     _lib.check(_lib.lib().bevpool_fused_forward(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
                                                 out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
@@ -267,7 +340,12 @@ class VoxelPoolingFused(Function):
         with torch.cuda.device(depth.device):
             if plan is None:
                 assert geom_xyz.is_contiguous()
-                plan = PoolingPlan(geom_xyz, (X, Y, Z))
+                frustum = None
+                # (a run plan reads its run count back once to size the scratch rows: not while capturing)
+                if (geom_xyz.dim() == 6 and runs_supported(context.shape[1], depth.dtype)
+                        and not torch.cuda.is_current_stream_capturing()):
+                    frustum = tuple(geom_xyz.shape[1:5])      # (N, D, H, W): sort runs, not points
+                plan = PoolingPlan(geom_xyz, (X, Y, Z), frustum)
             assert plan.voxel_num == (X, Y, Z)
             context_rows = context_rows_nhwc(context)
             out = fused_forward(plan, depth, context, context_rows)

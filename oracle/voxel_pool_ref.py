@@ -153,3 +153,35 @@ def reference_test_inputs():
     geom_xyz = geom_xyz.reshape(2, -1, 3)
     features = torch.rand([2, 6, 10, 10, 10, 80]) - 0.5
     return geom_xyz, features
+
+
+def run_plan_ref(geom_xyz: torch.Tensor, voxel_num, rows_per_block: int = 16):
+    """Expected contents of a RUN plan (mm_training_b200/csrc/common.cuh) for ``geom_xyz`` (B, N, D, H, W, 3).
+
+    Not a reference data structure: the reference sums point by point
+    (``voxel_pooling_forward_cuda.cu:30-34``).  A run groups vertically adjacent points -- same image,
+    depth bin and column, consecutive rows inside one block of ``rows_per_block`` rows -- that the
+    reference's own index rule (``cell_index_ref``) sends to the same cell, so summing run by run adds
+    exactly the terms the reference adds, in a different (fixed) order.
+
+    Returns ``head`` (B, N, D, H, W) bool, ``run_code`` (B, Np) int32 (slot of the run for its first
+    point, -2 for continuation points, -1 for dropped points), ``cell_start`` (B*Y*X + 1,) CSR over
+    runs, ``sorted_ids`` (R,) global ids of first points ordered by (cell, id)."""
+    X, Y, Z = _voxel_num_ints(voxel_num)
+    B, N, D, H, W = geom_xyz.shape[:5]
+    kept, lin, _ = cell_index_ref(geom_xyz, voxel_num)
+    cell = torch.where(kept, lin, torch.full_like(lin, -1)).reshape(B, N, D, H, W)
+    prev = torch.full_like(cell, -1)
+    prev[:, :, :, 1:, :] = cell[:, :, :, :-1, :]
+    first_row = (torch.arange(H) % rows_per_block == 0).view(1, 1, 1, H, 1)
+    head = (cell >= 0) & (first_row | (prev != cell))
+    gid = torch.arange(cell.numel()).view_as(cell)
+    hid, hcell = gid[head], cell[head]
+    order = torch.sort(hcell, stable=True).indices
+    sorted_ids = hid[order]
+    counts = torch.bincount(hcell, minlength=B * X * Y)
+    cell_start = torch.zeros(B * X * Y + 1, dtype=torch.int64)
+    cell_start[1:] = counts.cumsum(0)
+    code = torch.where(cell.reshape(-1) >= 0, torch.tensor(-2), torch.tensor(-1)).to(torch.int32)
+    code[sorted_ids] = torch.arange(sorted_ids.numel(), dtype=torch.int32)
+    return head, code.view(B, -1), cell_start, sorted_ids

@@ -15,7 +15,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 tail -c 1500 gpurun_out/bench_${TAG}_reference.json
 CMD="python bench.py --steps 2 --warmup 1 --no-graph --no-extras"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/launches_${TAG}.log 2>&1
-KREG='regex:plan_key|sort_hist|sort_scatter|bucket_sort|scan_exclusive|pool_forward|fused_backward|grad_rows|transpose_kernel|column_'
+KREG='regex:frustum_|cell_sum|plan_key|sort_hist|sort_scatter|bucket_sort|scan_exclusive|pool_forward|fused_backward|grad_rows|transpose_kernel|column_'
 timeout 400 ncu --set full --clock-control none --import-source on -k "$KREG" --launch-skip 24 --launch-count 16 -f -o gpurun_out/prof_${TAG}_step $CMD > gpurun_out/prof_${TAG}_step.log 2>&1
 tail -3 gpurun_out/prof_${TAG}_step.log
 ls -la gpurun_out | tail -8
