@@ -34,7 +34,8 @@ static int env_int_runs(const char *name, int dflt) {
 }
 
 constexpr int kRaTW = 4;                     // image columns per CTA = one 16-byte segment
-constexpr int kRaDC = 32;                    // depth bins per staged chunk
+constexpr int kRaDC = 16;                    // depth bins per staged chunk
+constexpr int kRaStages = 3;                 // chunks of (code, depth) in shared memory: one reduced, two in flight
 constexpr int kRaThreads = 256;
 constexpr int kRaZeroCells = 32;             // cells covered by the zeroed shared-memory buffer
 
@@ -94,6 +95,10 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void cp_async16_runs(void *dst_smem, const void *src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+
 template <int NV2>
 __device__ __forceinline__ void g8_lds_row(const float *row, int l8, float (&v)[2 * NV2]) {
   constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
@@ -150,9 +155,9 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char s_raw[];
   float *s_ctx = reinterpret_cast<float *>(s_raw);                                  // [row][column][channel]
-  int4 (*s_code)[kRunHB] = reinterpret_cast<int4 (*)[kRunHB]>(s_ctx + kRunHB * kRaTW * C);   // [bin][row] x 4 columns
-  float4 (*s_dep)[kRunHB] = reinterpret_cast<float4 (*)[kRunHB]>(s_code + kRaDC);
-  float *s_zero = reinterpret_cast<float *>(s_dep + kRaDC);                         // kRaZeroCells * C zeros
+  int4 (*s_code)[kRaDC][kRunHB] = reinterpret_cast<int4 (*)[kRaDC][kRunHB]>(s_ctx + kRunHB * kRaTW * C);   // [stage][bin][row] x 4 columns
+  float4 (*s_dep)[kRaDC][kRunHB] = reinterpret_cast<float4 (*)[kRaDC][kRunHB]>(s_code + kRaStages);
+  float *s_zero = reinterpret_cast<float *>(s_dep + kRaStages);                     // kRaZeroCells * C zeros
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zero + kRaZeroCells * C);
   const int tid = threadIdx.x, lane = tid & 31, l8 = lane & 7, grp = lane >> 3, warp = tid >> 5;
   int bid = blockIdx.x;
@@ -219,26 +224,44 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
     if (issued_bulk) tma_store_commit();
   }
 
-  const int64_t slot0 = __ldg(cell_start + cell_base);
-  const int wl = warp & 3, dh = warp >> 2;
-  const float *ctx_col = s_ctx + wl * C;
-  // staging role: thread = (bin, row) of the chunk, 4 columns; two (bin, row) pairs per thread
+  // staging role: thread = (bin sd, row sh) of a chunk, 4 columns
   const int sh = tid & 15, sd = tid >> 4;
   const bool srow = h0 + sh < H;
   const int64_t sbase = (int64_t)bn * D * HW + (int64_t)(h0 + sh) * W + w0;
+  const int nchunks = (d_end - d_begin + kRaDC - 1) / kRaDC;
 
-  auto load_col = [&](int dl, RunCol &q) {
-    const int *cw = reinterpret_cast<const int *>(&s_code[dl][0]) + wl;
-    const float *pw = reinterpret_cast<const float *>(&s_dep[dl][0]) + wl;
-    q.c_lo = cw[4 * l8];
-    q.c_hi = cw[4 * (8 + l8)];
-    q.p_lo = pw[4 * l8];
-    q.p_hi = pw[4 * (8 + l8)];
-    const unsigned k_lo = __ballot_sync(kFull, q.c_lo != kRunDropped), k_hi = __ballot_sync(kFull, q.c_hi != kRunDropped);
-    const unsigned h_lo = __ballot_sync(kFull, q.c_lo >= 0), h_hi = __ballot_sync(kFull, q.c_hi >= 0);
-    q.km = ((k_lo >> (8 * grp)) & 0xffu) | (((k_hi >> (8 * grp)) & 0xffu) << 8);
-    q.hm = ((h_lo >> (8 * grp)) & 0xffu) | (((h_hi >> (8 * grp)) & 0xffu) << 8);
+  // (code, depth) segments of chunk c -> stage c % 3, as asynchronous 16-byte copies
+  auto issue_chunk = [&](int cidx) {
+    if (cidx < nchunks) {
+      const int st = cidx % kRaStages, d = d_begin + cidx * kRaDC + sd;
+      int4 *dc = &s_code[st][sd][sh];
+      float4 *dd = &s_dep[st][sd][sh];
+      if (srow && d < d_end) {
+        const int64_t gp = sbase + (int64_t)d * HW;
+        if (vec) {
+          cp_async16_runs(dc, run_code + gp);
+          cp_async16_runs(dd, depth + gp);
+        } else {
+          int4 pc = make_int4(kRunDropped, kRunDropped, kRunDropped, kRunDropped);
+          float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (w0 + 0 < W) { pc.x = __ldg(run_code + gp + 0); pd.x = __ldg(depth + gp + 0); }
+          if (w0 + 1 < W) { pc.y = __ldg(run_code + gp + 1); pd.y = __ldg(depth + gp + 1); }
+          if (w0 + 2 < W) { pc.z = __ldg(run_code + gp + 2); pd.z = __ldg(depth + gp + 2); }
+          if (w0 + 3 < W) { pc.w = __ldg(run_code + gp + 3); pd.w = __ldg(depth + gp + 3); }
+          *dc = pc;
+          *dd = pd;
+        }
+      } else {
+        *dc = make_int4(kRunDropped, kRunDropped, kRunDropped, kRunDropped);
+        *dd = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+
+  const int64_t slot0 = __ldg(cell_start + cell_base);
+  const int wl = warp & 3, dh = warp >> 2;
+  const float *ctx_col = s_ctx + wl * C;
   const uint64_t pol_rows = l2_policy_evict_last();
   auto store_run = [&](int64_t slot, const float (&acc)[NREG]) {
     if (slot >= 0 && slot < capacity) {
@@ -252,40 +275,32 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
     return m;
   };
 
+  issue_chunk(0);
+  issue_chunk(1);
   bool ctx_ready = false;
-  for (int d0 = d_begin; d0 < d_end; d0 += kRaDC) {
-    if (d0 != d_begin) __syncthreads();                  // every warp is done with the previous chunk
-    // (code, depth) of the chunk: one 16-byte segment of 4 columns per (bin, row)
-#pragma unroll
-    for (int j = 0; j < kRaDC * kRunHB / kRaThreads; ++j) {
-      const int dl = sd + j * (kRaThreads / kRunHB);
-      const int d = d0 + dl;
-      int4 pc = make_int4(kRunDropped, kRunDropped, kRunDropped, kRunDropped);
-      float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (srow && d < d_end) {
-        const int64_t gp = sbase + (int64_t)d * HW;
-        if (vec) {
-          pc = ldg_stream_i4(reinterpret_cast<const int4 *>(run_code + gp));
-          pd = ldg_stream_f4(reinterpret_cast<const float4 *>(depth + gp));
-        } else {
-          if (w0 + 0 < W) { pc.x = __ldg(run_code + gp + 0); pd.x = __ldg(depth + gp + 0); }
-          if (w0 + 1 < W) { pc.y = __ldg(run_code + gp + 1); pd.y = __ldg(depth + gp + 1); }
-          if (w0 + 2 < W) { pc.z = __ldg(run_code + gp + 2); pd.z = __ldg(depth + gp + 2); }
-          if (w0 + 3 < W) { pc.w = __ldg(run_code + gp + 3); pd.w = __ldg(depth + gp + 3); }
-        }
-      }
-      s_code[dl][sh] = pc;
-      s_dep[dl][sh] = pd;
-    }
-    __syncthreads();
-    if (!ctx_ready) {                                    // first chunk: the context tile must have landed
+  for (int cidx = 0; cidx < nchunks; ++cidx) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk cidx has landed (cidx + 1 may still be in flight)
+    __syncthreads();                                        // ... for every thread; and chunk cidx - 1 is fully reduced
+    issue_chunk(cidx + 2);                                  // into the stage chunk cidx - 1 just left
+    if (!ctx_ready) {                                       // first chunk: the context tile must have landed
       mbar_wait(s_bar, 0);
       ctx_ready = true;
     }
-
-#pragma unroll 1
-    for (int k = 0; k < kRaDC / 16; ++k) {
-      const int dl = dh * (kRaDC / 2) + 8 * k + 2 * grp;     // this group's bins: dl, dl + 1
+    const int st = cidx % kRaStages;
+    auto load_col = [&](int dl, RunCol &q) {
+      const int *cw = reinterpret_cast<const int *>(&s_code[st][dl][0]) + wl;
+      const float *pw = reinterpret_cast<const float *>(&s_dep[st][dl][0]) + wl;
+      q.c_lo = cw[4 * l8];
+      q.c_hi = cw[4 * (8 + l8)];
+      q.p_lo = pw[4 * l8];
+      q.p_hi = pw[4 * (8 + l8)];
+      const unsigned k_lo = __ballot_sync(kFull, q.c_lo != kRunDropped), k_hi = __ballot_sync(kFull, q.c_hi != kRunDropped);
+      const unsigned h_lo = __ballot_sync(kFull, q.c_lo >= 0), h_hi = __ballot_sync(kFull, q.c_hi >= 0);
+      q.km = ((k_lo >> (8 * grp)) & 0xffu) | (((k_hi >> (8 * grp)) & 0xffu) << 8);
+      q.hm = ((h_lo >> (8 * grp)) & 0xffu) | (((h_hi >> (8 * grp)) & 0xffu) << 8);
+    };
+    {
+      const int dl = dh * (kRaDC / 2) + 2 * grp;            // this group's bins: dl, dl + 1 (8 bins per warp)
       RunCol a, b;
       load_col(dl, a);
       load_col(dl + 1, b);
@@ -349,6 +364,7 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
       }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (!ctx_ready) mbar_wait(s_bar, 0);                   // (empty depth range) never leave a copy in flight
   if (issued_bulk) tma_store_wait_read();                // the zero buffer must outlive the bulk stores reading it
 }
@@ -367,7 +383,7 @@ static int launch_stage_a(const PlanView &pv, const float *dp, const float *cx, 
   const int splits = (int)ceil_div64(D, d_per_cta);
   const int64_t ctas = (int64_t)nb * num_cams * tiles_w * tiles_h * splits;
   if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
-  const size_t smem = (size_t)kRunHB * kRaTW * C * 4 + (size_t)kRaDC * kRunHB * 32 + (size_t)kRaZeroCells * C * 4 + 16;
+  const size_t smem = (size_t)kRunHB * kRaTW * C * 4 + (size_t)kRaStages * kRaDC * kRunHB * 32 + (size_t)kRaZeroCells * C * 4 + 16;
   if (smem > 48 * 1024)
     BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   frustum_reduce_kernel<NV2><<<(unsigned)ctas, kRaThreads, smem, s>>>(
