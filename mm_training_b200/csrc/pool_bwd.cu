@@ -29,6 +29,7 @@
 #include "pool_g8.cuh"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace bevpool {
 
@@ -174,10 +175,13 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
     issue_cells(c + 2);
 
     if (live_cur) {
-      const int *cell_i = reinterpret_cast<const int *>(&s_cell[c % kBtCellStages][0][0]);   // [bin][row][column] scalars
-      const float *dep_f = reinterpret_cast<const float *>(&s_dep[c % kBtCellStages][0][0]);
-      const float *g_st = s_g + (c & 1) * kRowFloats;
-      float *res_f = reinterpret_cast<float *>(s_res);
+      // this lane's (row, column) scalars of bin 0 and the gradient-row quarter of (bin 0, column wl); a bin
+      // further on is one multiply-add away (kBtTH * 4 scalars, kBtTW * C floats per bin)
+      const int *cell_p = reinterpret_cast<const int *>(&s_cell[c % kBtCellStages][0][0]) + my_off;
+      const float *dep_p = reinterpret_cast<const float *>(&s_dep[c % kBtCellStages][0][0]) + my_off;
+      const float4 *g_p = reinterpret_cast<const float4 *>(s_g + (c & 1) * kRowFloats + wl * C) + q * NQ;
+      const int *pc_p = reinterpret_cast<const int *>(&s_pc[c & 1][0]) + wl;
+      float *res_p = reinterpret_cast<float *>(s_res) + my_off;
       // bins of the chunk kept by at least one of the warp's 8 rows (lane = bin), and those that need
       // the per-lane path because some row left the primary cell
       const int fl = lane < kBtDC ? s_flag[c & 1][lane] >> (2 * wl + hh) : 0;
@@ -185,47 +189,41 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
       const unsigned smask = __ballot_sync(kFull, (fl >> 8) & 1);
       // Software-pipelined walk over the kept bins: the scalars of bin n+1 are fetched and the 4-lane
       // reduction + store of bin n-1 are issued while the gradient row of bin n is in flight, so a warp
-      // (in-order issue) is not parked on the shuffle tail before it can start the next loads.
-      int dq = -1, cell = -1;
-      float dv = 0.f;
+      // (in-order issue) is not parked on the shuffle tail before it can start the next loads.  The body
+      // is instantiated twice with the roles of the two scalar sets swapped (no register shuffling), and
+      // once per chunk flavour: kFast = every kept row of every bin lies in its primary cell.
+      float prev_dot = 0.f;
+      int prev_dst = -1;                                      // bin whose dot product is still to be reduced, -1: none
       auto fetch = [&](int &dq_, int &cell_, float &dv_) {
         dq_ = -1;
         if (dmask) {
           dq_ = __ffs(dmask) - 1;
           dmask &= dmask - 1u;
-          cell_ = cell_i[dq_ * (kBtTH * 4) + my_off];
-          dv_ = dep_f[dq_ * (kBtTH * 4) + my_off];
+          cell_ = cell_p[dq_ * (kBtTH * 4)];
+          dv_ = dep_p[dq_ * (kBtTH * 4)];
         }
       };
-      fetch(dq, cell, dv);
-      float prev_dot = 0.f;
-      int prev_dst = -1;                                      // index into res_f, -1: nothing to store
-      while (dq >= 0) {                                       // warp-uniform
+      auto body = [&](auto fast, int dq, int cell, float dv, int &ndq, int &ncell, float &ndv) {
         const bool on = cell >= 0;
         float4 g[NQ];
-        if (!((smask >> dq) & 1u)) {                           // warp-uniform: every kept row is in the primary cell
-          const float4 *gs = reinterpret_cast<const float4 *>(g_st + (dq * kBtTW + wl) * C) + q * NQ;
+        bool staged = true;
+        if (!decltype(fast)::value) {
+          if ((smask >> dq) & 1u) staged = cell == pc_p[dq * 4] || !on;
+        }
+        if (staged) {
+          const float4 *gs = g_p + dq * (kBtTW * C4);
 #pragma unroll
           for (int j = 0; j < NQ; ++j) g[j] = gs[j];
         } else {
-          const int pcell = reinterpret_cast<const int *>(&s_pc[c & 1][0])[dq * 4 + wl];
-          if (cell == pcell || !on) {
-            const float4 *gs = reinterpret_cast<const float4 *>(g_st + (dq * kBtTW + wl) * C) + q * NQ;
+          const float4 *gg = reinterpret_cast<const float4 *>(gbase + (int64_t)cell * C) + q * NQ;
 #pragma unroll
-            for (int j = 0; j < NQ; ++j) g[j] = gs[j];
-          } else {
-            const float4 *gg = reinterpret_cast<const float4 *>(gbase + (int64_t)cell * C) + q * NQ;
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) g[j] = __ldg(gg + j);
-          }
+          for (int j = 0; j < NQ; ++j) g[j] = __ldg(gg + j);
         }
-        int ndq, ncell = -1;
-        float ndv = 0.f;
         fetch(ndq, ncell, ndv);
         // finish the previous bin
         prev_dot += __shfl_xor_sync(kFull, prev_dot, 2);
         prev_dot += __shfl_xor_sync(kFull, prev_dot, 1);
-        if (prev_dst >= 0) res_f[prev_dst] = prev_dot;
+        if (prev_dst >= 0) res_p[prev_dst * (kBtTH * 4)] = prev_dot;
         // this bin
         float2 dot_a = make_float2(0.f, 0.f), dot_b = make_float2(0.f, 0.f);
         if (on) {
@@ -240,12 +238,22 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
           }
         }
         prev_dot = (dot_a.x + dot_a.y) + (dot_b.x + dot_b.y);
-        prev_dst = (on && q == 0) ? dq * (kBtTH * 4) + my_off : -1;
-        dq = ndq; cell = ncell; dv = ndv;
-      }
+        prev_dst = (on && q == 0) ? dq : -1;
+      };
+      auto walk = [&](auto fast) {
+        int dq0 = -1, cell0 = -1, dq1 = -1, cell1 = -1;
+        float dv0 = 0.f, dv1 = 0.f;
+        fetch(dq0, cell0, dv0);
+        while (dq0 >= 0) {                                    // warp-uniform
+          body(fast, dq0, cell0, dv0, dq1, cell1, dv1);
+          if (dq1 < 0) break;
+          body(fast, dq1, cell1, dv1, dq0, cell0, dv0);
+        }
+      };
+      if (smask == 0u) walk(std::true_type{}); else walk(std::false_type{});
       prev_dot += __shfl_xor_sync(kFull, prev_dot, 2);
       prev_dot += __shfl_xor_sync(kFull, prev_dot, 1);
-      if (prev_dst >= 0) res_f[prev_dst] = prev_dot;
+      if (prev_dst >= 0) res_p[prev_dst * (kBtTH * 4)] = prev_dot;
     }
     __syncthreads();
     // ---- grad_depth of the chunk: one 16-byte segment per (bin, row); the entry is this thread's own

@@ -425,7 +425,8 @@ extern "C" int bevpool_fused_forward_runs(const void *plan, const void *depth, c
   if (fpc <= 0 || fpc > batch) fpc = batch;
   const int fill = env_int_runs("BEVPOOL_RUN_FILL", 1) != 0;        // 0: stage B fills the empty cells itself
   const int hints = env_int_runs("BEVPOOL_RUN_HINTS", 1) != 0;      // L2 eviction-priority hints on the fill / run-row stores
-  const int cps_b = 5;                                               // stage B CTAs per SM (4 warps each)
+  int cps_b = env_int_runs("BEVPOOL_RUN_CPSB", 5);                   // stage B CTAs per SM (4 warps each)
+  cps_b = cps_b < 1 ? 1 : (cps_b > kFwMaxCtasPerSm - 1 ? kFwMaxCtasPerSm - 1 : cps_b);
   const float *dp = static_cast<const float *>(depth), *cx = static_cast<const float *>(context_nhwc);
   float *rr = static_cast<float *>(run_rows), *out = static_cast<float *>(out_nhwc);
   const FastDiv one = make_fastdiv(1u);

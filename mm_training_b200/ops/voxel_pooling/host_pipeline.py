@@ -14,7 +14,7 @@ from typing import Sequence
 
 import torch
 
-from .voxel_pooling import voxel_pooling_fused
+from .voxel_pooling import build_plan, voxel_pooling_fused
 
 
 class HostPoolingPipeline:
@@ -61,7 +61,10 @@ class HostPoolingPipeline:
                 self.s_run.wait_event(self.ev_in[k])
                 d = self.d_depth[k][:m * N].detach().requires_grad_(True)
                 c = self.d_ctx[k][:m * N].detach().requires_grad_(True)
-                o = voxel_pooling_fused(self.d_geom[k][:m], d, c, self.vn)
+                # point plan: sizing the scratch rows of a run plan would read the run count back (a host
+                # sync per chunk that stalls the copy streams); a chunk's kernels hide behind PCIe anyway
+                plan = build_plan(self.d_geom[k][:m], self.vn)
+                o = voxel_pooling_fused(None, d, c, self.vn, plan)
                 o.backward(self.d_go[k][:m])
                 self.ev_free[k].record(self.s_run)
                 done = torch.cuda.Event()
