@@ -104,3 +104,51 @@ def test_fused_oracle_forward_and_grads():
                             gc2[b * N + n, :, h, w] += depth[b * N + n, d, h, w].double() * g
     assert torch.allclose(gd, gd2, rtol=1e-12, atol=1e-14)
     assert torch.allclose(gc, gc2, rtol=1e-12, atol=1e-14)
+
+
+def test_run_plan_oracle_is_consistent_with_the_point_oracle():
+    """``run_plan_ref`` (the expected contents of a run plan) regroups the reference's terms without
+    changing them: summing depth*context run by run and then per cell equals the point-by-point oracle,
+    every kept point belongs to exactly one run, and runs never cross a 16-row block."""
+    g = torch.Generator().manual_seed(5)
+    B, N, D, H, W, C, vn = 2, 2, 6, 20, 5, 8, (16, 8, 1)
+    x = torch.randint(-1, 17, (B, N, D, 1, W), generator=g).expand(B, N, D, H, W)
+    y = torch.randint(-1, 9, (B, N, D, 1, W), generator=g).expand(B, N, D, H, W)
+    z = torch.randint(-1, 2, (B, N, D, H, W), generator=g)
+    geom = torch.stack([x, y, z], -1).int().contiguous()
+    depth = torch.rand(B * N, D, H, W, generator=g).softmax(1).double()
+    ctx = (torch.rand(B * N, C, H, W, generator=g) - 0.5).double()
+    head, code, cell_start, sorted_ids = vp.run_plan_ref(geom, vn)
+    kept, lin, _ = vp.cell_index_ref(geom, vn)
+    assert int((code >= 0).sum()) == sorted_ids.numel() == int(cell_start[-1])
+    assert torch.equal((code != -1), kept)
+    hh = torch.arange(H).view(1, 1, 1, H, 1).expand_as(head)
+    assert bool(head[(hh % 16 == 0) & kept.view_as(head)].all())          # a block's first kept row starts a run
+    # run rows, then per-cell sums in slot order
+    feats = vp.materialise_features_ref(depth, ctx, B, N).reshape(-1, C)
+    code_f = code.reshape(-1)
+    run_rows = torch.zeros(sorted_ids.numel(), C, dtype=torch.float64)
+    slot = torch.full((code_f.numel(),), -1, dtype=torch.long)
+    cur = -1
+    Wn = W
+    # walk every (b, n, d, w) column top to bottom: a head opens a run, -2 continues it
+    idx = torch.arange(code_f.numel()).view(B, N, D, H, W)
+    for col in idx.permute(0, 1, 2, 4, 3).reshape(-1, H).tolist():
+        cur = -1
+        for p in col:
+            cv = int(code_f[p])
+            if cv >= 0:
+                cur = cv
+            elif cv == -1:
+                cur = -1
+            if cv != -1:
+                assert cur >= 0
+                slot[p] = cur
+    k = slot >= 0
+    run_rows.index_add_(0, slot[k], feats[k])
+    X, Y, _ = vn
+    out = torch.zeros(B * X * Y, C, dtype=torch.float64)
+    cells = lin.reshape(-1)[sorted_ids]
+    out.index_add_(0, cells, run_rows)
+    ref = vp.voxel_pooling_ref(geom, feats.view(B, -1, C), vn, acc_dtype=torch.float64)
+    assert torch.allclose(out.view(B, Y, X, C).permute(0, 3, 1, 2), ref, rtol=1e-12, atol=1e-14)
