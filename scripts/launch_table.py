@@ -16,7 +16,7 @@ for r in rows[hi + 1:]:
 ls = list(launch.values())
 # one step = from a plan key kernel to the next; the timed loop comes first, per-stage timing loops after it
 starts = [i for i, l in enumerate(ls) if 'plan_key' in l['name']]
-a, b = starts[1], starts[2]          # second step of the main loop (first is warm-up)
+a, b = starts[3], starts[4]          # a warm-up step of the main loop (earlier ones are the probe / set-up steps)
 tot = sum(l.get('gpu__time_duration.sum', 0) for l in ls[a:b])
 print(f'one step = {b - a} launches, {tot / 1e3:.1f} us (ncu: cold caches, serialised)')
 for l in ls[a:b]:
