@@ -214,6 +214,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()
 
