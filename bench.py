@@ -152,6 +152,43 @@ def run_cpu_baseline(cfg, frames: int, iters: int):
                       f'materialise + index_add_ forward + autograd backward', 'ms_per_frame': best / frames * 1e3}
 
 
+def run_lidar_side(dev, peak_gbs, sweeps: int = 8):
+    """Side measurement (not the headline metric): ``sweeps`` synthetic 200k-point long-range sweeps
+     through voxelize (+ fused HardSimpleVFE mean) and pillar scatter, and the
+    serial CPU restatement of mmcv's hard_voxelize on one sweep (mmcv's CPU kernel is single-threaded)."""
+    import numpy as np
+    from mm_training_b200.configs import CFG_3
+    from mm_training_b200.ops.voxelize import Voxelization, pillar_scatter, voxelize
+    v = CFG_3
+    clouds_np = [synthetic.lidar_sweep(v.points_per_sweep, v.num_point_features, seed=2 + i) for i in range(sweeps)]
+    clouds = [torch.from_numpy(a).to(dev) for a in clouds_np]
+    layer = Voxelization(list(v.voxel_size), list(v.point_cloud_range), v.max_num_points, v.max_voxels).eval()
+    gx, gy, gz = (int(g) for g in layer.grid_size.tolist())
+
+    def run():
+        voxels, num_points, coors, mean = voxelize(clouds, layer, mean_features=v.vfe_features)
+        canvas = pillar_scatter(mean, coors, sweeps, (gz, gy, gx))
+        return voxels, canvas
+    voxels, canvas = run()
+    torch.cuda.synchronize()
+    M = voxels.shape[0] / sweeps
+    med, mn = time_cuda(run, 10, 3)                      # includes the one D2H sync of the voxel counts
+    F, T = v.num_point_features, v.max_num_points
+    vox_bytes = 4 * F * v.points_per_sweep + 4 * F * T * M + 20 * M
+    sc_bytes = 4 * v.vfe_features * M + 16 * M + 4 * v.vfe_features * gz * gy * gx
+    gbs = (vox_bytes + sc_bytes) * sweeps / (med * 1e-3) / 1e9
+    from oracle import voxelize_ref as vr
+    t0 = time.perf_counter()
+    vr.hard_voxelize_c(clouds_np[0], list(v.voxel_size), list(v.point_cloud_range), T, v.max_voxels)
+    cpu_s = time.perf_counter() - t0
+    return {'workload': v.name, 'sweeps_per_step': sweeps, 'ms_per_step': med, 'sweeps_per_s': sweeps / (med * 1e-3),
+            'points_per_s': sweeps * v.points_per_sweep / (med * 1e-3), 'voxels_per_sweep': M,
+            'algorithmic_bytes_per_sweep': vox_bytes + sc_bytes, 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peak_gbs,
+            'what': 'voxelize(list of sweeps, mean_features=5) + pillar_scatter to (B, 5, 256, 2048), incl. 1 D2H sync',
+            'cpu_hard_voxelize': {'sweeps_per_s': 1.0 / cpu_s, 'cores': 1, 'kind': 'port',
+                                  'sample': '1 sweep, serial C restatement of mmcv hard_voxelize (oracle/)'}}
+
+
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -395,6 +432,12 @@ def main():
 
         # ---- CPU baseline: oracle port on the host cores, bounded sample
         line['cpu_baseline'] = run_cpu_baseline(cfg, 2, 3)
+
+        # ---- LiDAR branch (BASELINE.json configs[2]): hard voxelization + HardSimpleVFE mean + pillar scatter
+        try:
+            line['lidar'] = run_lidar_side(dev, peak_gbs)
+        except Exception as e:                                  # pragma: no cover
+            line['lidar'] = {'error': repr(e)}
 
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -365,8 +365,21 @@ grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ g
     if (occ == 0) continue;                       // CTA-uniform
     const int64_t cell0 = ((int64_t)blockIdx.x * kGrTilesPerCta + k) * 32;
     const int ncell = (int)min((int64_t)32, G - cell0);
-    for (int c = warp; c < C; c += 8)
-      if (lane < ncell) tile[lane * ld + c] = grad_nchw[((int64_t)b * C + c) * G + cell0 + lane];
+    // a warp takes every 8th channel; 10 independent 128-byte row loads in flight per lane (80 channels per round)
+    const E *src = grad_nchw + (int64_t)b * C * G + cell0 + lane;
+    for (int c0 = warp; c0 < C; c0 += 80) {
+      E v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const int ch = c0 + 8 * k;
+        v[k] = (ch < C && lane < ncell) ? src[(int64_t)ch * G] : E(0);
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+        const int ch = c0 + 8 * k;
+        if (ch < C) tile[lane * ld + ch] = v[k];
+      }
+    }
     __syncthreads();
     for (int j = warp; j < ncell; j += 8) {
       if (!((occ >> j) & 1u)) continue;
