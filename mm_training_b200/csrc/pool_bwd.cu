@@ -192,17 +192,25 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
       // (in-order issue) is not parked on the shuffle tail before it can start the next loads.  The body
       // is instantiated twice with the roles of the two scalar sets swapped (no register shuffling), and
       // once per chunk flavour: kFast = every kept row of every bin lies in its primary cell.
-      float prev_dot = 0.f;
-      int prev_dst = -1;                                      // bin whose dot product is still to be reduced, -1: none
-      auto fetch = [&](int &dq_, int &cell_, float &dv_) {
-        dq_ = -1;
-        if (dmask) {
-          dq_ = __ffs(dmask) - 1;
-          dmask &= dmask - 1u;
-          cell_ = cell_p[dq_ * (kBtTH * 4)];
-          dv_ = dep_p[dq_ * (kBtTH * 4)];
-        }
+      // carried state: `pend` = the next kept bin (its find-first-set runs on the slow XU pipe, so it is
+      // computed one iteration before it is used); prev_h = the previous bin's dot product after the first
+      // of its two shuffle steps (issued at the end of its body, consumed in the middle of the next one).
+      int pend = -1;
+      auto advance = [&]() {
+        pend = dmask ? __ffs(dmask) - 1 : -1;
+        dmask &= dmask - 1u;
       };
+      advance();
+      auto fetch = [&](int &dq_, int &cell_, float &dv_) {
+        dq_ = pend;
+        if (pend >= 0) {
+          cell_ = cell_p[pend * (kBtTH * 4)];
+          dv_ = dep_p[pend * (kBtTH * 4)];
+        }
+        advance();
+      };
+      float prev_h = 0.f;
+      int prev_dst = -1;                                      // bin whose dot product is still to be stored, -1: none
       auto body = [&](auto fast, int dq, int cell, float dv, int &ndq, int &ncell, float &ndv) {
         const bool on = cell >= 0;
         float4 g[NQ];
@@ -220,10 +228,8 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
           for (int j = 0; j < NQ; ++j) g[j] = __ldg(gg + j);
         }
         fetch(ndq, ncell, ndv);
-        // finish the previous bin
-        prev_dot += __shfl_xor_sync(kFull, prev_dot, 2);
-        prev_dot += __shfl_xor_sync(kFull, prev_dot, 1);
-        if (prev_dst >= 0) res_p[prev_dst * (kBtTH * 4)] = prev_dot;
+        // second reduction step of the previous bin: in flight behind this bin's multiply-adds
+        const float prev_s = __shfl_xor_sync(kFull, prev_h, 1);
         // this bin
         float2 dot_a = make_float2(0.f, 0.f), dot_b = make_float2(0.f, 0.f);
         if (on) {
@@ -237,7 +243,9 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
             gacc[j] = make_float4(t0.x, t0.y, t1.x, t1.y);
           }
         }
-        prev_dot = (dot_a.x + dot_a.y) + (dot_b.x + dot_b.y);
+        if (prev_dst >= 0) res_p[prev_dst * (kBtTH * 4)] = prev_h + prev_s;
+        const float dot = (dot_a.x + dot_a.y) + (dot_b.x + dot_b.y);
+        prev_h = dot + __shfl_xor_sync(kFull, dot, 2);         // first step: in flight across the loop back-edge
         prev_dst = (on && q == 0) ? dq : -1;
       };
       auto walk = [&](auto fast) {
@@ -251,9 +259,8 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
         }
       };
       if (smask == 0u) walk(std::true_type{}); else walk(std::false_type{});
-      prev_dot += __shfl_xor_sync(kFull, prev_dot, 2);
-      prev_dot += __shfl_xor_sync(kFull, prev_dot, 1);
-      if (prev_dst >= 0) res_p[prev_dst * (kBtTH * 4)] = prev_dot;
+      const float last_s = __shfl_xor_sync(kFull, prev_h, 1);
+      if (prev_dst >= 0) res_p[prev_dst * (kBtTH * 4)] = prev_h + last_s;
     }
     __syncthreads();
     // ---- grad_depth of the chunk: one 16-byte segment per (bin, row); the entry is this thread's own
