@@ -109,8 +109,7 @@ int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const vo
  * plan (cell_of_point is identical; cell_start / sorted_ids / sorted_cells describe RUNS: the first
  * point of each run, ordered by (cell, point id)) plus run_code int32[B*Np]: the run's slot for the
  * first point of a run, -2 for its continuation points, -1 for dropped points.
- * Returns BEVPOOL_E_RANGE when the grid has more than 2^18 or fewer than 2^9 cells per sample (use
- * the point plan).  run_rows: caller-owned scratch of run_rows_capacity rows of `channels` floats;
+ * Any grid size.  run_rows: caller-owned scratch of run_rows_capacity rows of `channels` floats;
  * capacity must be >= the largest number of runs in any group of BEVPOOL_RUN_CHUNK (default 8)
  * consecutive samples (default: all) -- the total run count cell_start[B*X*Y] always suffices.
  * workspace: bevpool_forward_workspace_bytes(channels) bytes, as for the other forward entry points.

@@ -290,87 +290,310 @@ plan_key_msd_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X,
     hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
 }
 
-// ---- run plans: same as plan_key_msd_kernel, but only the FIRST point of every run enters the sort ----
+// ==== run plans ===================================================================================
 // Points are enumerated (n, d, h, w); the vertical predecessor of point p is p - W.  A kept point starts
 // a run when it is the first row of a kRunHB-row block or its predecessor lies in another cell (or was
-// dropped).  run_code: cell id for run heads (replaced by the run's slot once the sort has placed it),
-// kRunCont for continuation points, kRunDropped for dropped points.
+// dropped).  Only run heads are sorted -- 11x fewer entries than kept points at the aiMotive shape -- and
+// with so few entries a radix sort is mostly launch and latency overhead.  Instead:
+//   K1 plan_key_runs_kernel   cell index, run_code, per-cell run counts (integer atomicAdd), and every
+//                             warp's run heads compacted into its own slice of a (cell, id) list
+//   K2 scan_exclusive_kernel  counts -> cell_start (CSR over runs)
+//   K3 run_place_kernel       head -> some position of its cell's segment (atomic cursor: arbitrary order)
+//   K4 run_finish_kernel      one thread per cell: orders the segment by point id (median 2 runs per cell),
+//                             writes sorted_ids / sorted_cells and each head's slot into run_code
+// The result does not depend on the order the atomics happened in: a deterministic, stable sort.
 __device__ __forceinline__ int cell_of_xyz(int x, int y, int z, int X, int Y, int Z) {
   // reference bounds test, voxel_pooling_forward_cuda.cu:24; z gates only (:32-33)
   return (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) ? y * X + x : -1;
 }
 
+constexpr int kRunWarpSlots = kSortItems * 32;   // points (= upper bound of run heads) one warp of K1 handles
+
 __global__ void __launch_bounds__(kSortThreads)
 plan_key_runs_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
                      int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code,
-                     uint32_t *__restrict__ hist, int low_bits, int bins, int tiles_per_sample,
-                     FastDiv div_w, FastDiv div_h) {
-  extern __shared__ uint32_t s_hist[];
+                     uint32_t *__restrict__ counts, int32_t *__restrict__ head_cells,
+                     int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
+                     uint32_t *__restrict__ sample_total, int tiles_per_sample, FastDiv div_w, FastDiv div_h) {
   const int b = blockIdx.y, tile = blockIdx.x;
-  for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
-  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t sample_base = (int64_t)b * num_points;
   const int64_t tile_base = (int64_t)tile * kSortTile;
+  const int64_t cells = (int64_t)X * Y;
   const int W = (int)div_w.div, H = (int)div_h.div;
   const bool vec = ((sample_base + tile_base) & 3) == 0 && (W & 3) == 0;   // quads are 16-byte aligned and stay in one row
+  const int64_t region = (((int64_t)b * tiles_per_sample + tile) * kSortWarps + warp) * kRunWarpSlots;
+  uint32_t filled = 0;                 // heads this warp has written so far (warp-uniform)
 #pragma unroll
   for (int q = 0; q < kSortItems / 4; ++q) {
     const int64_t p0 = tile_base + ((int64_t)q * kSortThreads + threadIdx.x) * 4;
-    if (p0 >= num_points) continue;
     const int64_t gp0 = sample_base + p0;
     int cell[4], code[4];
-    if (vec && p0 + 3 < num_points) {
-      const int4 *src = reinterpret_cast<const int4 *>(geom + gp0 * 3);
-      const int4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
-      cell[0] = cell_of_xyz(a0.x, a0.y, a0.z, X, Y, Z);
-      cell[1] = cell_of_xyz(a0.w, a1.x, a1.y, X, Y, Z);
-      cell[2] = cell_of_xyz(a1.z, a1.w, a2.x, X, Y, Z);
-      cell[3] = cell_of_xyz(a2.y, a2.z, a2.w, X, Y, Z);
-      const uint32_t row = fastdiv((uint32_t)p0, div_w);
-      const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
-      int pcell[4] = {-1, -1, -1, -1};
-      if ((h % kRunHB) != 0 && (cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0 || cell[3] >= 0)) {
-        const int4 *ps = reinterpret_cast<const int4 *>(geom + (gp0 - W) * 3);   // the row above: an L1/L2 hit
-        const int4 b0 = __ldg(ps), b1 = __ldg(ps + 1), b2 = __ldg(ps + 2);
-        pcell[0] = cell_of_xyz(b0.x, b0.y, b0.z, X, Y, Z);
-        pcell[1] = cell_of_xyz(b0.w, b1.x, b1.y, X, Y, Z);
-        pcell[2] = cell_of_xyz(b1.z, b1.w, b2.x, X, Y, Z);
-        pcell[3] = cell_of_xyz(b2.y, b2.z, b2.w, X, Y, Z);
-      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        code[k] = cell[k] < 0 ? kRunDropped : (pcell[k] != cell[k] ? cell[k] : kRunCont);
-      *reinterpret_cast<int4 *>(cell_of_point + gp0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
-      *reinterpret_cast<int4 *>(run_code + gp0) = make_int4(code[0], code[1], code[2], code[3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        cell[k] = -1;
-        code[k] = kRunDropped;
-        if (p0 + k >= num_points) continue;
-        const int32_t *g = geom + (gp0 + k) * 3;
-        cell[k] = cell_of_xyz(__ldg(g), __ldg(g + 1), __ldg(g + 2), X, Y, Z);
-        if (cell[k] >= 0) {
-          const uint32_t row = fastdiv((uint32_t)(p0 + k), div_w);
-          const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
-          int pc = -1;
-          if ((h % kRunHB) != 0) {
-            const int32_t *pg = g - (int64_t)W * 3;
-            pc = cell_of_xyz(__ldg(pg), __ldg(pg + 1), __ldg(pg + 2), X, Y, Z);
-          }
-          code[k] = pc != cell[k] ? cell[k] : kRunCont;
+    for (int k = 0; k < 4; ++k) { cell[k] = -1; code[k] = kRunDropped; }
+    if (p0 < num_points) {
+      if (vec && p0 + 3 < num_points) {
+        const int4 *src = reinterpret_cast<const int4 *>(geom + gp0 * 3);
+        const int4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+        cell[0] = cell_of_xyz(a0.x, a0.y, a0.z, X, Y, Z);
+        cell[1] = cell_of_xyz(a0.w, a1.x, a1.y, X, Y, Z);
+        cell[2] = cell_of_xyz(a1.z, a1.w, a2.x, X, Y, Z);
+        cell[3] = cell_of_xyz(a2.y, a2.z, a2.w, X, Y, Z);
+        const uint32_t row = fastdiv((uint32_t)p0, div_w);
+        const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
+        int pcell[4] = {-1, -1, -1, -1};
+        if ((h % kRunHB) != 0 && (cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0 || cell[3] >= 0)) {
+          const int4 *ps = reinterpret_cast<const int4 *>(geom + (gp0 - W) * 3);   // the row above: an L1/L2 hit
+          const int4 b0 = __ldg(ps), b1 = __ldg(ps + 1), b2 = __ldg(ps + 2);
+          pcell[0] = cell_of_xyz(b0.x, b0.y, b0.z, X, Y, Z);
+          pcell[1] = cell_of_xyz(b0.w, b1.x, b1.y, X, Y, Z);
+          pcell[2] = cell_of_xyz(b1.z, b1.w, b2.x, X, Y, Z);
+          pcell[3] = cell_of_xyz(b2.y, b2.z, b2.w, X, Y, Z);
         }
-        cell_of_point[gp0 + k] = cell[k];
-        run_code[gp0 + k] = code[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          code[k] = cell[k] < 0 ? kRunDropped : (pcell[k] != cell[k] ? cell[k] : kRunCont);
+        *reinterpret_cast<int4 *>(cell_of_point + gp0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
+        *reinterpret_cast<int4 *>(run_code + gp0) = make_int4(code[0], code[1], code[2], code[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (p0 + k >= num_points) continue;
+          const int32_t *g = geom + (gp0 + k) * 3;
+          cell[k] = cell_of_xyz(__ldg(g), __ldg(g + 1), __ldg(g + 2), X, Y, Z);
+          if (cell[k] >= 0) {
+            const uint32_t row = fastdiv((uint32_t)(p0 + k), div_w);
+            const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
+            int pc = -1;
+            if ((h % kRunHB) != 0) {
+              const int32_t *pg = g - (int64_t)W * 3;
+              pc = cell_of_xyz(__ldg(pg), __ldg(pg + 1), __ldg(pg + 2), X, Y, Z);
+            }
+            code[k] = pc != cell[k] ? cell[k] : kRunCont;
+          }
+          cell_of_point[gp0 + k] = cell[k];
+          run_code[gp0 + k] = code[k];
+        }
       }
     }
+    // warp compaction of this round's heads (order inside the slice is irrelevant: K4 orders by id)
+    const uint32_t mine = (code[0] >= 0) + (code[1] >= 0) + (code[2] >= 0) + (code[3] >= 0);
+    uint32_t incl = mine;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (code[k] >= 0) atomicAdd(s_hist + (code[k] >> low_bits), 1u);
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    uint32_t pos = filled + incl - mine;
+    filled += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (code[k] >= 0) {
+        head_cells[region + pos] = code[k];
+        head_ids[region + pos] = (int32_t)(gp0 + k);
+        atomicAdd(counts + (int64_t)b * cells + code[k], 1u);
+        ++pos;
+      }
+    }
+  }
+  __shared__ uint32_t s_cta_total;
+  if (threadIdx.x == 0) s_cta_total = 0u;
+  __syncthreads();
+  if (lane == 0) {
+    warp_count[((int64_t)b * tiles_per_sample + tile) * kSortWarps + warp] = (int32_t)filled;
+    if (filled) atomicAdd(&s_cta_total, filled);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < bins; i += kSortThreads)
-    hist[((int64_t)b * bins + i) * tiles_per_sample + tile] = s_hist[i];
+  if (threadIdx.x == 0 && s_cta_total) atomicAdd(sample_total + b, s_cta_total);   // one global atomic per CTA
+}
+
+// K2: exclusive scan of the per-cell run counts, one independent look-back chain per SAMPLE (a single
+// chain over B*G cells is latency-bound on its 250 tile hand-offs); a sample's base offset is the sum
+// of the run totals of the samples before it (accumulated by K1).  Same tile scheme as scan.cuh.
+__global__ void __launch_bounds__(kScanThreads)
+run_csr_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ cell_start, int64_t cells,
+                    const uint32_t *__restrict__ sample_total, int batch, unsigned long long *status,
+                    unsigned int *tickets, int tiles_per_sample) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_tile, s_prefix, s_base;
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) s_tile = atomicAdd(tickets + b, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t *in = counts + (int64_t)b * cells;
+  uint32_t *out = cell_start + (int64_t)b * cells;
+  unsigned long long *st_b = status + (int64_t)b * tiles_per_sample;
+  const int64_t warp_base = (int64_t)tile * kScanTile + warp * 512;
+
+  uint4 v[4];
+  uint32_t excl[4];
+  uint32_t run = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t idx = warp_base + r * 128 + lane * 4;
+    if (idx + 3 < cells) {
+      v[r] = *reinterpret_cast<const uint4 *>(in + idx);
+    } else {
+      v[r].x = idx < cells ? in[idx] : 0u;
+      v[r].y = idx + 1 < cells ? in[idx + 1] : 0u;
+      v[r].z = idx + 2 < cells ? in[idx + 2] : 0u;
+      v[r].w = 0u;
+    }
+    const uint32_t s = v[r].x + v[r].y + v[r].z + v[r].w;
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    excl[r] = run + incl - s;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) s_warp[warp] = run;
+  __syncthreads();
+
+  if (warp == 0) {
+    const uint32_t w = lane < kScanThreads / 32 ? s_warp[lane] : 0u;
+    uint32_t incl = w;
+#pragma unroll
+    for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, kScanThreads / 32 - 1);
+    if (lane < kScanThreads / 32) s_warp[lane] = incl - w;
+    // base of this sample = runs of all earlier samples
+    uint32_t base = 0;
+    for (int i = lane; i < b; i += 32) base += sample_total[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+
+    uint32_t exclusive = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(st_b, kScanPrefix | total);
+      if (b == batch - 1 && lane == 0) cell_start[(int64_t)batch * cells] = base + sample_total[b];
+    } else {
+      if (lane == 0) st_volatile_u64(st_b + tile, kScanAggregate | total);
+      int64_t look = (int64_t)tile - 1;
+      while (true) {
+        const int64_t idx = look - lane;
+        unsigned long long st;
+        do {
+          st = idx >= 0 ? ld_volatile_u64(st_b + idx) : kScanPrefix;
+        } while (__any_sync(0xffffffffu, (st >> 32) == 0ull));
+        const unsigned pm = __ballot_sync(0xffffffffu, (st >> 32) == 2ull);
+        const int first = pm ? __ffs(pm) - 1 : 32;
+        uint32_t contrib = lane <= first ? (uint32_t)(st & 0xffffffffull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        exclusive += contrib;
+        if (pm) break;
+        look -= 32;
+      }
+      if (lane == 0) st_volatile_u64(st_b + tile, kScanPrefix | (uint64_t)(exclusive + total));
+    }
+    if (lane == 0) { s_prefix = exclusive; s_base = base; }
+  }
+  __syncthreads();
+
+  const uint32_t base = s_base + s_prefix + s_warp[warp];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t idx = warp_base + r * 128 + lane * 4;
+    uint4 o;
+    o.x = base + excl[r];
+    o.y = o.x + v[r].x;
+    o.z = o.y + v[r].y;
+    o.w = o.z + v[r].z;
+    if (idx + 3 < cells) {
+      *reinterpret_cast<uint4 *>(out + idx) = o;
+    } else {
+      if (idx < cells) out[idx] = o.x;
+      if (idx + 1 < cells) out[idx + 1] = o.y;
+      if (idx + 2 < cells) out[idx + 2] = o.z;
+    }
+  }
+}
+
+// K3: eight lanes per K1 warp slice (a slice holds 11 heads on average)
+__global__ void __launch_bounds__(256)
+run_place_kernel(const int32_t *__restrict__ head_cells, const int32_t *__restrict__ head_ids,
+                 const int32_t *__restrict__ warp_count, const uint32_t *__restrict__ cell_start,
+                 uint32_t *__restrict__ counts, int32_t *__restrict__ placed_ids,
+                 int32_t *__restrict__ placed_cells, int64_t num_slices, int slices_per_sample,
+                 int64_t cells_per_sample) {
+  const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int l8 = threadIdx.x & 7;
+  if (slice >= num_slices) return;
+  const int n = warp_count[slice];
+  const int64_t cell_base = (slice / slices_per_sample) * cells_per_sample;
+  for (int i = l8; i < n; i += 8) {
+    const int64_t gc = cell_base + head_cells[slice * kRunWarpSlots + i];
+    const uint32_t left = atomicSub(counts + gc, 1u);          // the per-cell count doubles as the cursor
+    const uint32_t pos = cell_start[gc] + left - 1u;
+    placed_ids[pos] = head_ids[slice * kRunWarpSlots + i];
+    placed_cells[pos] = (int32_t)gc;
+  }
+}
+
+// K4: one thread per run head; rank of a head = number of heads of its cell with a smaller point id (the
+// cell's segment is a handful of consecutive ints: L1 hits).  Cells with more than kRunSmallCell runs
+// (none for camera rigs: the aiMotive shapes peak at 54 runs per cell) are queued for K5 by the thread
+// that holds the segment's first entry, so no thread ever walks a long segment.
+constexpr uint32_t kRunSmallCell = 64;
+__global__ void __launch_bounds__(256)
+run_finish_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__restrict__ placed_ids,
+                  const int32_t *__restrict__ placed_cells, int64_t total_cells, int32_t *__restrict__ sorted_ids,
+                  int32_t *__restrict__ sorted_cells, int32_t *__restrict__ run_code, int32_t *__restrict__ big_list,
+                  uint32_t *__restrict__ big_count) {
+  const uint32_t total = cell_start[total_cells];
+  for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += gridDim.x * blockDim.x) {
+    const int32_t gc = placed_cells[pos];
+    const uint32_t s = cell_start[gc], e = cell_start[gc + 1];
+    if (e - s > kRunSmallCell) {
+      if (pos == s) big_list[atomicAdd(big_count, 1u)] = gc;     // (order of the queue is irrelevant)
+      continue;
+    }
+    const int32_t id = placed_ids[pos];
+    uint32_t rank = 0;
+    for (uint32_t j = s; j < e; ++j) rank += placed_ids[j] < id;
+    sorted_ids[s + rank] = id;
+    sorted_cells[s + rank] = gc;
+    run_code[id] = (int32_t)(s + rank);
+  }
+}
+
+// K5: one CTA per queued cell, same rank rule with the ids staged through shared memory
+__global__ void __launch_bounds__(256)
+run_finish_big_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__restrict__ placed_ids,
+                      const int32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
+                      int32_t *__restrict__ sorted_ids, int32_t *__restrict__ sorted_cells,
+                      int32_t *__restrict__ run_code) {
+  constexpr int kTile = 2048;
+  __shared__ int32_t s_ids[kTile];
+  const uint32_t nbig = *big_count;
+  for (uint32_t q = blockIdx.x; q < nbig; q += gridDim.x) {
+    const int64_t gc = big_list[q];
+    const uint32_t s = cell_start[gc], n = cell_start[gc + 1] - s;
+    for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+      const uint32_t i = i0 + threadIdx.x;
+      const int32_t id = i < n ? placed_ids[s + i] : INT32_MAX;
+      uint32_t rank = 0;
+      for (uint32_t j0 = 0; j0 < n; j0 += kTile) {
+        __syncthreads();
+        const uint32_t m = min((uint32_t)kTile, n - j0);
+        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) s_ids[j] = placed_ids[s + j0 + j];
+        __syncthreads();
+        for (uint32_t j = 0; j < m; ++j) rank += s_ids[j] < id;
+      }
+      if (i < n) {
+        sorted_ids[s + rank] = id;
+        sorted_cells[s + rank] = (int32_t)gc;
+        run_code[id] = (int32_t)(s + rank);
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kSortThreads)
@@ -606,15 +829,43 @@ extern "C" int bevpool_plan_views(const void *plan, int batch, int64_t num_point
   return BEVPOOL_OK;
 }
 
-// ---- run plan (fused op): see common.cuh.  Same pipeline as the MSD point plan, on run heads only. ----
+// ---- run plan (fused op): see common.cuh and the K1..K4 kernels above ----
+struct RunTempLayout {
+  size_t off_scan, off_counts, zero_bytes;     // [0, zero_bytes) is memset to 0 per build
+  size_t off_big_count, off_sample_total, off_tickets, off_status;   // (inside the zeroed part)
+  size_t off_head_cells, off_head_ids, off_warp_count, off_placed, off_placed_cells, off_big_list, bytes;
+  int tiles_per_sample;
+};
+static RunTempLayout run_temp_layout(int batch, int64_t num_points, int X, int Y) {
+  RunTempLayout L{};
+  L.tiles_per_sample = (int)ceil_div64(num_points, kSortTile);
+  const size_t G1 = (size_t)batch * X * Y + 1;
+  const size_t slices = (size_t)batch * L.tiles_per_sample * kSortWarps;
+  size_t o = 0;
+  L.off_scan = o;        o += scan_workspace_bytes((int64_t)G1);
+  L.off_counts = o;      o = align_up(o + G1 * 4, 256);
+  L.off_big_count = o;   o += 256;
+  L.off_sample_total = o; o = align_up(o + (size_t)batch * 4, 256);
+  L.off_tickets = o;     o = align_up(o + (size_t)batch * 4, 256);
+  L.off_status = o;      o = align_up(o + (size_t)batch * scan_num_tiles((int64_t)X * Y) * 8, 256);
+  L.zero_bytes = o;
+  L.off_head_cells = o;  o = align_up(o + slices * kRunWarpSlots * 4, 256);
+  L.off_head_ids = o;    o = align_up(o + slices * kRunWarpSlots * 4, 256);
+  L.off_warp_count = o;  o = align_up(o + slices * 4, 256);
+  L.off_placed = o;      o = align_up(o + (size_t)batch * num_points * 4, 256);
+  L.off_placed_cells = o; o = align_up(o + (size_t)batch * num_points * 4, 256);
+  L.off_big_list = o;    o = align_up(o + ((size_t)batch * num_points / 16 + 1) * 4, 256);
+  L.bytes = o;
+  return L;
+}
+
 extern "C" int bevpool_runplan_sizes(int batch, int64_t num_points, int X, int Y, size_t *plan_bytes,
                                      size_t *temp_bytes) {
   int rc = check_plan_dims(batch, num_points, X, Y);
   if (rc) return rc;
   if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
-  if (!sort_config((int64_t)X * Y).msd) return BEVPOOL_E_RANGE;   // grids of 2^9 .. 2^18 cells per sample
   *plan_bytes = plan_layout(batch, num_points, X, Y, true).bytes;
-  *temp_bytes = temp_layout(batch, num_points, X, Y).bytes;
+  *temp_bytes = run_temp_layout(batch, num_points, X, Y).bytes;
   return BEVPOOL_OK;
 }
 
@@ -626,37 +877,52 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
   if (rc) return rc;
   if (!geom || !plan || !temp || Z <= 0) return BEVPOOL_E_ARG;
   if (!aligned16(plan) || !aligned16(temp) || !aligned16(geom)) return BEVPOOL_E_ALIGN;
+  if (batch > 65535) return BEVPOOL_E_RANGE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int64_t cells = (int64_t)X * Y;
-  const SortConfig sc = sort_config(cells);
-  if (!sc.msd) return BEVPOOL_E_RANGE;
+  const int64_t cells = (int64_t)X * Y, total_cells = (int64_t)batch * cells;
   const PlanLayout PL = plan_layout(batch, num_points, X, Y, true);
-  const TempLayout TL = temp_layout(batch, num_points, X, Y);
+  const RunTempLayout TL = run_temp_layout(batch, num_points, X, Y);
   char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
   int32_t *cell_of_point = reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point);
-  int32_t *cell_start = reinterpret_cast<int32_t *>(pb + PL.off_cell_start);
+  uint32_t *cell_start = reinterpret_cast<uint32_t *>(pb + PL.off_cell_start);
   int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
   int32_t *sorted_cells = reinterpret_cast<int32_t *>(pb + PL.off_sorted_cells);
   int32_t *run_code = reinterpret_cast<int32_t *>(pb + PL.off_run_code);
-  uint32_t *hist = reinterpret_cast<uint32_t *>(tb + TL.off_hist[0]);
-  int32_t *keys = reinterpret_cast<int32_t *>(tb + TL.off_keys[0]);
-  int32_t *ids = reinterpret_cast<int32_t *>(tb + TL.off_ids[0]);
+  uint32_t *counts = reinterpret_cast<uint32_t *>(tb + TL.off_counts);
+  int32_t *head_cells = reinterpret_cast<int32_t *>(tb + TL.off_head_cells);
+  int32_t *head_ids = reinterpret_cast<int32_t *>(tb + TL.off_head_ids);
+  int32_t *warp_count = reinterpret_cast<int32_t *>(tb + TL.off_warp_count);
+  int32_t *placed = reinterpret_cast<int32_t *>(tb + TL.off_placed);
+  int32_t *placed_cells = reinterpret_cast<int32_t *>(tb + TL.off_placed_cells);
+  uint32_t *sample_total = reinterpret_cast<uint32_t *>(tb + TL.off_sample_total);
   const int T = TL.tiles_per_sample;
-  const dim3 grid(T, batch);
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(pb, 0, PL.off_cell_of_point, stream));
-  const int low = sc.bits[0], bins_hi = 1 << sc.bits[1];
-  plan_key_runs_kernel<<<grid, kSortThreads, bins_hi * 4, stream>>>(
-      geom, num_points, X, Y, Z, cell_of_point, run_code, hist, low, bins_hi, T,
+  plan_key_runs_kernel<<<dim3(T, batch), kSortThreads, 0, stream>>>(
+      geom, num_points, X, Y, Z, cell_of_point, run_code, counts, head_cells, head_ids, warp_count, sample_total, T,
       make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h));
   BEVPOOL_LAUNCH_CHECK();
-  rc = launch_scan_exclusive(hist, hist, TL.hist_n[0], tb + TL.off_scan[0], stream);
-  if (rc) return rc;
-  sort_scatter_kernel<true><<<grid, kSortThreads, kSortWarps * bins_hi * 4, stream>>>(
-      run_code, nullptr, keys, ids, nullptr, (int32_t)cells, hist, hist, bins_hi, num_points, low, bins_hi, T);
+  if ((cells & 3) == 0) {            // per-sample chains (16-byte aligned sample segments)
+    const int tps = (int)scan_num_tiles(cells);
+    run_csr_scan_kernel<<<dim3(tps, batch), kScanThreads, 0, stream>>>(
+        counts, cell_start, cells, sample_total, batch, reinterpret_cast<unsigned long long *>(tb + TL.off_status),
+        reinterpret_cast<unsigned int *>(tb + TL.off_tickets), tps);
+    BEVPOOL_LAUNCH_CHECK();
+  } else {
+    rc = launch_scan_exclusive(counts, cell_start, total_cells + 1, tb + TL.off_scan, stream);
+    if (rc) return rc;
+  }
+  const int64_t slices = (int64_t)batch * T * kSortWarps;
+  run_place_kernel<<<(unsigned)ceil_div64(slices * 8, 256), 256, 0, stream>>>(
+      head_cells, head_ids, warp_count, cell_start, counts, placed, placed_cells, slices, T * kSortWarps, cells);
   BEVPOOL_LAUNCH_CHECK();
-  bucket_sort_kernel<<<dim3(bins_hi, batch), kSortThreads, 0, stream>>>(
-      keys, ids, hist, bins_hi, T, low, (int32_t)cells, batch, cell_start, sorted_ids, sorted_cells, run_code);
+  int32_t *big_list = reinterpret_cast<int32_t *>(tb + TL.off_big_list);
+  uint32_t *big_count = reinterpret_cast<uint32_t *>(tb + TL.off_big_count);
+  run_finish_kernel<<<kSMs * 8, 256, 0, stream>>>(
+      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count);
+  BEVPOOL_LAUNCH_CHECK();
+  run_finish_big_kernel<<<kSMs * 2, 256, 0, stream>>>(cell_start, placed, big_list, big_count, sorted_ids, sorted_cells,
+                                                  run_code);
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }

@@ -70,7 +70,8 @@ CASES = [
     (1, 1, 40, 21, 10, 64, (40, 13, 1), True),    # W % 4 != 0: scalar loads, ragged column tile
     (3, 1, 5, 7, 5, 32, (512, 64, 1), False),     # aiMotive grid, tiny frustum
     (10, 1, 6, 16, 4, 96, (32, 16, 1), True),     # more samples than one stage-A/B chunk (8)
-    (1, 2, 4, 3, 4, 128, (512, 512, 1), False),   # 2^18 cells per sample: widest MSD sort
+    (1, 2, 4, 3, 4, 128, (512, 512, 1), False),   # 2^18 cells per sample
+    (1, 1, 3, 4, 4, 32, (8, 8, 1), False),        # 64 cells
 ]
 
 
@@ -91,12 +92,21 @@ def test_run_plan_and_forward(case):
     assert torch.allclose(gc.double().cpu(), rc, rtol=1e-5, atol=1.2e-7 * D)
 
 
-def test_run_plan_falls_back_outside_its_grid_range():
-    geom = _random_geom(5, 1, 1, 3, 4, 4, (8, 8, 1), False)
-    plan = build_plan(geom.cuda(), (8, 8, 1), frustum=(1, 3, 4, 4))            # 64 cells < 2^9
-    assert plan.mode == 'points'
+def test_run_plan_tiny_grid_big_cells_and_shape_check():
+    # 4 cells and 2 400 points: every cell holds far more runs than the per-thread ordering handles
+    # (the queued-cell kernel takes over); a frustum that does not match geom_xyz is refused
+    vn = (2, 2, 1)
+    g = torch.Generator().manual_seed(5)
+    geom = torch.stack([torch.randint(0, 2, (1, 2, 30, 8, 5), generator=g), torch.randint(0, 2, (1, 2, 30, 8, 5), generator=g),
+                        torch.randint(-1, 1, (1, 2, 30, 8, 5), generator=g)], -1).int().contiguous()
+    depth, ctx, go = _features(6, 1, 2, 30, 8, 5, 32, vn)
+    plan = build_plan(geom.cuda(), vn, frustum=(2, 30, 8, 5))
+    _assert_plan(plan, geom, vn)
+    cs = plan.cell_start.cpu()
+    assert int((cs[1:] - cs[:-1]).max()) > 64
+    _assert_forward(fused_forward(plan, depth.cuda(), ctx.cuda()), geom, depth, ctx, vn)
     with pytest.raises(AssertionError):
-        build_plan(geom.cuda(), (8, 8, 1), frustum=(2, 3, 4, 4))
+        build_plan(geom.cuda(), vn, frustum=(3, 30, 8, 5))
 
 
 @pytest.mark.parametrize('cfg,B', [(CFG_2, 2), (sweep_grid_config(256), 1)])
