@@ -390,58 +390,6 @@ grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ g
   }
 }
 
-// Same result, warp-per-tile: a resident grid whose warps scan the tile list 32 tiles at a time (one
-// occupancy test per lane), so the 72 % of tiles with no kept point cost one ballot instead of a CTA
-// launch, and an occupied tile's C channel rows are requested with 10 independent 128-byte loads in
-// flight per lane.  Rows of cells without points are not written (the backward never reads them).
-constexpr int kGrWarps = 4;
-template <typename E>
-__global__ void __launch_bounds__(kGrWarps * 32)
-grad_rows_warp_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ grad_nchw,
-                      E *__restrict__ rows, int64_t G, int C, int batch, int64_t tiles_per_sample) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ld = C + 1;
-  E *tile = reinterpret_cast<E *>(smem_raw) + (size_t)warp * 32 * ld;   // [32 cells][C + 1]
-  const int64_t total = (int64_t)batch * tiles_per_sample;
-  const int64_t nw = (int64_t)gridDim.x * kGrWarps;
-  for (int64_t base = ((int64_t)blockIdx.x * kGrWarps + warp) * 32; base < total; base += nw * 32) {
-    const int64_t t = base + lane;
-    bool occ = false;
-    if (t < total) {
-      const int64_t b = t / tiles_per_sample, c0 = (t - b * tiles_per_sample) * 32;
-      const int64_t c1 = min(G, c0 + 32);
-      occ = __ldg(cell_start + b * G + c1) > __ldg(cell_start + b * G + c0);
-    }
-    unsigned mask = __ballot_sync(0xffffffffu, occ);
-    while (mask) {
-      const int j = __ffs(mask) - 1;
-      mask &= mask - 1u;
-      const int64_t tt = base + j;
-      const int64_t b = tt / tiles_per_sample, cell0 = (tt - b * tiles_per_sample) * 32;
-      const int ncell = (int)min((int64_t)32, G - cell0);
-      const int64_t gc = b * G + cell0;
-      const int cs = __ldg(cell_start + gc + min(lane, ncell)), ce = __ldg(cell_start + gc + min(lane + 1, ncell));
-      unsigned om = __ballot_sync(0xffffffffu, lane < ncell && ce > cs);
-      const E *src = grad_nchw + (b * C) * G + cell0 + lane;
-#pragma unroll 10
-      for (int ch = 0; ch < C; ++ch) {
-        E v = 0;
-        if (lane < ncell) v = src[(int64_t)ch * G];
-        tile[lane * ld + ch] = v;
-      }
-      __syncwarp();
-      while (om) {
-        const int r = __ffs(om) - 1;
-        om &= om - 1u;
-        E *rp = rows + (gc + r) * C;
-        for (int ch = lane; ch < C; ch += 32) rp[ch] = tile[r * ld + ch];
-      }
-      __syncwarp();
-    }
-  }
-}
-
 // ---- (batch, R, Cc) -> (batch, Cc, R) tiled transpose ----------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -687,28 +635,6 @@ extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, vo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const PlanView pv = plan_view(plan, batch, num_points, X, Y);
   const int64_t G = (int64_t)X * Y;
-  if (env_int("BEVPOOL_GRAD_ROWS", 0) == 1 && (dtype == BEVPOOL_F32 || dtype == BEVPOOL_F16 || dtype == BEVPOOL_BF16)) {
-    const int es = dtype == BEVPOOL_F32 ? 4 : 2;
-    const size_t smem = (size_t)kGrWarps * 32 * (channels + 1) * es;
-    const int64_t tps = ceil_div64(G, 32);
-    int per_sm = (int)((size_t)200 * 1024 / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    const int64_t want = ceil_div64((int64_t)batch * tps, kGrWarps * 32);
-    const unsigned ctas = (unsigned)(want < (int64_t)sm_count() * per_sm ? (want < 1 ? 1 : want) : (int64_t)sm_count() * per_sm);
-    if (es == 4) {
-      if (smem > 48 * 1024)
-        BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(grad_rows_warp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      grad_rows_warp_kernel<uint32_t><<<ctas, kGrWarps * 32, smem, s>>>(pv.cell_start, static_cast<const uint32_t *>(grad_out_nchw),
-                                                                    static_cast<uint32_t *>(rows_nhwc), G, channels, batch, tps);
-    } else {
-      if (smem > 48 * 1024)
-        BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(grad_rows_warp_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      grad_rows_warp_kernel<uint16_t><<<ctas, kGrWarps * 32, smem, s>>>(pv.cell_start, static_cast<const uint16_t *>(grad_out_nchw),
-                                                                    static_cast<uint16_t *>(rows_nhwc), G, channels, batch, tps);
-    }
-    BEVPOOL_LAUNCH_CHECK();
-    return BEVPOOL_OK;
-  }
   const dim3 grid((unsigned)ceil_div64(G, 32 * kGrTilesPerCta), (unsigned)batch);
   if (dtype == BEVPOOL_F32) {
     const size_t smem = (size_t)32 * (channels + 1) * 4;
