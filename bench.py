@@ -379,6 +379,25 @@ def main():
     k_bwd = time_cuda(lambda: fused_backward(plan, go_nhwc, depth, ctx_nhwc), 20, 3)
     stages['fused_forward_kernel'] = k_fwd
     stages['fused_backward_kernel'] = k_bwd
+    # ---- the same step when the caller keeps context and gradient channels_last (zero-copy layouts: no
+    # context / context-gradient transposes, no gradient-row pass); reported beside the headline, not as it
+    def step_cl():
+        p = build_plan(geom, vn, frustum=frustum, max_runs=max_runs)
+        o = fused_forward(p, depth, ctx_nhwc)
+        return o, fused_backward(p, go_nhwc, depth, ctx_nhwc)
+    cl_ms = None
+    try:
+        s2 = torch.cuda.Stream()
+        s2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s2):
+            step_cl()
+        torch.cuda.current_stream().wait_stream(s2)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            keep2 = step_cl()                                   # noqa: F841
+        cl_ms = time_cuda(g2.replay, 20, 3)
+    except Exception as e:                                      # pragma: no cover
+        print(f'[bench] channels_last side measurement failed ({e})', file=sys.stderr)
     dom_name, dom = ('fused_backward', k_bwd) if k_bwd[0] >= k_fwd[0] else ('fused_forward', k_fwd)
     achieved = bytes_[dom_name] * B / (dom[0] * 1e-3) / 1e9
     traffic = None                      # dram__bytes_read+write per launch of that kernel, from the committed ncu capture
@@ -404,6 +423,10 @@ def main():
             'step_roofline': {'algorithmic_bytes_per_frame': bytes_['step'], 'achieved': step_gbs, 'unit': 'GB/s',
                               'frac': step_gbs / peak_gbs, 'frac_of_nominal_8TBps': step_gbs / 8000.0},
             'stages_ms': {k: {'median': v[0], 'min': v[1]} for k, v in stages.items()},
+            'channels_last_step': (None if cl_ms is None else
+                                   {'what': 'same step with channels_last context and incoming gradient (zero-copy '
+                                            'layouts: no transposes, no gradient-row pass), CUDA graph replay, this rank',
+                                    'ms_per_step': cl_ms[0], 'frames_per_s': B / (cl_ms[0] * 1e-3)}),
             'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks.summary()}
 
