@@ -152,6 +152,43 @@ def run_cpu_baseline(cfg, frames: int, iters: int):
                       f'materialise + index_add_ forward + autograd backward', 'ms_per_frame': best / frames * 1e3}
 
 
+def run_sweep(dev, peak_gbs, seed=7):
+    """BASELINE.json configs[4] in miniature: batch 1..64 on the aiMotive grid and the three square grids
+    at batch 8, same step (cold plan + fused forward + backward, NCHW layouts), one CUDA graph each."""
+    from mm_training_b200.configs import sweep_grid_config
+    from mm_training_b200.ops.voxel_pooling import build_plan, context_rows_nhwc, fused_backward, fused_forward
+    points = [(CFG_2, 1), (CFG_2, 8), (CFG_2, 64)] + [(sweep_grid_config(g), 8) for g in (128, 256, 512)]
+    rows_out = []
+    for cfg, B in points:
+        geom, vn_t = synthetic.camera_rig(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=seed)
+        vn = tuple(int(v) for v in vn_t.tolist())
+        depth, ctx, go = synthetic.camera_features(cfg, B, device=dev, seed=seed)
+        fr = tuple(geom.shape[1:5])
+        n = build_plan(geom, vn, frustum=fr).num_sorted
+
+        def step():
+            plan = build_plan(geom, vn, frustum=fr, max_runs=n)
+            rows = context_rows_nhwc(ctx)
+            out = fused_forward(plan, depth, ctx, rows)
+            return out, fused_backward(plan, go, depth, ctx, rows)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            keep = step()                                       # noqa: F841
+        med, _ = time_cuda(g.replay, 20, 3)
+        kept = int((build_plan(geom, vn).cell_of_point >= 0).sum().item()) / B
+        gbs = algorithmic_bytes(cfg, kept)['step'] * B / (med * 1e-3) / 1e9
+        rows_out.append({'workload': cfg.name, 'frames_per_step': B, 'ms_per_step': med,
+                         'frames_per_s': B / (med * 1e-3), 'frac_of_hbm_peak': gbs / peak_gbs})
+        del g, keep, geom, depth, ctx, go
+        torch.cuda.empty_cache()
+    return rows_out
+
+
 def run_lidar_side(dev, peak_gbs, sweeps: int = 8):
     """Side measurement (not the headline metric): ``sweeps`` synthetic 200k-point long-range sweeps
      through voxelize (+ fused HardSimpleVFE mean) and pillar scatter, and the
@@ -455,6 +492,12 @@ def main():
 
         # ---- CPU baseline: oracle port on the host cores, bounded sample
         line['cpu_baseline'] = run_cpu_baseline(cfg, 2, 3)
+
+        # ---- batch / grid sweep (BASELINE.json configs[4], single GPU)
+        try:
+            line['sweep'] = run_sweep(dev, peak_gbs)
+        except Exception as e:                                  # pragma: no cover
+            line['sweep'] = {'error': repr(e)}
 
         # ---- LiDAR branch (BASELINE.json configs[2]): hard voxelization + HardSimpleVFE mean + pillar scatter
         try:

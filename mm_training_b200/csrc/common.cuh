@@ -90,7 +90,7 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
 
 // ---- plan layout -------------------------------------------------------------------
 // A plan is one caller-owned buffer:
-//   header (256 B) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
+//   header (256 B, reserved: neither written nor read) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
 //   | sorted_cells int32[B*Np]
 // sorted_ids[k] is the global point id of the k-th kept point in (cell, point id) order and
 // sorted_cells[k] its global output row b*G + cell; only the first K = cell_start[B*G] entries
@@ -98,7 +98,7 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
 struct PlanLayout {
   size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, off_run_code, bytes;
 };
-struct PlanHeader {       // written by the device at build time
+struct PlanHeader {       // reserved layout of the first 256 bytes (not written by this version)
   int32_t magic, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
   int64_t num_points;
   int32_t num_kept_total;  // K = cell_start[B*G]

@@ -750,7 +750,6 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
   const dim3 grid(T, batch);
 
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
-  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(pb, 0, PL.off_cell_of_point, stream));
 
   if (sc.msd) {
     const int low = sc.bits[0], bins_hi = 1 << sc.bits[1];
@@ -897,7 +896,6 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
   uint32_t *sample_total = reinterpret_cast<uint32_t *>(tb + TL.off_sample_total);
   const int T = TL.tiles_per_sample;
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
-  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(pb, 0, PL.off_cell_of_point, stream));
   plan_key_runs_kernel<<<dim3(T, batch), kSortThreads, 0, stream>>>(
       geom, num_points, X, Y, Z, cell_of_point, run_code, counts, head_cells, head_ids, warp_count, sample_total, T,
       make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h));
