@@ -66,6 +66,53 @@ __device__ __forceinline__ void stg_stream_f4(float4 *p, const float4 &v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------
+// The step is a chain of ~12 short dependent kernels; a plain stream edge costs 2-3 us per link (the next
+// grid is only scheduled after the previous one has drained).  Kernels of the fused path are launched with
+// the programmatic-stream-serialization attribute: every CTA signals "dependents may be scheduled" at its
+// very top, so the next grid's CTAs take the SM slots the last wave frees and sit in pdl_wait() -- which
+// returns only when the whole previous grid has completed and its writes are visible.  pdl_wait() is the
+// FIRST statement of every such kernel (before any early return), so completion stays transitive along the
+// chain.  Both instructions are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();     // plan.cu: BEVPOOL_PDL != 0
+
+bool pdl_forward_enabled();   // plan.cu: BEVPOOL_PDL_FWD == 1 (off by default: measured slower for stage A -> stage B)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_if(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (allow && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -13,9 +13,21 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace bevpool {
 
 std::atomic<long long> g_kernel_launches{0};
+
+bool pdl_forward_enabled() {
+  static const bool on = [] { const char *e = std::getenv("BEVPOOL_PDL_FWD"); return e && e[0] == '1'; }();
+  return on;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char *e = std::getenv("BEVPOOL_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
@@ -315,6 +327,8 @@ plan_key_runs_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X
                      uint32_t *__restrict__ counts, int32_t *__restrict__ head_cells,
                      int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
                      uint32_t *__restrict__ sample_total, int tiles_per_sample, FastDiv div_w, FastDiv div_h) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y, tile = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t sample_base = (int64_t)b * num_points;
@@ -414,6 +428,8 @@ __global__ void __launch_bounds__(kScanThreads)
 run_csr_scan_kernel(const uint32_t *__restrict__ counts, uint32_t *__restrict__ cell_start, int64_t cells,
                     const uint32_t *__restrict__ sample_total, int batch, unsigned long long *status,
                     unsigned int *tickets, int tiles_per_sample) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ uint32_t s_warp[kScanThreads / 32];
   __shared__ uint32_t s_tile, s_prefix, s_base;
   const int b = blockIdx.y;
@@ -523,6 +539,8 @@ run_place_kernel(const int32_t *__restrict__ head_cells, const int32_t *__restri
                  uint32_t *__restrict__ counts, int32_t *__restrict__ placed_ids,
                  int32_t *__restrict__ placed_cells, int64_t num_slices, int slices_per_sample,
                  int64_t cells_per_sample) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int l8 = threadIdx.x & 7;
   if (slice >= num_slices) return;
@@ -547,6 +565,8 @@ run_finish_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__rest
                   const int32_t *__restrict__ placed_cells, int64_t total_cells, int32_t *__restrict__ sorted_ids,
                   int32_t *__restrict__ sorted_cells, int32_t *__restrict__ run_code, int32_t *__restrict__ big_list,
                   uint32_t *__restrict__ big_count) {
+  pdl_wait();
+  pdl_trigger();
   const uint32_t total = cell_start[total_cells];
   for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < total; pos += gridDim.x * blockDim.x) {
     const int32_t gc = placed_cells[pos];
@@ -570,6 +590,8 @@ run_finish_big_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__
                       const int32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
                       int32_t *__restrict__ sorted_ids, int32_t *__restrict__ sorted_cells,
                       int32_t *__restrict__ run_code) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int kTile = 2048;
   __shared__ int32_t s_ids[kTile];
   const uint32_t nbig = *big_count;
@@ -896,31 +918,31 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
   uint32_t *sample_total = reinterpret_cast<uint32_t *>(tb + TL.off_sample_total);
   const int T = TL.tiles_per_sample;
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
-  plan_key_runs_kernel<<<dim3(T, batch), kSortThreads, 0, stream>>>(
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(plan_key_runs_kernel, dim3(T, batch), dim3(kSortThreads), 0, stream,
       geom, num_points, X, Y, Z, cell_of_point, run_code, counts, head_cells, head_ids, warp_count, sample_total, T,
-      make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h));
+      make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h)));
   BEVPOOL_LAUNCH_CHECK();
   if ((cells & 3) == 0) {            // per-sample chains (16-byte aligned sample segments)
     const int tps = (int)scan_num_tiles(cells);
-    run_csr_scan_kernel<<<dim3(tps, batch), kScanThreads, 0, stream>>>(
+    BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_csr_scan_kernel, dim3(tps, batch), dim3(kScanThreads), 0, stream,
         counts, cell_start, cells, sample_total, batch, reinterpret_cast<unsigned long long *>(tb + TL.off_status),
-        reinterpret_cast<unsigned int *>(tb + TL.off_tickets), tps);
+        reinterpret_cast<unsigned int *>(tb + TL.off_tickets), tps));
     BEVPOOL_LAUNCH_CHECK();
   } else {
     rc = launch_scan_exclusive(counts, cell_start, total_cells + 1, tb + TL.off_scan, stream);
     if (rc) return rc;
   }
   const int64_t slices = (int64_t)batch * T * kSortWarps;
-  run_place_kernel<<<(unsigned)ceil_div64(slices * 8, 256), 256, 0, stream>>>(
-      head_cells, head_ids, warp_count, cell_start, counts, placed, placed_cells, slices, T * kSortWarps, cells);
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_place_kernel, dim3((unsigned)ceil_div64(slices * 8, 256)), dim3(256), 0, stream,
+      head_cells, head_ids, warp_count, cell_start, counts, placed, placed_cells, slices, T * kSortWarps, cells));
   BEVPOOL_LAUNCH_CHECK();
   int32_t *big_list = reinterpret_cast<int32_t *>(tb + TL.off_big_list);
   uint32_t *big_count = reinterpret_cast<uint32_t *>(tb + TL.off_big_count);
-  run_finish_kernel<<<kSMs * 8, 256, 0, stream>>>(
-      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count);
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_kernel, dim3(kSMs * 8), dim3(256), 0, stream,
+      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count));
   BEVPOOL_LAUNCH_CHECK();
-  run_finish_big_kernel<<<kSMs * 2, 256, 0, stream>>>(cell_start, placed, big_list, big_count, sorted_ids, sorted_cells,
-                                                  run_code);
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_big_kernel, dim3(kSMs * 2), dim3(256), 0, stream,
+                                    cell_start, placed, big_list, big_count, sorted_ids, sorted_cells, run_code));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }

@@ -341,6 +341,8 @@ template <typename E>
 __global__ void __launch_bounds__(256)
 grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ grad_nchw,
                  E *__restrict__ rows, int64_t G, int C) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   E *tile = reinterpret_cast<E *>(smem_raw);   // [32][C + 1]
   __shared__ unsigned s_occ[kGrTilesPerCta];
@@ -394,6 +396,8 @@ grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ g
 template <typename T>
 __global__ void __launch_bounds__(256)
 transpose_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t R, int64_t Cc) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ T tile[32][33];
   const int64_t batch_off = (int64_t)blockIdx.z * R * Cc;
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
@@ -640,8 +644,8 @@ extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, vo
     const size_t smem = (size_t)32 * (channels + 1) * 4;
     if (smem > 48 * 1024)
       BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(grad_rows_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    grad_rows_kernel<uint32_t><<<grid, 256, smem, s>>>(pv.cell_start, static_cast<const uint32_t *>(grad_out_nchw),
-                                                      static_cast<uint32_t *>(rows_nhwc), G, channels);
+    BEVPOOL_RETURN_IF_CUDA(launch_pdl(grad_rows_kernel<uint32_t>, grid, dim3(256), smem, s, pv.cell_start,
+                                      static_cast<const uint32_t *>(grad_out_nchw), static_cast<uint32_t *>(rows_nhwc), G, channels));
   } else if (dtype == BEVPOOL_F16 || dtype == BEVPOOL_BF16) {
     const size_t smem = (size_t)32 * (channels + 1) * 2;
     grad_rows_kernel<uint16_t><<<grid, 256, smem, s>>>(pv.cell_start, static_cast<const uint16_t *>(grad_out_nchw),
@@ -660,7 +664,8 @@ extern "C" int bevpool_transpose(const void *in, void *out, int dtype, int batch
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const dim3 grid((unsigned)ceil_div64(cols, 32), (unsigned)ceil_div64(rows, 32), (unsigned)batch);
   if (dtype == BEVPOOL_F32) {
-    transpose_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float *>(in), static_cast<float *>(out), rows, cols);
+    BEVPOOL_RETURN_IF_CUDA(launch_pdl(transpose_kernel<float>, grid, dim3(256), 0, s, static_cast<const float *>(in),
+                                      static_cast<float *>(out), rows, cols));
   } else if (dtype == BEVPOOL_F16 || dtype == BEVPOOL_BF16) {
     transpose_kernel<uint16_t><<<grid, 256, 0, s>>>(static_cast<const uint16_t *>(in), static_cast<uint16_t *>(out), rows, cols);
   } else {

@@ -52,6 +52,8 @@ fused_backward_tile_kernel(const int32_t *__restrict__ cell_of_point, const floa
                            const float *__restrict__ depth, const float *__restrict__ ctx_nhwc,
                            float *__restrict__ grad_depth, float *__restrict__ grad_ctx_nhwc, int num_cams,
                            int D, int H, int W, int64_t cells_per_sample, int tiles_h, int tiles_w) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int C = 16 * NV2, C4 = C / 4, NQ = NV2;      // NQ float4 per lane
   constexpr unsigned kFull = 0xffffffffu;
   constexpr int kRowFloats = kBtDC * kBtTW * C;            // one stage of gradient rows
@@ -302,9 +304,9 @@ static int launch_bt(const int32_t *cell_of_point, const float *grad_rows, const
   if (smem > 48 * 1024)
     BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_tile_kernel<NV2, kVec, kMinCtas>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fused_backward_tile_kernel<NV2, kVec, kMinCtas><<<(unsigned)ctas, kBtThreads, smem, s>>>(
-      cell_of_point, grad_rows, depth, ctx_nhwc, grad_depth, grad_ctx_nhwc, num_cams, D, H, W, cells_per_sample,
-      tiles_h, tiles_w);
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(fused_backward_tile_kernel<NV2, kVec, kMinCtas>, dim3((unsigned)ctas), dim3(kBtThreads),
+                                    smem, s, cell_of_point, grad_rows, depth, ctx_nhwc, grad_depth, grad_ctx_nhwc, num_cams, D,
+                                    H, W, cells_per_sample, tiles_h, tiles_w));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }

@@ -115,6 +115,8 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
                           float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t cell_base,
                           int64_t total_cells, FastDiv div_dhw, FastDiv div_hw, int fill_period, int exp_mask,
                           int exp_flags) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4;
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31, l8 = lane & 7, grp = lane >> 3, warp = threadIdx.x >> 5;
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(128)
 pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_cells,
                           const float *__restrict__ ws_head, const float *__restrict__ ws_tail,
                           float *__restrict__ out, int64_t cell_base, int64_t total_cells, int num_slices) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2;
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l8 = threadIdx.x & 7;
   if (s >= num_slices) return;

@@ -151,6 +151,8 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
                       const int32_t *__restrict__ cell_start, float *__restrict__ out, int img0,
                       int64_t cell_base, int64_t num_cells, int D, int H, int W, int d_split, int d_per_cta,
                       int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2;
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char s_raw[];
@@ -386,9 +388,9 @@ static int launch_stage_a(const PlanView &pv, const float *dp, const float *cx, 
   const size_t smem = (size_t)kRunHB * kRaTW * C * 4 + (size_t)kRaStages * kRaDC * kRunHB * 32 + (size_t)kRaZeroCells * C * 4 + 16;
   if (smem > 48 * 1024)
     BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  frustum_reduce_kernel<NV2><<<(unsigned)ctas, kRaThreads, smem, s>>>(
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
       pv.run_code, dp, cx, rr, pv.cell_start, out, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
-      tiles_w, capacity, vec, fill, hints);
+      tiles_w, capacity, vec, fill, hints));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -450,12 +452,18 @@ extern "C" int bevpool_fused_forward_runs(const void *plan, const void *depth, c
     const int slices = (int)(period_b ? ctas_b - ctas_b / period_b : ctas_b) * kFwWarpsPerCta * 4;
     float *ws_head = static_cast<float *>(workspace);
     float *ws_tail = ws_head + (size_t)slices * channels;
-    BEVPOOL_G8_DISPATCH(channels, (pool_forward_share_kernel<NV2, false, 4, true><<<ctas_b, kFwWarpsPerCta * 32, 0, s>>>(
-                                      pv.cell_start, nullptr, pv.sorted_cells, rr, nullptr, out, ws_head, ws_tail, cell_base,
-                                      ncells, one, one, period_b, -1, 0)));
+    cudaError_t le = cudaSuccess;
+    BEVPOOL_G8_DISPATCH(channels, (le = launch_pdl_if(pdl_forward_enabled(), pool_forward_share_kernel<NV2, false, 4, true>, dim3(ctas_b),
+                                                   dim3(kFwWarpsPerCta * 32), 0, s, pv.cell_start, (const int32_t *)nullptr,
+                                                   pv.sorted_cells, (const float *)rr, (const float *)nullptr, out, ws_head,
+                                                   ws_tail, cell_base, ncells, one, one, period_b, -1, 0)));
+    BEVPOOL_RETURN_IF_CUDA(le);
     BEVPOOL_LAUNCH_CHECK();
-    BEVPOOL_G8_DISPATCH(channels, (pool_forward_fixup_kernel<NV2><<<(unsigned)ceil_div64((int64_t)slices * 8, 128), 128, 0, s>>>(
-                                      pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, cell_base, ncells, slices)));
+    BEVPOOL_G8_DISPATCH(channels, (le = launch_pdl_if(pdl_forward_enabled(), pool_forward_fixup_kernel<NV2>,
+                                                   dim3((unsigned)ceil_div64((int64_t)slices * 8, 128)), dim3(128), 0, s,
+                                                   pv.cell_start, pv.sorted_cells, (const float *)ws_head,
+                                                   (const float *)ws_tail, out, cell_base, ncells, slices)));
+    BEVPOOL_RETURN_IF_CUDA(le);
     BEVPOOL_LAUNCH_CHECK();
   }
   return BEVPOOL_OK;
