@@ -54,15 +54,43 @@ def algorithmic_bytes(cfg, kept_per_frame: float, s: int = 4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The timed region
+    of this bench is tens of milliseconds, shorter than one `nvidia-smi -lms` period, so the sampler polls
+    NVML directly from a thread (a few hundred microseconds per sample); nvidia-smi is the fallback."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    NVML_REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.stop, self.thread, self.nvml, self.max_mhz = [], False, None, None, None
+
+    def _poll(self, handle):
+        import pynvml
+        while not self.stop:
+            try:
+                mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+                reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((mhz, reasons))
+            except Exception:                                   # pragma: no cover
+                break
+            time.sleep(0.0005)
 
     def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, args=(handle,), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -73,12 +101,23 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=2)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
+        if self.nvml is not None and self.samples:
+            sm = [s[0] for s in self.samples]
+            bits = 0
+            for s in self.samples:
+                bits |= s[1]
+            reasons = sorted(n for b, n in self.NVML_REASONS.items() if bits & b)
+            return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                    'samples': len(sm), 'source': 'nvml, polled during the timed region'}
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for ln in self.lines:
@@ -96,7 +135,7 @@ class ClockSampler:
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'source': 'nvidia-smi -lms 100'}
 
 
 def time_cuda(fn, iters, warmup):
