@@ -326,8 +326,12 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner with printf) get
+    # stderr as their stdout; the result line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')     # stdout carries exactly one JSON line
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()
 
@@ -544,7 +548,8 @@ def main():
         except Exception as e:                                  # pragma: no cover
             line['lidar'] = {'error': repr(e)}
 
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
