@@ -55,3 +55,16 @@ def test_python_ops_refuse_cpu_tensors():
     from mm_training_b200.ops.voxel_pooling import voxel_pooling
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         voxel_pooling(torch.zeros(1, 4, 3, dtype=torch.int32), torch.zeros(1, 4, 8), [2, 2, 1])
+
+
+def test_bench_byte_model_matches_the_survey():
+    """bench.py's roofline numerator is SURVEY.md section 8(d), row (B): 32.5 MB per CFG-2 frame."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from mm_training_b200.configs import CFG_2, CFG_AIM
+    b = bench.algorithmic_bytes(CFG_2, 150442)
+    assert abs(b['step'] - 32.5e6) < 0.1e6
+    assert b['fused_forward'] + b['fused_backward'] < b['step'] * 1.05
+    assert abs(bench.algorithmic_bytes(CFG_AIM, 738884)['step'] - 108e6) < 1.5e6
