@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BEVPOOL_ABI_VERSION 1
+#define BEVPOOL_ABI_VERSION 2
 
 #define BEVPOOL_OK            0
 #define BEVPOOL_E_ARG        -1   /* null pointer / non-positive size            */
@@ -36,6 +36,10 @@ extern "C" {
 #define BEVPOOL_E_CHANNELS   -3   /* channel count unsupported by this build     */
 #define BEVPOOL_E_ALIGN      -4   /* pointer not 16-byte aligned                 */
 #define BEVPOOL_E_DTYPE      -5   /* unknown dtype code                          */
+
+/* plan status word (bevpool_plan_status) */
+#define BEVPOOL_PLAN_OK            0
+#define BEVPOOL_PLAN_ROW_OVERFLOW  1   /* run_rows scratch smaller than the plan's run count: results invalid */
 
 /* element types of feature tensors (accumulation is always fp32) */
 #define BEVPOOL_F32  0
@@ -60,6 +64,9 @@ int bevpool_plan_build(const int32_t *geom_xyz, int batch, int64_t num_points,
 /* the reference's pos_memo (voxel_pooling.py:40, .cu:27-29): int32 (B, Np, 3) = (b, y, x) or -1 */
 int bevpool_plan_pos_memo(const void *plan, int batch, int64_t num_points, int num_voxel_x,
                           int num_voxel_y, int32_t *pos_memo, void *stream);
+/* status word of a plan (point or run plan): 0, or BEVPOOL_PLAN_* raised on the device by a consumer kernel.
+ * Synchronises `stream`. */
+int bevpool_plan_status(const void *plan, int *status_host, void *stream);
 /* device pointers into a built plan (for tests / diagnostics) */
 int bevpool_plan_views(const void *plan, int batch, int64_t num_points, int num_voxel_x,
                        int num_voxel_y, const int32_t **cell_of_point,
@@ -127,6 +134,45 @@ int bevpool_fused_forward_runs(const void *plan, const void *depth, const void *
                                void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
                                int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
                                void *run_rows, int64_t run_rows_capacity, void *workspace, void *stream);
+
+/* The same two operators on the reference's own tensor layout: context and its gradient as (B*N, C, H, W)
+ * (what DepthNet produces, layers/backbones/lss_fpn.py:441-443).  The kernels read / write the NCHW tensors
+ * through TMA tensor maps (boxes of 4 columns x 16 rows x C channels), so no layout pass is needed.
+ * fp32, channels in {32, 64, 80, 96, 128}, feat_w % 4 == 0 (else BEVPOOL_E_ALIGN: use the pixel-row entry points).
+ * run_rows_capacity may be smaller than the run count only by mistake: the kernels then never touch memory
+ * beyond the scratch, the output is invalid and the plan's status word is raised.                          */
+int bevpool_fused_forward_runs_nchw(const void *plan, const void *depth, const void *context_nchw,
+                                    void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
+                                    int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
+                                    void *run_rows, int64_t run_rows_capacity, void *workspace, void *stream);
+int bevpool_fused_backward_nchw(const void *plan, const void *grad_out_nhwc, const void *depth,
+                                const void *context_nchw, void *grad_depth, void *grad_context_nchw,
+                                int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                                int channels, int num_voxel_x, int num_voxel_y, void *stream);
+
+/* ---- run plan straight from the camera rig: no geom_xyz tensor -------------------------------------
+ * Replaces layers/backbones/lss_fpn.py:328-361 (get_geometry) + :461-462 (index quantisation) as the
+ * producer of the cell indices.  Inputs (all device pointers unless *_host):
+ *   combine      float32 (B*N, 4, 4) row-major = sensor2ego @ inverse(intrin)  (lss_fpn.py:354, left in torch)
+ *   frustum_x/y/d  the frustum axes of lss_fpn.py:308-326: x[W], y[H], d[D]
+ *   lower_host[3]  = voxel_coord - voxel_size / 2 ; voxel_size_host[3]          (lss_fpn.py:461-462)
+ *   variant      accumulation order of the 4-term dot products of `combine @ point`
+ *                (0 .. bevpool_rig_num_variants()-1); the host picks the one that reproduces torch's batched
+ *                matmul bit for bit on the device in use (mm_training_b200/ops/voxel_pooling/rig.py)
+ * The plan has exactly the layout bevpool_runplan_build produces.  bevpool_rig_geom writes the int32
+ * (B, N, D, H, W, 3) tensor the reference would have made (diagnostics and the variant self-test).       */
+int bevpool_rig_num_variants(void);
+int bevpool_runplan_rig_sizes(int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                              int num_voxel_x, int num_voxel_y, size_t *plan_bytes, size_t *temp_bytes);
+int bevpool_runplan_build_rig(const float *combine, const float *frustum_x, const float *frustum_y,
+                              const float *frustum_d, const float *lower_host, const float *voxel_size_host,
+                              int variant, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                              int num_voxel_x, int num_voxel_y, int num_voxel_z, void *plan, void *temp,
+                              void *stream);
+int bevpool_rig_geom(const float *combine, const float *frustum_x, const float *frustum_y,
+                     const float *frustum_d, const float *lower_host, const float *voxel_size_host, int variant,
+                     int batch, int num_cams, int depth_bins, int feat_h, int feat_w, int32_t *geom_xyz,
+                     void *stream);
 
 /* ---- gradient layout: grad_out (B, C, Y, X) contiguous -> rows (B, Y, X, C) --------------
  * Only rows of cells that received a point are written (the backward kernels read no

@@ -42,6 +42,12 @@ _SIGNATURES = {
     'bevpool_runplan_build': [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     'bevpool_runplan_views': [_vp, _i, _i64, _i, _i] + [ctypes.POINTER(_vp)] * 5,
     'bevpool_fused_forward_runs': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp],
+    'bevpool_fused_forward_runs_nchw': [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64, _vp, _vp],
+    'bevpool_fused_backward_nchw': [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    'bevpool_plan_status': [_vp, _ip, _vp],
+    'bevpool_runplan_rig_sizes': [_i, _i, _i, _i, _i, _i, _i, _szp, _szp],
+    'bevpool_runplan_build_rig': [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    'bevpool_rig_geom': [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _vp, _vp],
     'bevpool_grad_rows': [_vp, _vp, _vp, _i, _i, _i64, _i, _i, _i, _vp],
     'bevpool_transpose': [_vp, _vp, _i, _i, _i64, _i64, _vp],
     'bevvox_temp_bytes': [_i, _i64, _i, _i, _szp],
@@ -50,7 +56,8 @@ _SIGNATURES = {
     'pillar_scatter_forward': [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     'pillar_scatter_backward': [_vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp],
 }
-EXPORTED_SYMBOLS = ['bevpool_abi_version', 'bevpool_error_string', 'bevpool_launch_count', *_SIGNATURES]
+EXPORTED_SYMBOLS = ['bevpool_abi_version', 'bevpool_error_string', 'bevpool_launch_count', 'bevpool_rig_num_variants',
+                    *_SIGNATURES]
 
 
 class BevPoolError(RuntimeError):
@@ -74,6 +81,8 @@ def lib() -> ctypes.CDLL:
                 l.bevpool_error_string.argtypes = [_i]
                 l.bevpool_launch_count.restype = _i64
                 l.bevpool_launch_count.argtypes = []
+                l.bevpool_rig_num_variants.restype = _i
+                l.bevpool_rig_num_variants.argtypes = []
                 for name, argtypes in _SIGNATURES.items():
                     fn = getattr(l, name)
                     fn.restype = _i

@@ -137,7 +137,7 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
 
 // ---- plan layout -------------------------------------------------------------------
 // A plan is one caller-owned buffer:
-//   header (256 B, reserved: neither written nor read) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
+//   header (256 B: PlanHeader) | cell_of_point int32[B*Np] | cell_start int32[B*G+1] | sorted_ids int32[B*Np]
 //   | sorted_cells int32[B*Np]
 // sorted_ids[k] is the global point id of the k-th kept point in (cell, point id) order and
 // sorted_cells[k] its global output row b*G + cell; only the first K = cell_start[B*G] entries
@@ -145,11 +145,14 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
 struct PlanLayout {
   size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, off_run_code, bytes;
 };
-struct PlanHeader {       // reserved layout of the first 256 bytes (not written by this version)
-  int32_t magic, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
+struct PlanHeader {       // first 256 bytes of a plan buffer, written by the builders (one thread of the key kernel)
+  int32_t magic, kind, status, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
   int64_t num_points;
-  int32_t num_kept_total;  // K = cell_start[B*G]
 };
+constexpr int32_t kPlanKindPoints = 1, kPlanKindRuns = 2;
+// status word: 0 = ok.  Raised on the device by a consumer kernel, read back by bevpool_plan_status().
+constexpr int32_t kPlanStatusRowOverflow = 1;   // run_rows scratch smaller than the plan's run count
+inline int32_t *plan_status(void *plan) { return &static_cast<PlanHeader *>(plan)->status; }
 constexpr int32_t kPlanMagic = 0x42455631;  // "BEV1"
 
 // Run plan (fused op only): the sorted entries are RUNS, not points.  A run is a maximal set of
@@ -188,7 +191,14 @@ inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X
                   reinterpret_cast<const int32_t *>(b + L.off_run_code)};
 }
 
-// pool_bwd.cu: tile kernel of the fused backward (fp32, g8 channel counts)
+// pool_bwd2.cu: column kernel of the fused backward (fp32, g8 channel counts, W % 4 == 0); reads context and writes
+// the context gradient either as pixel rows (B*N, H, W, C) or, through TMA tensor maps, as NCHW (B*N, C, H, W)
+int launch_fused_backward_col(const int32_t *cell_of_point, const float *grad_rows, const float *depth,
+                              const float *ctx, float *grad_depth, float *grad_ctx, bool nchw, int batch, int num_cams,
+                              int D, int H, int W, int C, int64_t cells_per_sample, cudaStream_t s);
+bool fused_backward_col_supported(int C, int W, const void *depth, const void *grad_depth, const void *cell_of_point);
+
+// pool_bwd.cu: tile kernel of the fused backward (fp32, g8 channel counts; any W)
 int launch_fused_backward_tile(const int32_t *cell_of_point, const float *grad_rows, const float *depth,
                                const float *ctx_nhwc, float *grad_depth, float *grad_ctx_nhwc, int batch,
                                int num_cams, int D, int H, int W, int C, int64_t cells_per_sample,

@@ -29,6 +29,13 @@ bool pdl_enabled() {
   return on;
 }
 
+static PlanHeader make_plan_header(int32_t kind, int batch, int64_t num_points, int X, int Y, int Z) {
+  PlanHeader h{};
+  h.magic = kPlanMagic; h.kind = kind; h.status = 0; h.batch = batch;
+  h.num_voxel_x = X; h.num_voxel_y = Y; h.num_voxel_z = Z; h.num_points = num_points;
+  return h;
+}
+
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortItems = 8;
@@ -116,9 +123,10 @@ static TempLayout temp_layout(int batch, int64_t num_points, int X, int Y) {
 __global__ void __launch_bounds__(kSortThreads)
 plan_key_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
                 int32_t *__restrict__ cell_of_point, uint32_t *__restrict__ cell_count,
-                uint32_t *__restrict__ hist, int bins, int tiles_per_sample) {
+                uint32_t *__restrict__ hist, int bins, int tiles_per_sample, PlanHeader *hdr, PlanHeader hv) {
   extern __shared__ uint32_t s_hist[];
   const int b = blockIdx.y, tile = blockIdx.x;
+  if (b == 0 && tile == 0 && threadIdx.x == 0) *hdr = hv;
   for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
   __syncthreads();
   const int64_t sample_base = (int64_t)b * num_points;
@@ -257,9 +265,10 @@ sort_scatter_kernel(const int32_t *__restrict__ in_keys, const int32_t *__restri
 __global__ void __launch_bounds__(kSortThreads)
 plan_key_msd_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
                     int32_t *__restrict__ cell_of_point, uint32_t *__restrict__ hist, int low_bits,
-                    int bins, int tiles_per_sample) {
+                    int bins, int tiles_per_sample, PlanHeader *hdr, PlanHeader hv) {
   extern __shared__ uint32_t s_hist[];
   const int b = blockIdx.y, tile = blockIdx.x;
+  if (b == 0 && tile == 0 && threadIdx.x == 0) *hdr = hv;
   for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0u;
   __syncthreads();
   const int64_t sample_base = (int64_t)b * num_points;
@@ -326,10 +335,12 @@ plan_key_runs_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X
                      int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code,
                      uint32_t *__restrict__ counts, int32_t *__restrict__ head_cells,
                      int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
-                     uint32_t *__restrict__ sample_total, int tiles_per_sample, FastDiv div_w, FastDiv div_h) {
+                     uint32_t *__restrict__ sample_total, int tiles_per_sample, FastDiv div_w, FastDiv div_h,
+                     PlanHeader *hdr, PlanHeader hv) {
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.y, tile = blockIdx.x;
+  if (b == 0 && tile == 0 && threadIdx.x == 0) *hdr = hv;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t sample_base = (int64_t)b * num_points;
   const int64_t tile_base = (int64_t)tile * kSortTile;
@@ -419,6 +430,166 @@ plan_key_runs_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_cta_total) atomicAdd(sample_total + b, s_cta_total);   // one global atomic per CTA
+}
+
+// ==== run plan straight from the camera rig (no geom_xyz tensor) ===================================
+// Replaces layers/backbones/lss_fpn.py:328-361 (get_geometry) + :461-462 (quantisation) of the reference as
+// the producer of the cell indices: the (B, N, D, H, W, 3) float and int32 tensors are never written or read.
+// What stays in torch is what is tiny: combine = sensor2ego @ inverse(intrin) (B*N matrices), the frustum
+// axes and the two 3-vectors of the quantisation.  Per point, op for op what the reference's ATen ops do:
+//   p = (x*d, y*d, d, 1)                                   (:351-353, float32 multiply)
+//   e = combine @ p                                        (:355, rows 0..2; the 4-term dot product in the
+//                                                           accumulation order selected by kVariant)
+//   q = ((e - (voxel_coord - voxel_size/2)) / voxel_size).int()   (:461-462: IEEE subtract, TRUE division,
+//                                                           truncation toward zero)
+// Which accumulation order reproduces the reference's batched matmul bit for bit depends on the BLAS kernel
+// behind it; the host picks the variant by comparing against torch on the device in use (and falls back to
+// the geom_xyz path if none matches): mm_training_b200/ops/voxel_pooling/rig.py.
+// Thread = one (image, depth bin, 16-row block, column) pair, walking its rows top to bottom, so run heads
+// are found without re-deriving the row above; lanes = consecutive columns (coalesced 4-byte stores).
+struct RigParams {
+  const float *combine;          // (B*N, 4, 4) row-major
+  const float *fx, *fy, *fd;     // frustum axes: x[W], y[H], d[D]  (lss_fpn.py:308-326)
+  float lo[3], vs[3], inv_vs[3]; // voxel_coord - voxel_size/2, voxel_size, 1/voxel_size (fast path only)
+};
+
+template <int kVariant>
+__device__ __forceinline__ float rig_dot4(const float (&m)[4], float px, float py, float pz) {
+  // the homogeneous coordinate is exactly 1.0f, so m[3] * 1 == m[3]
+  if (kVariant == 0) {          // ascending k, fused multiply-add
+    float a = __fmul_rn(m[0], px);
+    a = __fmaf_rn(m[1], py, a);
+    a = __fmaf_rn(m[2], pz, a);
+    return __fadd_rn(a, m[3]);
+  } else if (kVariant == 1) {   // descending k, fused multiply-add
+    float a = __fmaf_rn(m[2], pz, m[3]);
+    a = __fmaf_rn(m[1], py, a);
+    return __fmaf_rn(m[0], px, a);
+  } else if (kVariant == 2) {   // two k-slices (0,1) + (2,3), each an ascending fused chain that starts from a rounded product
+    const float a = __fmaf_rn(m[1], py, __fmul_rn(m[0], px));
+    const float b = __fadd_rn(__fmul_rn(m[2], pz), m[3]);
+    return __fadd_rn(a, b);
+  } else if (kVariant == 3) {   // ascending k, separate multiply and add
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], px), __fmul_rn(m[1], py)), __fmul_rn(m[2], pz)), m[3]);
+  } else if (kVariant == 4) {   // even / odd k-slices (0,2) + (1,3)
+    const float a = __fmaf_rn(m[2], pz, __fmul_rn(m[0], px));
+    const float b = __fadd_rn(__fmul_rn(m[1], py), m[3]);
+    return __fadd_rn(a, b);
+  } else {                      // pairwise with the translation fused into the second product
+    const float a = __fmaf_rn(m[1], py, __fmul_rn(m[0], px));
+    const float b = __fmaf_rn(m[2], pz, m[3]);
+    return __fadd_rn(a, b);
+  }
+}
+
+// trunc((e - lo) / vs) with IEEE semantics.  The quotient by reciprocal is within 2 ulp of the true quotient:
+// when it is farther than that from every integer it truncates to the same value, otherwise (a fraction of a
+// percent of the points) the exact division decides.
+__device__ __forceinline__ int rig_quantise(float e, float lo, float vs, float inv_vs) {
+  const float t = __fsub_rn(e, lo);
+  const float qf = __fmul_rn(t, inv_vs);
+  const float fr = fabsf(qf - rintf(qf));
+  if (fr > 1e-3f && fabsf(qf) < 4194304.f) return __float2int_rz(qf);
+  return __float2int_rz(__fdiv_rn(t, vs));
+}
+
+constexpr int kRigThreads = 256;
+
+template <int kVariant>
+__global__ void __launch_bounds__(kRigThreads)
+plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int X, int Y, int Z, int64_t num_points,
+                    int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code, uint32_t *__restrict__ counts,
+                    int32_t *__restrict__ head_cells, int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
+                    uint32_t *__restrict__ sample_total, int warps_per_sample, int slot_cap, PlanHeader *hdr, PlanHeader hv) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) *hdr = hv;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t pairs = (int64_t)num_cams * D * HB * W;
+  const int64_t q = (int64_t)blockIdx.x * kRigThreads + threadIdx.x;
+  const bool valid = q < pairs;
+  int w = 0, hb = 0, d = 0, n = 0;
+  if (valid) {
+    int64_t t = q;
+    w = (int)(t % W); t /= W;
+    hb = (int)(t % HB); t /= HB;
+    d = (int)(t % D);
+    n = (int)(t / D);
+  }
+  float m0[4], m1[4], m2[4];
+  {
+    const float4 *mp = reinterpret_cast<const float4 *>(rp.combine + ((int64_t)b * num_cams + n) * 16);
+    const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
+    m0[0] = r0.x; m0[1] = r0.y; m0[2] = r0.z; m0[3] = r0.w;
+    m1[0] = r1.x; m1[1] = r1.y; m1[2] = r1.z; m1[3] = r1.w;
+    m2[0] = r2.x; m2[1] = r2.y; m2[2] = r2.z; m2[3] = r2.w;
+  }
+  const float dd = __ldg(rp.fd + d);
+  const float px = __fmul_rn(__ldg(rp.fx + w), dd);
+  const int64_t cells = (int64_t)X * Y;
+  const int64_t region = ((int64_t)b * warps_per_sample + (int64_t)blockIdx.x * (kRigThreads / 32) + warp) * slot_cap;
+  const int64_t col_base = (int64_t)b * num_points + ((int64_t)n * D + d) * H * W + w;
+  const unsigned lt = (1u << lane) - 1u;
+  uint32_t filled = 0;                 // heads this warp has written so far (warp-uniform)
+  int prev = -2;
+#pragma unroll 4
+  for (int r = 0; r < kRunHB; ++r) {
+    const int h = hb * kRunHB + r;
+    const bool act = valid && h < H;
+    int cell = -1, code = kRunDropped;
+    if (act) {
+      const float py = __fmul_rn(__ldg(rp.fy + h), dd);
+      const int ix = rig_quantise(rig_dot4<kVariant>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
+      const int iy = rig_quantise(rig_dot4<kVariant>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
+      const int iz = rig_quantise(rig_dot4<kVariant>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
+      cell = cell_of_xyz(ix, iy, iz, X, Y, Z);
+      code = cell < 0 ? kRunDropped : (cell != prev ? cell : kRunCont);
+      prev = cell;
+      const int64_t gp = col_base + (int64_t)h * W;
+      cell_of_point[gp] = cell;
+      run_code[gp] = code;          // heads: overwritten with their slot by K4
+    }
+    const bool head = code >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int64_t pos = region + filled + __popc(bal & lt);
+      head_cells[pos] = code;
+      head_ids[pos] = (int32_t)(col_base + (int64_t)h * W);
+      atomicAdd(counts + (int64_t)b * cells + code, 1u);
+    }
+    filled += __popc(bal);
+  }
+  __shared__ uint32_t s_cta_total;
+  if (threadIdx.x == 0) s_cta_total = 0u;
+  __syncthreads();
+  if (lane == 0) {
+    warp_count[(int64_t)b * warps_per_sample + (int64_t)blockIdx.x * (kRigThreads / 32) + warp] = (int32_t)filled;
+    if (filled) atomicAdd(&s_cta_total, filled);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_cta_total) atomicAdd(sample_total + b, s_cta_total);   // one global atomic per CTA
+}
+
+// the cell index alone (diagnostics / the variant self-test): geom_xyz int32 (B, N, D, H, W, 3) as the reference makes it
+template <int kVariant>
+__global__ void __launch_bounds__(256)
+rig_geom_kernel(RigParams rp, int num_cams, int D, int H, int W, int64_t total, int32_t *__restrict__ geom) {
+  const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= total) return;
+  int64_t t = gp;
+  const int w = (int)(t % W); t /= W;
+  const int h = (int)(t % H); t /= H;
+  const int d = (int)(t % D); t /= D;            // t = b * num_cams + n
+  const float *mp = rp.combine + t * 16;
+  float m0[4], m1[4], m2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { m0[k] = __ldg(mp + k); m1[k] = __ldg(mp + 4 + k); m2[k] = __ldg(mp + 8 + k); }
+  const float dd = __ldg(rp.fd + d);
+  const float px = __fmul_rn(__ldg(rp.fx + w), dd), py = __fmul_rn(__ldg(rp.fy + h), dd);
+  geom[gp * 3 + 0] = rig_quantise(rig_dot4<kVariant>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
+  geom[gp * 3 + 1] = rig_quantise(rig_dot4<kVariant>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
+  geom[gp * 3 + 2] = rig_quantise(rig_dot4<kVariant>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
 }
 
 // K2: exclusive scan of the per-cell run counts, one independent look-back chain per SAMPLE (a single
@@ -538,7 +709,7 @@ run_place_kernel(const int32_t *__restrict__ head_cells, const int32_t *__restri
                  const int32_t *__restrict__ warp_count, const uint32_t *__restrict__ cell_start,
                  uint32_t *__restrict__ counts, int32_t *__restrict__ placed_ids,
                  int32_t *__restrict__ placed_cells, int64_t num_slices, int slices_per_sample,
-                 int64_t cells_per_sample) {
+                 int64_t cells_per_sample, int slot_cap) {
   pdl_wait();
   pdl_trigger();
   const int64_t slice = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
@@ -547,10 +718,10 @@ run_place_kernel(const int32_t *__restrict__ head_cells, const int32_t *__restri
   const int n = warp_count[slice];
   const int64_t cell_base = (slice / slices_per_sample) * cells_per_sample;
   for (int i = l8; i < n; i += 8) {
-    const int64_t gc = cell_base + head_cells[slice * kRunWarpSlots + i];
+    const int64_t gc = cell_base + head_cells[slice * slot_cap + i];
     const uint32_t left = atomicSub(counts + gc, 1u);          // the per-cell count doubles as the cursor
     const uint32_t pos = cell_start[gc] + left - 1u;
-    placed_ids[pos] = head_ids[slice * kRunWarpSlots + i];
+    placed_ids[pos] = head_ids[slice * slot_cap + i];
     placed_cells[pos] = (int32_t)gc;
   }
 }
@@ -772,11 +943,12 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
   const dim3 grid(T, batch);
 
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
+  const PlanHeader hv = make_plan_header(kPlanKindPoints, batch, num_points, X, Y, Z);
 
   if (sc.msd) {
     const int low = sc.bits[0], bins_hi = 1 << sc.bits[1];
     plan_key_msd_kernel<<<grid, kSortThreads, bins_hi * 4, stream>>>(geom, num_points, X, Y, Z, cell_of_point,
-                                                                    hist[0], low, bins_hi, T);
+                                                                    hist[0], low, bins_hi, T, static_cast<PlanHeader *>(plan), hv);
     BEVPOOL_LAUNCH_CHECK();
     rc = launch_scan_exclusive(hist[0], hist[0], TL.hist_n[0], tb + TL.off_scan[0], stream);
     if (rc) return rc;
@@ -794,7 +966,7 @@ extern "C" int bevpool_plan_build(const int32_t *geom, int batch, int64_t num_po
 
   const int bins0 = 1 << sc.bits[0];
   plan_key_kernel<<<grid, kSortThreads, bins0 * 4, stream>>>(
-      geom, num_points, X, Y, Z, cell_of_point, cell_start, hist[0], bins0, T);
+      geom, num_points, X, Y, Z, cell_of_point, cell_start, hist[0], bins0, T, static_cast<PlanHeader *>(plan), hv);
   BEVPOOL_LAUNCH_CHECK();
   rc = launch_scan_exclusive(hist[0], hist[0], TL.hist_n[0], tb + TL.off_scan[0], stream);
   if (rc) return rc;
@@ -855,13 +1027,14 @@ struct RunTempLayout {
   size_t off_scan, off_counts, zero_bytes;     // [0, zero_bytes) is memset to 0 per build
   size_t off_big_count, off_sample_total, off_tickets, off_status;   // (inside the zeroed part)
   size_t off_head_cells, off_head_ids, off_warp_count, off_placed, off_placed_cells, off_big_list, bytes;
-  int tiles_per_sample;
+  int slices_per_sample, slot_cap;             // K1 warp slices of the head lists and their capacity
 };
-static RunTempLayout run_temp_layout(int batch, int64_t num_points, int X, int Y) {
+static RunTempLayout run_temp_layout(int batch, int64_t num_points, int X, int Y, int slices_per_sample, int slot_cap) {
   RunTempLayout L{};
-  L.tiles_per_sample = (int)ceil_div64(num_points, kSortTile);
+  L.slices_per_sample = slices_per_sample;
+  L.slot_cap = slot_cap;
   const size_t G1 = (size_t)batch * X * Y + 1;
-  const size_t slices = (size_t)batch * L.tiles_per_sample * kSortWarps;
+  const size_t slices = (size_t)batch * slices_per_sample;
   size_t o = 0;
   L.off_scan = o;        o += scan_workspace_bytes((int64_t)G1);
   L.off_counts = o;      o = align_up(o + G1 * 4, 256);
@@ -870,14 +1043,23 @@ static RunTempLayout run_temp_layout(int batch, int64_t num_points, int X, int Y
   L.off_tickets = o;     o = align_up(o + (size_t)batch * 4, 256);
   L.off_status = o;      o = align_up(o + (size_t)batch * scan_num_tiles((int64_t)X * Y) * 8, 256);
   L.zero_bytes = o;
-  L.off_head_cells = o;  o = align_up(o + slices * kRunWarpSlots * 4, 256);
-  L.off_head_ids = o;    o = align_up(o + slices * kRunWarpSlots * 4, 256);
+  L.off_head_cells = o;  o = align_up(o + slices * slot_cap * 4, 256);
+  L.off_head_ids = o;    o = align_up(o + slices * slot_cap * 4, 256);
   L.off_warp_count = o;  o = align_up(o + slices * 4, 256);
   L.off_placed = o;      o = align_up(o + (size_t)batch * num_points * 4, 256);
   L.off_placed_cells = o; o = align_up(o + (size_t)batch * num_points * 4, 256);
   L.off_big_list = o;    o = align_up(o + ((size_t)batch * num_points / 16 + 1) * 4, 256);
   L.bytes = o;
   return L;
+}
+static RunTempLayout run_temp_layout_geom(int batch, int64_t num_points, int X, int Y) {
+  return run_temp_layout(batch, num_points, X, Y, (int)ceil_div64(num_points, kSortTile) * kSortWarps, kRunWarpSlots);
+}
+static RunTempLayout run_temp_layout_rig(int batch, int N, int D, int H, int W, int X, int Y) {
+  const int HB = (int)ceil_div64(H, kRunHB);
+  const int64_t pairs = (int64_t)N * D * HB * W;
+  return run_temp_layout(batch, (int64_t)N * D * H * W, X, Y, (int)ceil_div64(pairs, kRigThreads) * (kRigThreads / 32),
+                         32 * (H < kRunHB ? H : kRunHB));
 }
 
 extern "C" int bevpool_runplan_sizes(int batch, int64_t num_points, int X, int Y, size_t *plan_bytes,
@@ -886,7 +1068,60 @@ extern "C" int bevpool_runplan_sizes(int batch, int64_t num_points, int X, int Y
   if (rc) return rc;
   if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
   *plan_bytes = plan_layout(batch, num_points, X, Y, true).bytes;
-  *temp_bytes = run_temp_layout(batch, num_points, X, Y).bytes;
+  *temp_bytes = run_temp_layout_geom(batch, num_points, X, Y).bytes;
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_runplan_rig_sizes(int batch, int num_cams, int depth_bins, int feat_h, int feat_w, int X, int Y,
+                                         size_t *plan_bytes, size_t *temp_bytes) {
+  if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  const int64_t num_points = (int64_t)num_cams * depth_bins * feat_h * feat_w;
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
+  *plan_bytes = plan_layout(batch, num_points, X, Y, true).bytes;
+  *temp_bytes = run_temp_layout_rig(batch, num_cams, depth_bins, feat_h, feat_w, X, Y).bytes;
+  return BEVPOOL_OK;
+}
+
+// K2..K5 of a run plan: per-cell run counts + per-warp head lists (K1's output) -> CSR, sorted run list, slots
+static int run_plan_finish(const RunTempLayout &TL, const PlanLayout &PL, int batch, int64_t cells, char *pb, char *tb,
+                           cudaStream_t stream) {
+  const int64_t total_cells = (int64_t)batch * cells;
+  uint32_t *cell_start = reinterpret_cast<uint32_t *>(pb + PL.off_cell_start);
+  int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
+  int32_t *sorted_cells = reinterpret_cast<int32_t *>(pb + PL.off_sorted_cells);
+  int32_t *run_code = reinterpret_cast<int32_t *>(pb + PL.off_run_code);
+  uint32_t *counts = reinterpret_cast<uint32_t *>(tb + TL.off_counts);
+  int32_t *head_cells = reinterpret_cast<int32_t *>(tb + TL.off_head_cells);
+  int32_t *head_ids = reinterpret_cast<int32_t *>(tb + TL.off_head_ids);
+  int32_t *warp_count = reinterpret_cast<int32_t *>(tb + TL.off_warp_count);
+  int32_t *placed = reinterpret_cast<int32_t *>(tb + TL.off_placed);
+  int32_t *placed_cells = reinterpret_cast<int32_t *>(tb + TL.off_placed_cells);
+  uint32_t *sample_total = reinterpret_cast<uint32_t *>(tb + TL.off_sample_total);
+  if ((cells & 3) == 0) {            // per-sample chains (16-byte aligned sample segments)
+    const int tps = (int)scan_num_tiles(cells);
+    BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_csr_scan_kernel, dim3(tps, batch), dim3(kScanThreads), 0, stream,
+        counts, cell_start, cells, sample_total, batch, reinterpret_cast<unsigned long long *>(tb + TL.off_status),
+        reinterpret_cast<unsigned int *>(tb + TL.off_tickets), tps));
+    BEVPOOL_LAUNCH_CHECK();
+  } else {
+    int rc = launch_scan_exclusive(counts, cell_start, total_cells + 1, tb + TL.off_scan, stream);
+    if (rc) return rc;
+  }
+  const int64_t slices = (int64_t)batch * TL.slices_per_sample;
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_place_kernel, dim3((unsigned)ceil_div64(slices * 8, 256)), dim3(256), 0, stream,
+      head_cells, head_ids, warp_count, cell_start, counts, placed, placed_cells, slices, TL.slices_per_sample, cells,
+      TL.slot_cap));
+  BEVPOOL_LAUNCH_CHECK();
+  int32_t *big_list = reinterpret_cast<int32_t *>(tb + TL.off_big_list);
+  uint32_t *big_count = reinterpret_cast<uint32_t *>(tb + TL.off_big_count);
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_kernel, dim3(kSMs * 8), dim3(256), 0, stream,
+      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count));
+  BEVPOOL_LAUNCH_CHECK();
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_big_kernel, dim3(kSMs * 2), dim3(256), 0, stream,
+                                    cell_start, placed, big_list, big_count, sorted_ids, sorted_cells, run_code));
+  BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
 
@@ -900,50 +1135,112 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
   if (!aligned16(plan) || !aligned16(temp) || !aligned16(geom)) return BEVPOOL_E_ALIGN;
   if (batch > 65535) return BEVPOOL_E_RANGE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int64_t cells = (int64_t)X * Y, total_cells = (int64_t)batch * cells;
+  const int64_t cells = (int64_t)X * Y;
   const PlanLayout PL = plan_layout(batch, num_points, X, Y, true);
-  const RunTempLayout TL = run_temp_layout(batch, num_points, X, Y);
+  const RunTempLayout TL = run_temp_layout_geom(batch, num_points, X, Y);
   char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
-  int32_t *cell_of_point = reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point);
-  uint32_t *cell_start = reinterpret_cast<uint32_t *>(pb + PL.off_cell_start);
-  int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
-  int32_t *sorted_cells = reinterpret_cast<int32_t *>(pb + PL.off_sorted_cells);
-  int32_t *run_code = reinterpret_cast<int32_t *>(pb + PL.off_run_code);
-  uint32_t *counts = reinterpret_cast<uint32_t *>(tb + TL.off_counts);
-  int32_t *head_cells = reinterpret_cast<int32_t *>(tb + TL.off_head_cells);
-  int32_t *head_ids = reinterpret_cast<int32_t *>(tb + TL.off_head_ids);
-  int32_t *warp_count = reinterpret_cast<int32_t *>(tb + TL.off_warp_count);
-  int32_t *placed = reinterpret_cast<int32_t *>(tb + TL.off_placed);
-  int32_t *placed_cells = reinterpret_cast<int32_t *>(tb + TL.off_placed_cells);
-  uint32_t *sample_total = reinterpret_cast<uint32_t *>(tb + TL.off_sample_total);
-  const int T = TL.tiles_per_sample;
+  const int T = (int)ceil_div64(num_points, kSortTile);
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
   BEVPOOL_RETURN_IF_CUDA(launch_pdl(plan_key_runs_kernel, dim3(T, batch), dim3(kSortThreads), 0, stream,
-      geom, num_points, X, Y, Z, cell_of_point, run_code, counts, head_cells, head_ids, warp_count, sample_total, T,
-      make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h)));
+      geom, num_points, X, Y, Z, reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
+      reinterpret_cast<int32_t *>(pb + PL.off_run_code), reinterpret_cast<uint32_t *>(tb + TL.off_counts),
+      reinterpret_cast<int32_t *>(tb + TL.off_head_cells), reinterpret_cast<int32_t *>(tb + TL.off_head_ids),
+      reinterpret_cast<int32_t *>(tb + TL.off_warp_count), reinterpret_cast<uint32_t *>(tb + TL.off_sample_total), T,
+      make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h), static_cast<PlanHeader *>(plan),
+      make_plan_header(kPlanKindRuns, batch, num_points, X, Y, Z)));
   BEVPOOL_LAUNCH_CHECK();
-  if ((cells & 3) == 0) {            // per-sample chains (16-byte aligned sample segments)
-    const int tps = (int)scan_num_tiles(cells);
-    BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_csr_scan_kernel, dim3(tps, batch), dim3(kScanThreads), 0, stream,
-        counts, cell_start, cells, sample_total, batch, reinterpret_cast<unsigned long long *>(tb + TL.off_status),
-        reinterpret_cast<unsigned int *>(tb + TL.off_tickets), tps));
-    BEVPOOL_LAUNCH_CHECK();
-  } else {
-    rc = launch_scan_exclusive(counts, cell_start, total_cells + 1, tb + TL.off_scan, stream);
-    if (rc) return rc;
+  return run_plan_finish(TL, PL, batch, cells, pb, tb, stream);
+}
+
+constexpr int kRigVariants = 6;
+extern "C" int bevpool_rig_num_variants(void) { return kRigVariants; }
+
+static int make_rig_params(RigParams *rp, const float *combine, const float *fx, const float *fy, const float *fd,
+                           const float *lower_host, const float *voxel_size_host) {
+  if (!combine || !fx || !fy || !fd || !lower_host || !voxel_size_host) return BEVPOOL_E_ARG;
+  if (!aligned16(combine)) return BEVPOOL_E_ALIGN;
+  rp->combine = combine; rp->fx = fx; rp->fy = fy; rp->fd = fd;
+  for (int i = 0; i < 3; ++i) {
+    if (!(voxel_size_host[i] != 0.f)) return BEVPOOL_E_ARG;
+    rp->lo[i] = lower_host[i];
+    rp->vs[i] = voxel_size_host[i];
+    rp->inv_vs[i] = 1.0f / voxel_size_host[i];
   }
-  const int64_t slices = (int64_t)batch * T * kSortWarps;
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_place_kernel, dim3((unsigned)ceil_div64(slices * 8, 256)), dim3(256), 0, stream,
-      head_cells, head_ids, warp_count, cell_start, counts, placed, placed_cells, slices, T * kSortWarps, cells));
+  return BEVPOOL_OK;
+}
+
+#define BEVPOOL_RIG_DISPATCH(variant, CALL)                 \
+  switch (variant) {                                        \
+    case 0: { constexpr int V = 0; CALL; break; }           \
+    case 1: { constexpr int V = 1; CALL; break; }           \
+    case 2: { constexpr int V = 2; CALL; break; }           \
+    case 3: { constexpr int V = 3; CALL; break; }           \
+    case 4: { constexpr int V = 4; CALL; break; }           \
+    case 5: { constexpr int V = 5; CALL; break; }           \
+    default: return BEVPOOL_E_ARG;                          \
+  }
+
+extern "C" int bevpool_runplan_build_rig(const float *combine, const float *frustum_x, const float *frustum_y,
+                                         const float *frustum_d, const float *lower_host, const float *voxel_size_host,
+                                         int variant, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                                         int X, int Y, int Z, void *plan, void *temp, void *stream_) {
+  if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  const int64_t num_points = (int64_t)num_cams * depth_bins * feat_h * feat_w;
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan || !temp || Z <= 0) return BEVPOOL_E_ARG;
+  if (!aligned16(plan) || !aligned16(temp)) return BEVPOOL_E_ALIGN;
+  if (batch > 65535) return BEVPOOL_E_RANGE;
+  RigParams rp;
+  if ((rc = make_rig_params(&rp, combine, frustum_x, frustum_y, frustum_d, lower_host, voxel_size_host))) return rc;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t cells = (int64_t)X * Y;
+  const PlanLayout PL = plan_layout(batch, num_points, X, Y, true);
+  const RunTempLayout TL = run_temp_layout_rig(batch, num_cams, depth_bins, feat_h, feat_w, X, Y);
+  char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
+  const int HB = (int)ceil_div64(feat_h, kRunHB);
+  const int64_t pairs = (int64_t)num_cams * depth_bins * HB * feat_w;
+  const dim3 grid((unsigned)ceil_div64(pairs, kRigThreads), (unsigned)batch);
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
+  cudaError_t le = cudaSuccess;
+  BEVPOOL_RIG_DISPATCH(variant, (le = launch_pdl(plan_key_rig_kernel<V>, grid, dim3(kRigThreads), 0, stream, rp, num_cams,
+      depth_bins, feat_h, feat_w, HB, X, Y, Z, num_points, reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
+      reinterpret_cast<int32_t *>(pb + PL.off_run_code), reinterpret_cast<uint32_t *>(tb + TL.off_counts),
+      reinterpret_cast<int32_t *>(tb + TL.off_head_cells), reinterpret_cast<int32_t *>(tb + TL.off_head_ids),
+      reinterpret_cast<int32_t *>(tb + TL.off_warp_count), reinterpret_cast<uint32_t *>(tb + TL.off_sample_total),
+      TL.slices_per_sample, TL.slot_cap, static_cast<PlanHeader *>(plan),
+      make_plan_header(kPlanKindRuns, batch, num_points, X, Y, Z))));
+  BEVPOOL_RETURN_IF_CUDA(le);
   BEVPOOL_LAUNCH_CHECK();
-  int32_t *big_list = reinterpret_cast<int32_t *>(tb + TL.off_big_list);
-  uint32_t *big_count = reinterpret_cast<uint32_t *>(tb + TL.off_big_count);
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_kernel, dim3(kSMs * 8), dim3(256), 0, stream,
-      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count));
+  return run_plan_finish(TL, PL, batch, cells, pb, tb, stream);
+}
+
+extern "C" int bevpool_rig_geom(const float *combine, const float *frustum_x, const float *frustum_y,
+                                const float *frustum_d, const float *lower_host, const float *voxel_size_host, int variant,
+                                int batch, int num_cams, int depth_bins, int feat_h, int feat_w, int32_t *geom_xyz,
+                                void *stream_) {
+  if (batch <= 0 || num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0 || !geom_xyz) return BEVPOOL_E_ARG;
+  RigParams rp;
+  int rc = make_rig_params(&rp, combine, frustum_x, frustum_y, frustum_d, lower_host, voxel_size_host);
+  if (rc) return rc;
+  const int64_t total = (int64_t)batch * num_cams * depth_bins * feat_h * feat_w;
+  if (total >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  BEVPOOL_RIG_DISPATCH(variant, (rig_geom_kernel<V><<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(
+                                    rp, num_cams, depth_bins, feat_h, feat_w, total, geom_xyz)));
   BEVPOOL_LAUNCH_CHECK();
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_big_kernel, dim3(kSMs * 2), dim3(256), 0, stream,
-                                    cell_start, placed, big_list, big_count, sorted_ids, sorted_cells, run_code));
-  BEVPOOL_LAUNCH_CHECK();
+  return BEVPOOL_OK;
+}
+
+// the plan's status word (0 = ok, BEVPOOL_PLAN_ROW_OVERFLOW = a consumer found the run_rows scratch too small);
+// synchronises `stream`
+extern "C" int bevpool_plan_status(const void *plan, int *status_host, void *stream_) {
+  if (!plan || !status_host) return BEVPOOL_E_ARG;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int32_t v = 0;
+  BEVPOOL_RETURN_IF_CUDA(cudaMemcpyAsync(&v, plan_status(const_cast<void *>(plan)), 4, cudaMemcpyDeviceToHost, stream));
+  BEVPOOL_RETURN_IF_CUDA(cudaStreamSynchronize(stream));
+  *status_host = (int)v;
   return BEVPOOL_OK;
 }
 

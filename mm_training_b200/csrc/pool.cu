@@ -13,6 +13,7 @@
 // are bit-stable run to run (the reference's are not).
 #include "common.cuh"
 #include "pool_g8.cuh"
+#include "tma.cuh"
 
 #include <cstdlib>
 #include <type_traits>
@@ -392,6 +393,64 @@ grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ g
   }
 }
 
+// ---- gradient rows, fp32, TMA version ---------------------------------------------------------------
+// Same contract as grad_rows_kernel (rows of occupied 32-cell tiles only).  A tile of 32 consecutive cells of
+// one BEV row is ONE tensor-map box of the NCHW gradient -- 32 x-cells x C channels, 128-byte rows -- landing in
+// shared memory as [channel][cell]; it is turned into [cell][channel] by a diagonal walk (lane l moves element
+// (channel c0 + l/2, cell l): reads hit 32 distinct banks, writes (16*cell + channel) mod 32 do too) and leaves
+// as ONE contiguous bulk store of 32 rows (32 * C * 4 bytes: the tile's rows are adjacent in the NHWC
+// buffer).  No LSU traffic to global memory at all; CTAs loop over tiles so that empty tiles (80 % of the
+// aiMotive grid) cost two cached loads, not a CTA launch.
+constexpr int kGtCells = 32;
+constexpr int kGtThreads = 128;
+template <int C>
+__global__ void __launch_bounds__(kGtThreads)
+grad_rows_tma_kernel(const __grid_constant__ CUtensorMap grad_map, const int32_t *__restrict__ cell_start,
+                     float *__restrict__ rows, int X, int Y, int batch, int tiles_x) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(128) unsigned char gt_raw[];
+  float *s_in = reinterpret_cast<float *>(gt_raw);                 // [C][32]
+  float *s_out = s_in + C * kGtCells;                              // [32][C]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_out + C * kGtCells);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const int64_t tiles = (int64_t)batch * Y * tiles_x;
+  uint32_t phase = 0;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int tx = (int)(t % tiles_x);
+    const int64_t by = t / tiles_x;                                // b * Y + y
+    const int64_t c0 = by * X + (int64_t)tx * kGtCells;           // first cell (global row index)
+    const int ncell = min(kGtCells, X - tx * kGtCells);
+    if (__ldg(cell_start + c0 + ncell) == __ldg(cell_start + c0)) continue;      // CTA-uniform: nothing landed here
+    const int y = (int)(by % Y), b = (int)(by / Y);
+    if (tid == 0) {
+      mbar_expect_tx(s_bar, (uint32_t)(C * kGtCells * 4));
+      tma_load_4d(s_in, &grad_map, tx * kGtCells, y, 0, b, s_bar);
+    }
+    mbar_wait(s_bar, phase);
+    phase ^= 1u;
+    // diagonal transpose: warp w handles channel offsets c0 = w, w + 4, ...
+    for (int cb = warp; cb < C; cb += kGtThreads / 32) {
+      int c = cb + (lane >> 1);
+      c = c >= C ? c - C : c;
+      s_out[lane * C + c] = s_in[c * kGtCells + lane];
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_1d(rows + c0 * C, s_out, (uint32_t)(ncell * C * 4));
+      tma_store_commit();
+      tma_store_wait_read();                                       // s_out is rewritten by the next tile
+    }
+    __syncthreads();
+  }
+}
+
 // ---- (batch, R, Cc) -> (batch, Cc, R) tiled transpose ----------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -416,17 +475,13 @@ transpose_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t R, int64
 }
 
 // ---- launchers ----------------------------------------------------------------------------
-static int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = kSMs;
-  }
-  return cached;
+static int sm_count() {                     // per device (a process may drive several GPUs)
+  int dev = 0, n = 0;
+  static int cached[64] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kSMs;
+  if (cached[dev] == 0)
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : kSMs;
+  return cached[dev];
 }
 static size_t forward_workspace_bytes(int C) {
   // head + tail partial rows of every slice of the largest grid the forward may launch
@@ -443,9 +498,8 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
       if (!workspace) return BEVPOOL_E_ARG;
       if (!aligned16(workspace)) return BEVPOOL_E_ALIGN;
       const FastDiv fd_dhw = make_fastdiv((uint32_t)dhw), fd_hw = make_fastdiv((uint32_t)hw);
-      int cps = env_int("BEVPOOL_FW_CPS", 6);          // CTAs per SM: cps-1 reduce + 1 zero-fill
-      cps = cps < 2 ? 2 : (cps > kFwMaxCtasPerSm ? kFwMaxCtasPerSm : cps);
-      const int u = env_int("BEVPOOL_FW_U", 4);
+      static const int cps_env = env_int("BEVPOOL_FW_CPS", 6), u = env_int("BEVPOOL_FW_U", 4);   // read once
+      const int cps = cps_env < 2 ? 2 : (cps_env > kFwMaxCtasPerSm ? kFwMaxCtasPerSm : cps_env);   // CTAs per SM: cps-1 reduce + 1 zero-fill
       const unsigned ctas = (unsigned)(sm_count() * cps);
       const int slices = (int)(ctas - ctas / cps) * kFwWarpsPerCta * 4;
       float *ws_head = static_cast<float *>(workspace);
@@ -453,15 +507,15 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
       if (u == 2) {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 2><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
+                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, (int64_t)INT32_MAX)));
       } else {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 4><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))));
+                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, (int64_t)INT32_MAX)));
       }
       BEVPOOL_LAUNCH_CHECK();
       BEVPOOL_G8_DISPATCH(C, (pool_forward_fixup_kernel<NV2><<<(unsigned)ceil_div64((int64_t)slices * 8, 128), 128, 0, s>>>(
-                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, (int64_t)0, total_cells, slices)));
+                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, (int64_t)0, total_cells, slices, (int64_t)INT32_MAX)));
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
@@ -523,36 +577,25 @@ static int fused_forward_t(const void *plan, const void *depth, const void *ctx,
 template <typename T>
 static int fused_backward_t(const void *plan, const void *grad, const void *depth, const void *ctx,
                             void *gdepth, void *gctx, int B, int N, int D, int H, int W, int C, int X,
-                            int Y, cudaStream_t s) {
+                            int Y, cudaStream_t s, bool nchw = false) {
   const int64_t Np = (int64_t)N * D * H * W;
   const PlanView pv = plan_view(plan, B, Np, X, Y);
   const int C4 = C >> 2;
+  (void)nchw;
   const T *g = static_cast<const T *>(grad), *dp = static_cast<const T *>(depth), *cx = static_cast<const T *>(ctx);
   T *gd = static_cast<T *>(gdepth), *gc = static_cast<T *>(gctx);
   const int64_t cells = (int64_t)X * Y;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
-      if (env_int("BEVPOOL_BW_KERNEL", 1) == 1 && fused_backward_tile_supported(C))   // 1: tile kernel with staged gradient rows (pool_bwd.cu); 0: per-group gather
+      // 2: column kernel (pool_bwd2.cu; needs W % 4 == 0), 1: tile kernel (pool_bwd.cu; any W, C <= 96)
+      static const int which = env_int("BEVPOOL_BW_KERNEL", 2);
+      if (which == 2 && fused_backward_col_supported(C, W, dp, gd, pv.cell_of_point))
+        return launch_fused_backward_col(pv.cell_of_point, g, dp, cx, gd, gc, nchw, B, N, D, H, W, C, cells, s);
+      if (!nchw && fused_backward_tile_supported(C))
         return launch_fused_backward_tile(pv.cell_of_point, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
-      const int hg = env_int("BEVPOOL_BW_HG", 2) == 1 ? 1 : 2;
-      const int64_t tiles_h = ceil_div64(H, 4 * hg), tiles_w = ceil_div64(W, kBwTW);
-      const int64_t ctas = (int64_t)B * N * tiles_h * tiles_w;
-      if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
-      const bool vec = (W % 4 == 0) && aligned16(dp) && aligned16(gd);
-#define BEVPOOL_BW_LAUNCH(HG, VEC, U)                                                                      \
-  BEVPOOL_G8_DISPATCH(C, (fused_backward_g8_kernel<NV2, HG, VEC, U><<<(unsigned)ctas, 128 * HG, 0, s>>>(   \
-                             pv.cell_of_point, g, dp, cx, gd, gc, N, D, H, W, cells, (int)tiles_h, (int)tiles_w, env_int("BEVPOOL_EXP_MASK", -1), env_int("BEVPOOL_EXP_FLAGS", 0))))
-      const int bu = env_int("BEVPOOL_BW_U", 2);
-      if (!vec) { if (hg == 1) { BEVPOOL_BW_LAUNCH(1, false, 2); } else { BEVPOOL_BW_LAUNCH(2, false, 2); } }
-      else if (hg == 1 && bu == 4) { BEVPOOL_BW_LAUNCH(1, true, 4); }
-      else if (hg == 1) { BEVPOOL_BW_LAUNCH(1, true, 2); }
-      else if (bu == 4) { BEVPOOL_BW_LAUNCH(2, true, 4); }
-      else { BEVPOOL_BW_LAUNCH(2, true, 2); }
-#undef BEVPOOL_BW_LAUNCH
-      BEVPOOL_LAUNCH_CHECK();
-      return BEVPOOL_OK;
     }
   }
+  if (nchw) return BEVPOOL_E_CHANNELS;      // the NCHW entry point exists only on the column kernel
   if (C4 <= 32) return launch_fused_backward_cpl<T, 1>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
   if (C4 <= 64) return launch_fused_backward_cpl<T, 2>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
   return launch_fused_backward_cpl<T, 4>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
@@ -630,6 +673,24 @@ extern "C" int bevpool_fused_backward(const void *plan, const void *grad_out_nhw
   BEVPOOL_DISPATCH_DTYPE(dtype, (fused_backward_t<T>(plan, grad_out_nhwc, depth, context_nhwc, grad_depth, grad_context_nhwc, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
 }
 
+extern "C" int bevpool_fused_backward_nchw(const void *plan, const void *grad_out_nhwc, const void *depth,
+                                           const void *context_nchw, void *grad_depth, void *grad_context_nchw,
+                                           int dtype, int batch, int num_cams, int depth_bins, int feat_h,
+                                           int feat_w, int channels, int X, int Y, void *stream) {
+  if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
+  int rc = check_plan_dims(batch, np, X, Y);
+  if (rc) return rc;
+  if (dtype != BEVPOOL_F32) return BEVPOOL_E_DTYPE;
+  if (!g8_supported(channels)) return BEVPOOL_E_CHANNELS;
+  if (!plan || !grad_out_nhwc || !depth || !context_nchw || !grad_depth || !grad_context_nchw) return BEVPOOL_E_ARG;
+  if (!aligned16(grad_out_nhwc) || !aligned16(context_nchw) || !aligned16(grad_context_nchw) || (feat_w % 4) != 0 ||
+      !aligned16(depth) || !aligned16(grad_depth))
+    return BEVPOOL_E_ALIGN;
+  return fused_backward_t<float>(plan, grad_out_nhwc, depth, context_nchw, grad_depth, grad_context_nchw, batch, num_cams,
+                                 depth_bins, feat_h, feat_w, channels, X, Y, static_cast<cudaStream_t>(stream), true);
+}
+
 extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nhwc, int dtype,
                                  int batch, int64_t num_points, int channels, int X, int Y, void *stream) {
   int rc = check_plan_dims(batch, num_points, X, Y);
@@ -640,7 +701,39 @@ extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, vo
   const PlanView pv = plan_view(plan, batch, num_points, X, Y);
   const int64_t G = (int64_t)X * Y;
   const dim3 grid((unsigned)ceil_div64(G, 32 * kGrTilesPerCta), (unsigned)batch);
-  if (dtype == BEVPOOL_F32) {
+  static const int use_tma = env_int("BEVPOOL_GRAD_ROWS_TMA", 1);
+  if (dtype == BEVPOOL_F32 && use_tma && g8_supported(channels) && (X % 4) == 0 && aligned16(grad_out_nchw) &&
+      aligned16(rows_nhwc)) {
+    CUtensorMap gmap{};
+    const uint64_t dims[4] = {(uint64_t)X, (uint64_t)Y, (uint64_t)channels, (uint64_t)batch};
+    const uint64_t strides[3] = {(uint64_t)X * 4, (uint64_t)G * 4, (uint64_t)channels * G * 4};
+    const uint32_t box[4] = {kGtCells, 1, (uint32_t)channels, 1};
+    if ((rc = make_tensor_map_f32(&gmap, grad_out_nchw, 4, dims, strides, box))) return rc;
+    const int tiles_x = (int)ceil_div64(X, kGtCells);
+    const int64_t tiles = (int64_t)batch * Y * tiles_x;
+    const size_t smem = (size_t)2 * channels * kGtCells * 4 + 16;
+    const int per_sm = (int)((size_t)200 * 1024 / (smem + 1024));
+    int64_t ctas = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 12 ? 12 : per_sm));
+    ctas = ctas > tiles ? tiles : ctas;
+    cudaError_t le = cudaSuccess;
+#define BEVPOOL_GT_LAUNCH(CC)                                                                                          \
+    do {                                                                                                               \
+      if (smem > 48 * 1024)                                                                                            \
+        BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(grad_rows_tma_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      le = launch_pdl(grad_rows_tma_kernel<CC>, dim3((unsigned)ctas), dim3(kGtThreads), smem, s, gmap, pv.cell_start,  \
+                      static_cast<float *>(rows_nhwc), X, Y, batch, tiles_x);                                          \
+    } while (0)
+    switch (channels) {
+      case 32: BEVPOOL_GT_LAUNCH(32); break;
+      case 64: BEVPOOL_GT_LAUNCH(64); break;
+      case 80: BEVPOOL_GT_LAUNCH(80); break;
+      case 96: BEVPOOL_GT_LAUNCH(96); break;
+      case 128: BEVPOOL_GT_LAUNCH(128); break;
+      default: return BEVPOOL_E_CHANNELS;
+    }
+#undef BEVPOOL_GT_LAUNCH
+    BEVPOOL_RETURN_IF_CUDA(le);
+  } else if (dtype == BEVPOOL_F32) {
     const size_t smem = (size_t)32 * (channels + 1) * 4;
     if (smem > 48 * 1024)
       BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(grad_rows_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -62,6 +62,47 @@ __device__ __forceinline__ int g8_channel(int r, int l8) {
   return r < 4 * NF4 ? 32 * (r >> 2) + 4 * l8 + (r & 3) : 32 * NF4 + 2 * l8 + (r - 4 * NF4);
 }
 
+// ---- shared-memory row access and hinted stores (g8 layout) -------------------------------------
+__device__ __forceinline__ void stg_hint_f4(float *p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint_f2(float *p, float2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+
+template <int NV2>
+__device__ __forceinline__ void g8_lds_row(const float *row, int l8, float (&v)[2 * NV2]) {
+  constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
+#pragma unroll
+  for (int k = 0; k < NF4; ++k) {
+    const float4 t = *reinterpret_cast<const float4 *>(row + 32 * k + 4 * l8);
+    v[4 * k + 0] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+  if (NF2) {
+    const float2 t = *reinterpret_cast<const float2 *>(row + 32 * NF4 + 2 * l8);
+    v[4 * NF4 + 0] = t.x; v[4 * NF4 + 1] = t.y;
+  }
+}
+
+template <int NV2>
+__device__ __forceinline__ void g8_store_row_hint(float *row, int l8, const float (&v)[2 * NV2], uint64_t pol) {
+  constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
+#pragma unroll
+  for (int k = 0; k < NF4; ++k)
+    stg_hint_f4(row + 32 * k + 4 * l8, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]), pol);
+  if (NF2) stg_hint_f2(row + 32 * NF4 + 2 * l8, make_float2(v[4 * NF4], v[4 * NF4 + 1]), pol);
+}
+
+template <int NV2>
+__device__ __forceinline__ void g8_store_row_plain(float *row, int l8, const float (&v)[2 * NV2]) {
+  constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
+#pragma unroll
+  for (int k = 0; k < NF4; ++k)
+    *reinterpret_cast<float4 *>(row + 32 * k + 4 * l8) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  if (NF2) *reinterpret_cast<float2 *>(row + 32 * NF4 + 2 * l8) = make_float2(v[4 * NF4], v[4 * NF4 + 1]);
+}
+
 // ---- packed fp32 math (Blackwell FFMA2 / FADD2: two fp32 lanes per instruction) ---------------
 template <int NREG>
 __device__ __forceinline__ void axpy_row(float (&acc)[NREG], float a, const float (&v)[NREG]) {
@@ -113,8 +154,8 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
                           const int32_t *__restrict__ sorted_cells, const float *__restrict__ rows,
                           const float *__restrict__ depth, float *__restrict__ out,
                           float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t cell_base,
-                          int64_t total_cells, FastDiv div_dhw, FastDiv div_hw, int fill_period, int exp_mask,
-                          int exp_flags) {
+                          int64_t total_cells, FastDiv div_dhw, FastDiv div_hw, int fill_period,
+                          int64_t row_capacity) {
   pdl_wait();
   pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4;
@@ -124,7 +165,6 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
   // the other CTAs, co-resident on the same SMs, run the latency-bound reduction.
   const int bid = blockIdx.x;
   if (fill_period > 0 && bid % fill_period == fill_period - 1) {
-    if (exp_flags & 1) return;
     const int fwarp = (bid / fill_period) * kFwWarpsPerCta + warp;
     const int nfw = (gridDim.x / fill_period) * kFwWarpsPerCta;
     const int64_t per_warp = ((total_cells + nfw - 1) / nfw + 31) & ~(int64_t)31;
@@ -160,9 +200,9 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
   const int nwarps = (fill_period > 0 ? gridDim.x - gridDim.x / fill_period : gridDim.x) * kFwWarpsPerCta;
 
   // ---- my slice of the sorted list (entries [e0, K) of it)
-  if (exp_flags & 2) return;
   const int e0 = __ldg(cell_start + cell_base);
-  const int K = __ldg(cell_start + cell_base + total_cells);
+  // kIdent: never walk past the rows the caller allocated (a stale max_runs hint; stage A raised the plan's status word)
+  const int K = (int)min((int64_t)__ldg(cell_start + cell_base + total_cells), kIdent ? (int64_t)e0 + row_capacity : (int64_t)INT32_MAX);
   const int L = fwd_slice_len(K - e0, nwarps * 4);
   const int s = wglobal * 4 + grp;
   const int lo = (int)min((int64_t)e0 + (int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
@@ -224,7 +264,7 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
       int kk[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const unsigned row = __shfl_sync(kFull, row_c, j0 + u, 8) & (unsigned)exp_mask;
+        const unsigned row = __shfl_sync(kFull, row_c, j0 + u, 8);
         d[u] = __shfl_sync(kFull, d_c, j0 + u, 8);
         kk[u] = __shfl_sync(kFull, key_c, j0 + u, 8);
         if (!guard || pos + j0 + u < hi) {
@@ -263,14 +303,15 @@ template <int NV2>
 __global__ void __launch_bounds__(128)
 pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_cells,
                           const float *__restrict__ ws_head, const float *__restrict__ ws_tail,
-                          float *__restrict__ out, int64_t cell_base, int64_t total_cells, int num_slices) {
+                          float *__restrict__ out, int64_t cell_base, int64_t total_cells, int num_slices,
+                          int64_t row_capacity) {
   pdl_wait();
   pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2;
   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, l8 = threadIdx.x & 7;
   if (s >= num_slices) return;
   const int e0 = __ldg(cell_start + cell_base);
-  const int K = __ldg(cell_start + cell_base + total_cells);
+  const int K = (int)min((int64_t)__ldg(cell_start + cell_base + total_cells), (int64_t)e0 + row_capacity);
   const int L = fwd_slice_len(K - e0, num_slices);
   const int lo = (int)min((int64_t)e0 + (int64_t)s * L, (int64_t)K), hi = min(lo + L, K);
   if (hi <= lo || hi >= K) return;
@@ -287,150 +328,6 @@ pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t 
     if (!(thi < K && __ldg(sorted_cells + thi - 1) == key && __ldg(sorted_cells + thi) == key)) break;
   }
   g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)key * C), l8, acc);
-}
-
-// ---- fused backward ---------------------------------------------------------------------------
-// Pixel-centric, no atomics, no sort:
-//   grad_depth[d, pix]  = <grad_out[cell(d, pix), :], context[pix, :]>
-//   grad_context[pix,:] = sum_d depth[d, pix] * grad_out[cell(d, pix), :]
-// CTA tile = 4 image columns x (4*HG) image rows of one camera image; warp = one column x 4 rows,
-// 8-lane group = one pixel, which it follows through all depth bins (its context row and its
-// context-gradient accumulator live in registers, summed in ascending-d order).
-//  * The 4 rows of a warp project to the same BEV cell for a level camera, so the 4 groups ask for
-//    the SAME gradient row: one L1 wavefront per 128 B instead of four, and the other row-warps of
-//    the CTA hit the line in L1.  Nothing relies on that: rows with different cells just cost more
-//    wavefronts.
-//  * cell_of_point / depth / grad_depth are (d, h, w)-major, i.e. strided by H*W along a pixel's
-//    ray.  They are moved 32 depth bins at a time as 16-byte (4-column) segments through shared
-//    memory, one segment per thread, and the next chunk's segments are prefetched into registers
-//    while the current chunk is reduced.
-constexpr int kBwTW = 4;     // image columns per CTA = one 16-byte segment
-constexpr int kBwDC = 32;    // depth bins per staged chunk
-constexpr int kBwHG = 2;     // row groups (of 4 rows) per CTA
-
-template <int NV2, int HG, bool kVec, int kBwU /* depth bins in flight per warp */>
-__global__ void __launch_bounds__(128 * HG)
-fused_backward_g8_kernel(const int32_t *__restrict__ cell_of_point, const float *__restrict__ grad_rows,
-                         const float *__restrict__ depth, const float *__restrict__ ctx_nhwc,
-                         float *__restrict__ grad_depth, float *__restrict__ grad_ctx_nhwc, int num_cams,
-                         int D, int H, int W, int64_t cells_per_sample, int tiles_h, int tiles_w, int exp_mask,
-                         int exp_flags) {
-  constexpr int C = 16 * NV2, NREG = 2 * NV2, TH = 4 * HG, LD = kBwDC + 1;
-  __shared__ uint2 s_cd[kBwTW][TH][LD];    // (cell, depth bits) of the chunk, [column][row][bin]
-  __shared__ float s_res[kBwTW][TH][LD];   // grad_depth of the chunk
-  const int tid = threadIdx.x, lane = tid & 31, l8 = lane & 7, grp = lane >> 3, warp = tid >> 5;
-  int bid = blockIdx.x;
-  const int th = bid % tiles_h; bid /= tiles_h;
-  const int tw = bid % tiles_w;
-  const int bn = bid / tiles_w;
-  const int h0 = th * TH, w0 = tw * kBwTW;
-  const int HW = H * W;
-  const int64_t img_base = (int64_t)bn * D * HW;
-  const char *gbase = opaque_ptr(grad_rows + (int64_t)(bn / num_cams) * cells_per_sample * C);
-
-  // staging role: thread = (bin sd of the chunk, row sh of the tile), 4 columns
-  const int sd = lane, sh = warp;
-  const bool srow = h0 + sh < H;
-  const int64_t sbase = img_base + (int64_t)(h0 + sh) * W + w0;
-  // reducing role: warp = (column wl, row group hg); group = row hl
-  const int wl = warp & 3, hl = 4 * (warp >> 2) + grp;
-  const bool pix_ok = (w0 + wl < W) && (h0 + hl < H);
-  const int hw = (h0 + hl) * W + w0 + wl;
-
-  float cx[NREG], gacc[NREG];
-#pragma unroll
-  for (int r = 0; r < NREG; ++r) cx[r] = gacc[r] = 0.f;
-  // context row of the group's pixel: one contiguous C-float row of the (B*N, H, W, C) tensor
-  if (pix_ok) g8_load_row<NV2, true>(reinterpret_cast<const char *>(ctx_nhwc + ((int64_t)bn * HW + hw) * C), l8, cx);
-
-  int4 pc = make_int4(-1, -1, -1, -1);
-  float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto prefetch = [&](int d0) {
-    const int d = d0 + sd;
-    pc = make_int4(-1, -1, -1, -1);
-    if (srow && d < D) {
-      const int64_t gp = sbase + (int64_t)d * HW;
-      if (kVec) {
-        pc = ldg_stream_i4(reinterpret_cast<const int4 *>(cell_of_point + gp));
-        pd = ldg_stream_f4(reinterpret_cast<const float4 *>(depth + gp));
-      } else {
-        if (w0 + 0 < W) { pc.x = __ldg(cell_of_point + gp + 0); pd.x = __ldg(depth + gp + 0); }
-        if (w0 + 1 < W) { pc.y = __ldg(cell_of_point + gp + 1); pd.y = __ldg(depth + gp + 1); }
-        if (w0 + 2 < W) { pc.z = __ldg(cell_of_point + gp + 2); pd.z = __ldg(depth + gp + 2); }
-        if (w0 + 3 < W) { pc.w = __ldg(cell_of_point + gp + 3); pd.w = __ldg(depth + gp + 3); }
-      }
-    }
-  };
-  prefetch(0);
-
-  for (int d0 = 0; d0 < D; d0 += kBwDC) {
-    s_cd[0][sh][sd] = make_uint2((unsigned)pc.x, __float_as_uint(pd.x));
-    s_cd[1][sh][sd] = make_uint2((unsigned)pc.y, __float_as_uint(pd.y));
-    s_cd[2][sh][sd] = make_uint2((unsigned)pc.z, __float_as_uint(pd.z));
-    s_cd[3][sh][sd] = make_uint2((unsigned)pc.w, __float_as_uint(pd.w));
-    s_res[0][sh][sd] = 0.f; s_res[1][sh][sd] = 0.f; s_res[2][sh][sd] = 0.f; s_res[3][sh][sd] = 0.f;
-    __syncthreads();
-    if (d0 + kBwDC < D) prefetch(d0 + kBwDC);     // in flight while this chunk is reduced
-
-    // bins of the chunk kept by at least one of the warp's 4 rows
-    unsigned dmask = 0u;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = (int)s_cd[wl][hl][l8 + 8 * k].x;
-      unsigned m = __ballot_sync(0xffffffffu, c >= 0);
-      m |= m >> 16;
-      m |= m >> 8;
-      dmask |= (m & 0xffu) << (8 * k);
-    }
-    if (exp_flags & 1) dmask = 0u;
-    while (dmask) {
-      int dq[kBwU];
-      uint2 e[kBwU];
-      bool on[kBwU];
-      float g[kBwU][NREG];
-#pragma unroll
-      for (int q = 0; q < kBwU; ++q) {
-        dq[q] = dmask ? __ffs(dmask) - 1 : 0;
-        on[q] = dmask != 0u;
-        dmask &= dmask - 1u;
-        e[q] = s_cd[wl][hl][dq[q]];
-        on[q] = on[q] && (int)e[q].x >= 0;
-        if (on[q]) g8_load_row<NV2, false>(row_ptr<C * 4>(gbase, e[q].x & (unsigned)exp_mask), l8, g[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < kBwU; ++q) {
-        float dot = 0.f;
-        if (on[q]) {
-          const float dv = __uint_as_float(e[q].y);
-          float2 dot2 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int r = 0; r < NREG; r += 2)
-            dot2 = __ffma2_rn(make_float2(g[q][r], g[q][r + 1]), make_float2(cx[r], cx[r + 1]), dot2);
-          dot = dot2.x + dot2.y;
-          axpy_row<NREG>(gacc, dv, g[q]);
-        }
-        dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        if (on[q] && l8 == 0) s_res[wl][hl][dq[q]] = dot;
-      }
-    }
-    __syncthreads();
-    const int d = d0 + sd;
-    if (srow && d < D) {
-      const int64_t gp = sbase + (int64_t)d * HW;
-      const float4 r4 = make_float4(s_res[0][sh][sd], s_res[1][sh][sd], s_res[2][sh][sd], s_res[3][sh][sd]);
-      if (kVec) {
-        stg_stream_f4(reinterpret_cast<float4 *>(grad_depth + gp), r4);
-      } else {
-        if (w0 + 0 < W) grad_depth[gp + 0] = r4.x;
-        if (w0 + 1 < W) grad_depth[gp + 1] = r4.y;
-        if (w0 + 2 < W) grad_depth[gp + 2] = r4.z;
-        if (w0 + 3 < W) grad_depth[gp + 3] = r4.w;
-      }
-    }
-  }
-  if (pix_ok) g8_store_row<NV2>(reinterpret_cast<char *>(grad_ctx_nhwc + ((int64_t)bn * HW + hw) * C), l8, gacc);
 }
 
 inline bool g8_supported(int C) {

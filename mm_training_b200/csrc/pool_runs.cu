@@ -23,6 +23,7 @@
 // read back through L2 (11x fewer rows), processed a few frames at a time so it never leaves L2.
 #include "common.cuh"
 #include "pool_g8.cuh"
+#include "tma.cuh"
 
 #include <cstdlib>
 
@@ -39,98 +40,6 @@ constexpr int kRaStages = 3;                 // chunks of (code, depth) in share
 constexpr int kRaThreads = 256;
 constexpr int kRaZeroCells = 32;             // cells covered by the zeroed shared-memory buffer
 
-// ---- TMA (bulk async copy) + mbarrier helpers, sm_90+ PTX ---------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared, completion counted in bytes on the mbarrier (16-byte aligned addresses and size)
-__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// shared -> global, tracked by the thread's bulk async-group
-__device__ __forceinline__ void tma_store_1d(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-// L2 eviction-priority policies: the zero-fill is written once and never read by these kernels
-// (evict_first), the run rows are read back by stage B right after (evict_last)
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void tma_store_1d_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-               ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void stg_hint_f4(float *p, float4 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
-               ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void stg_hint_f2(float *p, float2 v, uint64_t pol) {
-  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async16_runs(void *dst_smem, const void *src_gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-
-template <int NV2>
-__device__ __forceinline__ void g8_lds_row(const float *row, int l8, float (&v)[2 * NV2]) {
-  constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
-#pragma unroll
-  for (int k = 0; k < NF4; ++k) {
-    const float4 t = *reinterpret_cast<const float4 *>(row + 32 * k + 4 * l8);
-    v[4 * k + 0] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-  }
-  if (NF2) {
-    const float2 t = *reinterpret_cast<const float2 *>(row + 32 * NF4 + 2 * l8);
-    v[4 * NF4 + 0] = t.x; v[4 * NF4 + 1] = t.y;
-  }
-}
-
-template <int NV2>
-__device__ __forceinline__ void g8_store_row_hint(float *row, int l8, const float (&v)[2 * NV2], uint64_t pol) {
-  constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
-#pragma unroll
-  for (int k = 0; k < NF4; ++k)
-    stg_hint_f4(row + 32 * k + 4 * l8, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]), pol);
-  if (NF2) stg_hint_f2(row + 32 * NF4 + 2 * l8, make_float2(v[4 * NF4], v[4 * NF4 + 1]), pol);
-}
-
-template <int NV2>
-__device__ __forceinline__ void g8_store_row_plain(float *row, int l8, const float (&v)[2 * NV2]) {
-  constexpr int NF4 = NV2 / 2, NF2 = NV2 & 1;
-#pragma unroll
-  for (int k = 0; k < NF4; ++k)
-    *reinterpret_cast<float4 *>(row + 32 * k + 4 * l8) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-  if (NF2) *reinterpret_cast<float2 *>(row + 32 * NF4 + 2 * l8) = make_float2(v[4 * NF4], v[4 * NF4 + 1]);
-}
-
 // one (depth bin, column) pair of an 8-lane group: codes / depths of its 16 rows (lane l8 holds rows l8 and
 // l8 + 8), the group's kept-row and first-of-run masks
 struct RunCol {
@@ -139,17 +48,45 @@ struct RunCol {
   unsigned km, hm;
 };
 
+// In-place layout change of a TMA box of the NCHW context tensor, [channel][16 rows][4 columns], into pixel
+// rows [row][column][channel], through registers (all threads read, barrier, all threads write).  Element e of
+// the thread walks the channels fastest with the row rotated by the channel, so the transposed writes are
+// conflict-free and the reads 4-way conflicted at worst (once per CTA: ~1 % of its lifetime).
+template <int C>
+__device__ __forceinline__ void nchw_box_to_rows(float *s_ctx, int tid) {
+  constexpr int kElems = kRunHB * kRaTW * C, kPer = (kElems + kRaThreads - 1) / kRaThreads;
+  float v[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int e = k * kRaThreads + tid;
+    if (e < kElems) {
+      const int c = e % C, rest = e / C, w = rest & (kRaTW - 1), h = ((rest >> 2) + c) & (kRunHB - 1);
+      v[k] = s_ctx[(c * kRunHB + h) * kRaTW + w];
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) {
+    const int e = k * kRaThreads + tid;
+    if (e < kElems) {
+      const int c = e % C, rest = e / C, w = rest & (kRaTW - 1), h = ((rest >> 2) + c) & (kRunHB - 1);
+      s_ctx[(h * kRaTW + w) * C + c] = v[k];
+    }
+  }
+  __syncthreads();
+}
+
 // ---- stage A ----------------------------------------------------------------------------------
 // CTA = (image, 4 columns x 16 rows, one of `d_split` depth ranges), walked in chunks of 32 depth bins.
 // warp = (column wl, 8 consecutive bins per round): every 8-lane group walks the rows of TWO
 // (bin, column) pairs, so one shared-memory read of a context row (one wavefront for the whole warp:
 // all four groups read the same row) feeds 8 depth (x) context products.
-template <int NV2>
+template <int NV2, bool kNchw>
 __global__ void __launch_bounds__(kRaThreads, 4)
-frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restrict__ depth,
-                      const float *__restrict__ ctx_nhwc, float *__restrict__ run_rows,
-                      const int32_t *__restrict__ cell_start, float *__restrict__ out, int img0,
-                      int64_t cell_base, int64_t num_cells, int D, int H, int W, int d_split, int d_per_cta,
+frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t *__restrict__ run_code,
+                      const float *__restrict__ depth, const float *__restrict__ ctx_nhwc, float *__restrict__ run_rows,
+                      const int32_t *__restrict__ cell_start, float *__restrict__ out, int32_t *__restrict__ status,
+                      int img0, int64_t cell_base, int64_t num_cells, int D, int H, int W, int d_split, int d_per_cta,
                       int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints) {
   pdl_wait();
   pdl_trigger();
@@ -172,7 +109,10 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
   const int HW = H * W;
   const int rows_here = min(kRunHB, H - h0), cols_here = min(kRaTW, W - w0);
 
-  // ---- context tile by TMA: one bulk copy per image row (cols_here * C contiguous floats)
+  // ---- context tile by TMA.  Pixel rows (B*N, H, W, C): one bulk copy per image row (cols_here * C contiguous
+  // floats).  NCHW (the reference's layout, lss_fpn.py:441-443): ONE tensor-map box of 4 columns x 16 rows x C
+  // channels, landing as [channel][row][column] and turned into pixel rows in place below (rows beyond H arrive
+  // as zeros).
   if (tid == 0) {
     mbar_init(s_bar, 1);
     fence_proxy_async();
@@ -180,16 +120,21 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
   if (fill) {
     for (int i = tid; i < kRaZeroCells * C / 4; i += kRaThreads) reinterpret_cast<float4 *>(s_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  if (rows_here < kRunHB || cols_here < kRaTW) {       // ragged tile: rows / columns the copies do not cover read as zeros
+  if (!kNchw && (rows_here < kRunHB || cols_here < kRaTW)) {       // ragged tile: rows / columns the copies do not cover read as zeros
     for (int i = tid; i < kRunHB * kRaTW * C / 4; i += kRaThreads) reinterpret_cast<float4 *>(s_ctx)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async();
   __syncthreads();
   if (tid == 0) {
-    const uint32_t row_bytes = (uint32_t)cols_here * C * 4;
-    mbar_expect_tx(s_bar, row_bytes * rows_here);
-    for (int r = 0; r < rows_here; ++r)
-      tma_load_1d(s_ctx + r * (kRaTW * C), ctx_nhwc + (((int64_t)bn * H + h0 + r) * W + w0) * C, row_bytes, s_bar);
+    if (kNchw) {
+      mbar_expect_tx(s_bar, (uint32_t)(kRunHB * kRaTW * C * 4));
+      tma_load_4d(s_ctx, &ctx_map, w0, h0, 0, bn, s_bar);
+    } else {
+      const uint32_t row_bytes = (uint32_t)cols_here * C * 4;
+      mbar_expect_tx(s_bar, row_bytes * rows_here);
+      for (int r = 0; r < rows_here; ++r)
+        tma_load_1d(s_ctx + r * (kRaTW * C), ctx_nhwc + (((int64_t)bn * H + h0 + r) * W + w0) * C, row_bytes, s_bar);
+    }
   }
 
   // ---- zero-fill of this CTA's share of the empty BEV cells.  A block of 32 cells that is entirely
@@ -241,8 +186,8 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
       if (srow && d < d_end) {
         const int64_t gp = sbase + (int64_t)d * HW;
         if (vec) {
-          cp_async16_runs(dc, run_code + gp);
-          cp_async16_runs(dd, depth + gp);
+          cp_async16(dc, run_code + gp);
+          cp_async16(dd, depth + gp);
         } else {
           int4 pc = make_int4(kRunDropped, kRunDropped, kRunDropped, kRunDropped);
           float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -269,6 +214,8 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
     if (slot >= 0 && slot < capacity) {
       if (hints) g8_store_row_hint<NV2>(run_rows + slot * C, l8, acc, pol_rows);
       else g8_store_row_plain<NV2>(run_rows + slot * C, l8, acc);
+    } else if (slot >= capacity && l8 == 0) {
+      *status = kPlanStatusRowOverflow;      // the caller's run_rows scratch is smaller than the run count (stale max_runs hint)
     }
   };
   auto warp_union = [&](unsigned m) -> unsigned {       // any-group union of a per-group mask (warp-uniform)
@@ -287,6 +234,7 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
     if (!ctx_ready) {                                       // first chunk: the context tile must have landed
       mbar_wait(s_bar, 0);
       ctx_ready = true;
+      if (kNchw) nchw_box_to_rows<C>(s_ctx, tid);
     }
     const int st = cidx % kRaStages;
     auto load_col = [&](int dl, RunCol &q) {
@@ -375,10 +323,10 @@ frustum_reduce_kernel(const int32_t *__restrict__ run_code, const float *__restr
 
 using namespace bevpool;
 
-template <int NV2>
-static int launch_stage_a(const PlanView &pv, const float *dp, const float *cx, float *rr, float *out, int img0,
-                          int64_t cell_base, int64_t num_cells, int nb, int num_cams, int D, int H, int W,
-                          int64_t capacity, int vec, int fill, int hints, int d_split, cudaStream_t s) {
+template <int NV2, bool kNchw>
+static int launch_stage_a(const CUtensorMap &ctx_map, const PlanView &pv, const float *dp, const float *cx, float *rr,
+                          float *out, int32_t *status, int img0, int64_t cell_base, int64_t num_cells, int nb, int num_cams,
+                          int D, int H, int W, int64_t capacity, int vec, int fill, int hints, int d_split, cudaStream_t s) {
   constexpr int C = 16 * NV2;
   const int tiles_h = (int)ceil_div64(H, kRunHB), tiles_w = (int)ceil_div64(W, kRaTW);
   const int d_per_cta = (int)(ceil_div64(ceil_div64(D, d_split), kRaDC) * kRaDC);      // whole chunks per CTA
@@ -387,64 +335,91 @@ static int launch_stage_a(const PlanView &pv, const float *dp, const float *cx, 
   if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
   const size_t smem = (size_t)kRunHB * kRaTW * C * 4 + (size_t)kRaStages * kRaDC * kRunHB * 32 + (size_t)kRaZeroCells * C * 4 + 16;
   if (smem > 48 * 1024)
-    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
-      pv.run_code, dp, cx, rr, pv.cell_start, out, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
+    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2, kNchw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
+      ctx_map, pv.run_code, dp, cx, rr, pv.cell_start, out, status, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
       tiles_w, capacity, vec, fill, hints));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
 
 static int sm_count_runs() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
-      cached = kSMs;
-  }
-  return cached;
+  int dev = 0, n = 0;
+  static int cached[64] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kSMs;
+  if (cached[dev] == 0)
+    cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : kSMs;
+  return cached[dev];
 }
 
-extern "C" int bevpool_fused_forward_runs(const void *plan, const void *depth, const void *context_nhwc,
-                                          void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
-                                          int feat_h, int feat_w, int channels, int X, int Y, void *run_rows,
-                                          int64_t run_rows_capacity, void *workspace, void *stream) {
+// tuning knobs, read once per process (defaults = the measured best; scripts/README.md)
+struct RunKnobs {
+  int chunk, fill, hints, cps_b, d_split;
+};
+static const RunKnobs &run_knobs() {
+  static const RunKnobs k = [] {
+    RunKnobs r;
+    r.chunk = env_int_runs("BEVPOOL_RUN_CHUNK", 0);            // frames per (stage A, stage B) pair; 0 = all
+    r.fill = env_int_runs("BEVPOOL_RUN_FILL", 1) != 0;         // 0: stage B fills the empty cells itself
+    r.hints = env_int_runs("BEVPOOL_RUN_HINTS", 1) != 0;       // L2 eviction-priority hints on the fill / run-row stores
+    r.cps_b = env_int_runs("BEVPOOL_RUN_CPSB", 5);             // stage B CTAs per SM (4 warps each)
+    r.cps_b = r.cps_b < 1 ? 1 : (r.cps_b > kFwMaxCtasPerSm - 1 ? kFwMaxCtasPerSm - 1 : r.cps_b);
+    r.d_split = env_int_runs("BEVPOOL_RUN_DSPLIT", 0);
+    return r;
+  }();
+  return k;
+}
+
+static int fused_forward_runs_impl(const void *plan, const void *depth, const void *context, bool nchw, void *out_nhwc,
+                                   int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                                   int channels, int X, int Y, void *run_rows, int64_t run_rows_capacity,
+                                   void *workspace, void *stream) {
   if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
   const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
   int rc = check_plan_dims(batch, np, X, Y);
   if (rc) return rc;
   if (dtype != BEVPOOL_F32) return BEVPOOL_E_DTYPE;
   if (!g8_supported(channels)) return BEVPOOL_E_CHANNELS;
-  if (!plan || !depth || !context_nhwc || !out_nhwc || !run_rows || !workspace || run_rows_capacity <= 0) return BEVPOOL_E_ARG;
-  if (!aligned16(context_nhwc) || !aligned16(out_nhwc) || !aligned16(run_rows) || !aligned16(workspace)) return BEVPOOL_E_ALIGN;
+  if (!plan || !depth || !context || !out_nhwc || !run_rows || !workspace || run_rows_capacity <= 0) return BEVPOOL_E_ARG;
+  if (!aligned16(context) || !aligned16(out_nhwc) || !aligned16(run_rows) || !aligned16(workspace)) return BEVPOOL_E_ALIGN;
+  if (nchw && (feat_w % 4) != 0) return BEVPOOL_E_ALIGN;      // the tensor-map rows must be multiples of 16 bytes
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const PlanView pv = plan_view(plan, batch, np, X, Y);
+  int32_t *status = plan_status(const_cast<void *>(plan));
   const int64_t G = (int64_t)X * Y;
   const int vec = (feat_w % 4 == 0) && aligned16(depth);
-  int fpc = env_int_runs("BEVPOOL_RUN_CHUNK", 0);           // frames per (stage A, stage B) pair; 0 = all
+  const RunKnobs &kn = run_knobs();
+  int fpc = kn.chunk;
   if (fpc <= 0 || fpc > batch) fpc = batch;
-  const int fill = env_int_runs("BEVPOOL_RUN_FILL", 1) != 0;        // 0: stage B fills the empty cells itself
-  const int hints = env_int_runs("BEVPOOL_RUN_HINTS", 1) != 0;      // L2 eviction-priority hints on the fill / run-row stores
-  int cps_b = env_int_runs("BEVPOOL_RUN_CPSB", 5);                   // stage B CTAs per SM (4 warps each)
-  cps_b = cps_b < 1 ? 1 : (cps_b > kFwMaxCtasPerSm - 1 ? kFwMaxCtasPerSm - 1 : cps_b);
-  const float *dp = static_cast<const float *>(depth), *cx = static_cast<const float *>(context_nhwc);
+  const int fill = kn.fill, hints = kn.hints, cps_b = kn.cps_b;
+  const float *dp = static_cast<const float *>(depth), *cx = static_cast<const float *>(context);
   float *rr = static_cast<float *>(run_rows), *out = static_cast<float *>(out_nhwc);
+  CUtensorMap ctx_map{};
+  if (nchw) {
+    const uint64_t dims[4] = {(uint64_t)feat_w, (uint64_t)feat_h, (uint64_t)channels, (uint64_t)batch * num_cams};
+    const uint64_t strides[3] = {(uint64_t)feat_w * 4, (uint64_t)feat_h * feat_w * 4, (uint64_t)channels * feat_h * feat_w * 4};
+    const uint32_t box[4] = {kRaTW, kRunHB, (uint32_t)channels, 1};
+    if ((rc = make_tensor_map_f32(&ctx_map, cx, 4, dims, strides, box))) return rc;
+  }
   const FastDiv one = make_fastdiv(1u);
   for (int b0 = 0; b0 < batch; b0 += fpc) {
     const int nb = batch - b0 < fpc ? batch - b0 : fpc;
     const int64_t cell_base = (int64_t)b0 * G, ncells = (int64_t)nb * G;
     // depth ranges per tile: enough CTAs for >= ~4 waves of 4 resident CTAs per SM
     const int64_t tiles = (int64_t)nb * num_cams * ceil_div64(feat_w, kRaTW) * ceil_div64(feat_h, kRunHB);
-    int d_split = env_int_runs("BEVPOOL_RUN_DSPLIT", 0);
+    int d_split = kn.d_split;
     if (d_split <= 0) {
       d_split = (int)ceil_div64((int64_t)16 * sm_count_runs(), tiles);
       const int max_split = (int)ceil_div64(depth_bins, kRaDC);
       d_split = d_split < 1 ? 1 : (d_split > max_split ? max_split : d_split);
     }
-    BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2>(pv, dp, cx, rr, out, b0 * num_cams, cell_base, ncells, nb, num_cams,
-                                                            depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, s)));
+    if (nchw) {
+      BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2, true>(ctx_map, pv, dp, cx, rr, out, status, b0 * num_cams, cell_base, ncells, nb, num_cams,
+                                                                    depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, s)));
+    } else {
+      BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2, false>(ctx_map, pv, dp, cx, rr, out, status, b0 * num_cams, cell_base, ncells, nb, num_cams,
+                                                                     depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, s)));
+    }
     if (rc) return rc;
     // stage B: even-share segmented sum of the run rows (identity ids), fill CTAs only if stage A did not fill
     const int period_b = fill ? 0 : cps_b + 1;
@@ -456,15 +431,31 @@ extern "C" int bevpool_fused_forward_runs(const void *plan, const void *depth, c
     BEVPOOL_G8_DISPATCH(channels, (le = launch_pdl_if(pdl_forward_enabled(), pool_forward_share_kernel<NV2, false, 4, true>, dim3(ctas_b),
                                                    dim3(kFwWarpsPerCta * 32), 0, s, pv.cell_start, (const int32_t *)nullptr,
                                                    pv.sorted_cells, (const float *)rr, (const float *)nullptr, out, ws_head,
-                                                   ws_tail, cell_base, ncells, one, one, period_b, -1, 0)));
+                                                   ws_tail, cell_base, ncells, one, one, period_b, run_rows_capacity)));
     BEVPOOL_RETURN_IF_CUDA(le);
     BEVPOOL_LAUNCH_CHECK();
     BEVPOOL_G8_DISPATCH(channels, (le = launch_pdl_if(pdl_forward_enabled(), pool_forward_fixup_kernel<NV2>,
                                                    dim3((unsigned)ceil_div64((int64_t)slices * 8, 128)), dim3(128), 0, s,
                                                    pv.cell_start, pv.sorted_cells, (const float *)ws_head,
-                                                   (const float *)ws_tail, out, cell_base, ncells, slices)));
+                                                   (const float *)ws_tail, out, cell_base, ncells, slices, run_rows_capacity)));
     BEVPOOL_RETURN_IF_CUDA(le);
     BEVPOOL_LAUNCH_CHECK();
   }
   return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_fused_forward_runs(const void *plan, const void *depth, const void *context_nhwc,
+                                          void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
+                                          int feat_h, int feat_w, int channels, int X, int Y, void *run_rows,
+                                          int64_t run_rows_capacity, void *workspace, void *stream) {
+  return fused_forward_runs_impl(plan, depth, context_nhwc, false, out_nhwc, dtype, batch, num_cams, depth_bins, feat_h,
+                                 feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream);
+}
+
+extern "C" int bevpool_fused_forward_runs_nchw(const void *plan, const void *depth, const void *context_nchw,
+                                               void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
+                                               int feat_h, int feat_w, int channels, int X, int Y, void *run_rows,
+                                               int64_t run_rows_capacity, void *workspace, void *stream) {
+  return fused_forward_runs_impl(plan, depth, context_nchw, true, out_nhwc, dtype, batch, num_cams, depth_bins, feat_h,
+                                 feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream);
 }

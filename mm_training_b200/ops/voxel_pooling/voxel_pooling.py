@@ -45,36 +45,59 @@ class PoolingPlan:
 
     ``frustum=(N, D, H, W)`` asks for a RUN plan (fused op only): vertically adjacent points of one
     (image, depth bin, column) that share a BEV cell are sorted as one entry -- 11x fewer entries at
-    the aiMotive shape -- and ``run_code`` maps every point to its run.  ``mode`` says which kind
-    was built ('runs' needs a grid of 2^9..2^18 cells per sample, else it falls back to 'points').
-    ``max_runs``: upper bound of the run count known to the caller (e.g. from an earlier plan of the
-    same rig); without it the first fused forward reads the count back (one D2H sync)."""
+    the aiMotive shape -- and ``run_code`` maps every point to its run.  Any grid size; ``mode`` says which
+    kind was built ('runs', or 'points' when ``geom_xyz`` is not 16-byte aligned).
+    ``max_runs``: the caller's upper bound of the run count; it sizes the scratch rows of the fused forward
+    without reading the count back (no host sync: what a CUDA-graph capture needs).  It is only valid for the
+    SAME ``geom_xyz`` (or a rig known to produce no more runs): if the real count is larger the kernels stay
+    inside the scratch, the output is invalid and ``status()`` returns BEVPOOL_PLAN_ROW_OVERFLOW (1) -- call
+    ``raise_if_overflowed()`` at a point where a sync is acceptable.  Without it the first fused forward reads
+    the exact count back (one D2H sync)."""
 
-    def __init__(self, geom_xyz: torch.Tensor, voxel_num: VoxelNum, frustum: Optional[Sequence[int]] = None,
-                 max_runs: Optional[int] = None):
+    def __init__(self, geom_xyz: Optional[torch.Tensor], voxel_num: VoxelNum, frustum: Optional[Sequence[int]] = None,
+                 max_runs: Optional[int] = None, _rig=None):
+        self.voxel_num = _voxel_num_ints(voxel_num)
+        self.mode = 'points'
+        self.frustum = None
+        self._num_runs = max_runs
+        self.hinted = max_runs is not None
+        X, Y, Z = self.voxel_num
+        L = _lib.lib()
+        pb, tb = ctypes.c_size_t(), ctypes.c_size_t()
+        if _rig is not None:                       # built from the camera rig (rig.py): no geom_xyz tensor exists
+            lsg, combine, variant = _rig
+            _lib.require_cuda(combine)
+            assert combine.dtype == torch.float32 and combine.is_contiguous() and combine.shape[-2:] == (4, 4)
+            self.batch, N = int(combine.shape[0]), int(combine.shape[1])
+            D, H, W = lsg.D, lsg.H, lsg.W
+            self.num_points = N * D * H * W
+            self.device = combine.device
+            self.mode, self.frustum = 'runs', (N, D, H, W)
+            _lib.check(L.bevpool_runplan_rig_sizes(self.batch, N, D, H, W, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
+                       'bevpool_runplan_rig_sizes')
+            with torch.cuda.device(self.device):
+                self.buffer = torch.empty(pb.value, dtype=torch.uint8, device=self.device)
+                temp = torch.empty(tb.value, dtype=torch.uint8, device=self.device)
+                _lib.check(L.bevpool_runplan_build_rig(combine.data_ptr(), lsg.fx.data_ptr(), lsg.fy.data_ptr(),
+                                                       lsg.fd.data_ptr(), lsg._lower_c, lsg._vs_c, variant, self.batch,
+                                                       N, D, H, W, X, Y, Z, self.buffer.data_ptr(), temp.data_ptr(),
+                                                       _lib.stream_ptr(self.device)), 'bevpool_runplan_build_rig')
+            return
         _lib.require_cuda(geom_xyz)
         if geom_xyz.dtype != torch.int32:
             raise TypeError(f'geom_xyz must be int32 (got {geom_xyz.dtype})')
         assert geom_xyz.is_contiguous()
         assert geom_xyz.shape[-1] == 3
-        self.voxel_num = _voxel_num_ints(voxel_num)
         self.batch = int(geom_xyz.shape[0])
         self.num_points = int(geom_xyz.numel() // (3 * self.batch))
         self.device = geom_xyz.device
-        self.mode = 'points'
-        self.frustum = None
-        self._num_runs = max_runs
-        X, Y, Z = self.voxel_num
-        L = _lib.lib()
-        pb, tb = ctypes.c_size_t(), ctypes.c_size_t()
         if frustum is not None:
             N, D, H, W = (int(v) for v in frustum)
             assert N * D * H * W == self.num_points, 'frustum shape does not match geom_xyz'
-            rc = L.bevpool_runplan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb))
-            if rc == 0 and geom_xyz.data_ptr() % 16 == 0:
+            if geom_xyz.data_ptr() % 16 == 0:
+                _lib.check(L.bevpool_runplan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
+                           'bevpool_runplan_sizes')
                 self.mode, self.frustum = 'runs', (N, D, H, W)
-            elif rc != -2:
-                _lib.check(rc, 'bevpool_runplan_sizes')
         if self.mode == 'points':
             _lib.check(L.bevpool_plan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
                        'bevpool_plan_sizes')
@@ -91,6 +114,26 @@ class PoolingPlan:
                                                 self.buffer.data_ptr(), temp.data_ptr(),
                                                 _lib.stream_ptr(self.device)), 'bevpool_plan_build')
         # temp is released to the caching allocator here; stream-ordered reuse keeps this safe
+
+    @classmethod
+    def from_rig(cls, lsg, combine: torch.Tensor, variant: int, max_runs: Optional[int] = None) -> 'PoolingPlan':
+        """Run plan from ``combine = sensor2ego @ inverse(intrin)`` (B, N, 4, 4) and the frustum axes of ``lsg``
+        (``rig.LiftSplatGeometry``): the geometry / index tensors of ``lss_fpn.py:328-361,461-462`` are never made."""
+        return cls(None, lsg.voxel_num, None, max_runs, _rig=(lsg, combine, variant))
+
+    def status(self) -> int:
+        """The plan's device status word (0 = ok, 1 = run-row scratch overflow).  Synchronises the stream."""
+        v = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().bevpool_plan_status(self.ptr, ctypes.byref(v), _lib.stream_ptr(self.device)),
+                       'bevpool_plan_status')
+        return int(v.value)
+
+    def raise_if_overflowed(self) -> None:
+        if self.status() == 1:
+            raise RuntimeError(f'PoolingPlan: max_runs={self._num_runs} is smaller than the run count of this geometry '
+                               '(the hint is only valid for the geom_xyz it was measured on); the pooled output of the '
+                               'forward calls that used this plan is invalid')
 
     @property
     def ptr(self) -> int:
@@ -170,9 +213,10 @@ def runs_supported(channels: int, dtype: torch.dtype) -> bool:
 
 def _transpose(x: torch.Tensor, batch: int, rows: int, cols: int) -> torch.Tensor:
     """(batch, rows, cols) -> (batch, cols, rows) with the library's tiled transpose."""
-    out = torch.empty(batch, cols, rows, dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().bevpool_transpose(x.data_ptr(), out.data_ptr(), _lib.dtype_code(x), batch, rows, cols,
-                                            _lib.stream_ptr(x.device)), 'bevpool_transpose')
+    with torch.cuda.device(x.device):
+        out = torch.empty(batch, cols, rows, dtype=x.dtype, device=x.device)
+        _lib.check(_lib.lib().bevpool_transpose(x.data_ptr(), out.data_ptr(), _lib.dtype_code(x), batch, rows, cols,
+                                                _lib.stream_ptr(x.device)), 'bevpool_transpose')
     return out
 
 
@@ -188,10 +232,11 @@ def _grad_rows_nhwc(grad_out: torch.Tensor, plan: PoolingPlan) -> torch.Tensor:
         return nhwc
     if not grad_out.is_contiguous():
         grad_out = grad_out.contiguous()
-    rows = torch.empty(B, Y, X, C, dtype=grad_out.dtype, device=grad_out.device)
-    _lib.check(_lib.lib().bevpool_grad_rows(plan.ptr, grad_out.data_ptr(), rows.data_ptr(),
-                                            _lib.dtype_code(grad_out), B, plan.num_points, C, X, Y,
-                                            _lib.stream_ptr(grad_out.device)), 'bevpool_grad_rows')
+    with torch.cuda.device(grad_out.device):
+        rows = torch.empty(B, Y, X, C, dtype=grad_out.dtype, device=grad_out.device)
+        _lib.check(_lib.lib().bevpool_grad_rows(plan.ptr, grad_out.data_ptr(), rows.data_ptr(),
+                                                _lib.dtype_code(grad_out), B, plan.num_points, C, X, Y,
+                                                _lib.stream_ptr(grad_out.device)), 'bevpool_grad_rows')
     return rows
 
 
@@ -208,11 +253,12 @@ def pool_forward(plan: PoolingPlan, input_features: torch.Tensor) -> torch.Tenso
     X, Y, _ = plan.voxel_num
     B, C = plan.batch, input_features.shape[-1]
     assert plan.mode == 'points', 'the drop-in op sums arbitrary per-point rows: it needs a point plan'
-    out = torch.empty(B, Y, X, C, dtype=input_features.dtype, device=input_features.device)
-    ws = _forward_workspace(C, out.device)
-    _lib.check(_lib.lib().bevpool_forward(plan.ptr, input_features.data_ptr(), out.data_ptr(),
-                                          _lib.dtype_code(input_features), B, plan.num_points, C, X, Y,
-                                          ws.data_ptr(), _lib.stream_ptr(out.device)), 'bevpool_forward')
+    with torch.cuda.device(input_features.device):
+        out = torch.empty(B, Y, X, C, dtype=input_features.dtype, device=input_features.device)
+        ws = _forward_workspace(C, out.device)
+        _lib.check(_lib.lib().bevpool_forward(plan.ptr, input_features.data_ptr(), out.data_ptr(),
+                                              _lib.dtype_code(input_features), B, plan.num_points, C, X, Y,
+                                              ws.data_ptr(), _lib.stream_ptr(out.device)), 'bevpool_forward')
     return out
 
 
@@ -221,10 +267,11 @@ def pool_backward(plan: PoolingPlan, grad_output: torch.Tensor, input_shape) -> 
     X, Y, _ = plan.voxel_num
     B, C = grad_output.shape[0], grad_output.shape[1]
     rows = _grad_rows_nhwc(grad_output, plan)
-    grad_in = torch.empty(input_shape, dtype=rows.dtype, device=rows.device)
-    _lib.check(_lib.lib().bevpool_backward(plan.ptr, rows.data_ptr(), grad_in.data_ptr(),
-                                           _lib.dtype_code(rows), B, plan.num_points, C, X, Y,
-                                           _lib.stream_ptr(rows.device)), 'bevpool_backward')
+    with torch.cuda.device(rows.device):
+        grad_in = torch.empty(input_shape, dtype=rows.dtype, device=rows.device)
+        _lib.check(_lib.lib().bevpool_backward(plan.ptr, rows.data_ptr(), grad_in.data_ptr(),
+                                               _lib.dtype_code(rows), B, plan.num_points, C, X, Y,
+                                               _lib.stream_ptr(rows.device)), 'bevpool_backward')
     return grad_in
 
 
@@ -238,6 +285,14 @@ def context_rows_nhwc(context: torch.Tensor) -> torch.Tensor:
     return rows
 
 
+def _nchw_direct(context: torch.Tensor, depth: torch.Tensor) -> bool:
+    """NCHW-contiguous fp32 context whose rows are multiples of 16 bytes: the kernels read it through a TMA
+    tensor map, no layout pass."""
+    return (context.is_contiguous() and context.dtype == torch.float32 and context.shape[3] % 4 == 0
+            and context.shape[1] in RUN_CHANNELS and context.data_ptr() % 16 == 0 and depth.data_ptr() % 16 == 0
+            and os.environ.get('BEVPOOL_DISABLE_G8', '0') != '1' and os.environ.get('BEVPOOL_NCHW_DIRECT', '1') != '0')
+
+
 def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
                   context_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     """depth (B*N, D, H, W), context (B*N, C, H, W) NCHW or channels_last -> (B, Y, X, C)."""
@@ -248,26 +303,34 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
     N = BN // B
     assert context.shape == (BN, C, H, W) and depth.dtype == context.dtype
     assert B * N == BN and plan.num_points == N * D * H * W
-    ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
-    out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
-    if plan.mode == 'runs':
-        if not runs_supported(C, depth.dtype):
-            raise ValueError(f'run plans need float32 and C in {RUN_CHANNELS}; build a point plan for C={C}, {depth.dtype}')
-        assert plan.frustum == (N, D, H, W)
-        cap = max(1, plan.num_sorted)
-        run_rows = torch.empty(cap, C, dtype=torch.float32, device=depth.device)
+    with torch.cuda.device(depth.device):
+        out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
+        if plan.mode == 'runs':
+            if not runs_supported(C, depth.dtype):
+                raise ValueError(f'run plans need float32 and C in {RUN_CHANNELS}; build a point plan for C={C}, {depth.dtype}')
+            assert plan.frustum == (N, D, H, W)
+            cap = max(1, plan.num_sorted)
+            run_rows = torch.empty(cap, C, dtype=torch.float32, device=depth.device)
+            ws = _forward_workspace(C, out.device)
+            if context_rows is None and _nchw_direct(context, depth):
+                _lib.check(_lib.lib().bevpool_fused_forward_runs_nchw(
+                    plan.ptr, depth.data_ptr(), context.data_ptr(), out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
+                    C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(), _lib.stream_ptr(depth.device)),
+                    'bevpool_fused_forward_runs_nchw')
+                return out
+            ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
+            _lib.check(_lib.lib().bevpool_fused_forward_runs(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
+                                                             out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
+                                                             C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(),
+                                                             _lib.stream_ptr(depth.device)),
+                       'bevpool_fused_forward_runs')
+            return out
+        ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
         ws = _forward_workspace(C, out.device)
-        _lib.check(_lib.lib().bevpool_fused_forward_runs(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
-                                                         out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
-                                                         C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(),
-                                                         _lib.stream_ptr(depth.device)),
-                   'bevpool_fused_forward_runs')
-        return out
-    ws = _forward_workspace(C, out.device)
-    _lib.check(_lib.lib().bevpool_fused_forward(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
-                                                out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
-                                                C, X, Y, ws.data_ptr(), _lib.stream_ptr(depth.device)),
-               'bevpool_fused_forward')
+        _lib.check(_lib.lib().bevpool_fused_forward(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
+                                                    out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
+                                                    C, X, Y, ws.data_ptr(), _lib.stream_ptr(depth.device)),
+                   'bevpool_fused_forward')
     return out
 
 
@@ -275,25 +338,33 @@ def fused_backward(plan: PoolingPlan, grad_output: torch.Tensor, depth: torch.Te
                    context: torch.Tensor, context_rows: Optional[torch.Tensor] = None):
     """grad_output (B, C, Y, X), any strides -> (grad_depth, grad_context).  grad_context has the
     memory format of ``context``: channels_last in -> channels_last out (zero-copy), NCHW in ->
-    NCHW out (one tiled transpose)."""
+    NCHW out (written NCHW by the kernel through a TMA tensor map; one tiled transpose on the generic path)."""
     BN, D, H, W = depth.shape
     C = context.shape[1]
     X, Y, _ = plan.voxel_num
     B = plan.batch
     N = BN // B
-    rows = _grad_rows_nhwc(grad_output, plan)
-    channels_last = context.permute(0, 2, 3, 1).is_contiguous()
-    ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
-    grad_depth = torch.empty_like(depth)
-    grad_ctx_nhwc = torch.empty(BN, H, W, C, dtype=context.dtype, device=context.device)
-    _lib.check(_lib.lib().bevpool_fused_backward(
-        plan.ptr, rows.data_ptr(), depth.data_ptr(), ctx_nhwc.data_ptr(), grad_depth.data_ptr(),
-        grad_ctx_nhwc.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
-        _lib.stream_ptr(depth.device)), 'bevpool_fused_backward')
-    if channels_last:
-        grad_context = grad_ctx_nhwc.permute(0, 3, 1, 2)
-    else:
-        grad_context = _transpose(grad_ctx_nhwc, BN, H * W, C).view(BN, C, H, W)
+    with torch.cuda.device(depth.device):
+        rows = _grad_rows_nhwc(grad_output, plan)
+        grad_depth = torch.empty_like(depth)
+        if context_rows is None and _nchw_direct(context, depth):
+            grad_context = torch.empty_like(context)
+            _lib.check(_lib.lib().bevpool_fused_backward_nchw(
+                plan.ptr, rows.data_ptr(), depth.data_ptr(), context.data_ptr(), grad_depth.data_ptr(),
+                grad_context.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_backward_nchw')
+            return grad_depth, grad_context
+        channels_last = context.permute(0, 2, 3, 1).is_contiguous()
+        ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
+        grad_ctx_nhwc = torch.empty(BN, H, W, C, dtype=context.dtype, device=context.device)
+        _lib.check(_lib.lib().bevpool_fused_backward(
+            plan.ptr, rows.data_ptr(), depth.data_ptr(), ctx_nhwc.data_ptr(), grad_depth.data_ptr(),
+            grad_ctx_nhwc.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+            _lib.stream_ptr(depth.device)), 'bevpool_fused_backward')
+        if channels_last:
+            grad_context = grad_ctx_nhwc.permute(0, 3, 1, 2)
+        else:
+            grad_context = _transpose(grad_ctx_nhwc, BN, H * W, C).view(BN, C, H, W)
     return grad_depth, grad_context
 
 
@@ -347,15 +418,23 @@ class VoxelPoolingFused(Function):
                     frustum = tuple(geom_xyz.shape[1:5])      # (N, D, H, W): sort runs, not points
                 plan = PoolingPlan(geom_xyz, (X, Y, Z), frustum)
             assert plan.voxel_num == (X, Y, Z)
-            context_rows = context_rows_nhwc(context)
+            direct = plan.mode == 'runs' and _nchw_direct(context, depth)
+            context_rows = None if direct else context_rows_nhwc(context)
             out = fused_forward(plan, depth, context, context_rows)
         ctx.plan = plan
-        ctx.save_for_backward(depth, context, context_rows)   # the rows are reused by backward
+        ctx.direct = direct
+        if direct:
+            ctx.save_for_backward(depth, context)
+        else:
+            ctx.save_for_backward(depth, context, context_rows)   # the rows are reused by backward
         return out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, grad_out):
-        depth, context, context_rows = ctx.saved_tensors
+        if ctx.direct:
+            (depth, context), context_rows = ctx.saved_tensors, None
+        else:
+            depth, context, context_rows = ctx.saved_tensors
         with torch.cuda.device(grad_out.device):
             grad_depth, grad_context = fused_backward(ctx.plan, grad_out, depth, context, context_rows)
         return None, grad_depth, grad_context, None, None

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_abi_version_and_error_strings(L):
-    assert L.bevpool_abi_version() == 1
+    assert L.bevpool_abi_version() == 2
     assert L.bevpool_error_string(0) == b'ok'
     assert b'channel' in L.bevpool_error_string(-3)
 
