@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bevpool {
@@ -47,7 +50,17 @@ inline int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, con
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? BEVPOOL_OK : (int)cudaErrorInvalidValue;
+  if (r != CUDA_SUCCESS) {
+    static const bool debug = [] { const char *e = std::getenv("BEVPOOL_DEBUG"); return e && e[0] == '1'; }();
+    if (debug) {
+      std::fprintf(stderr, "[bevpool] cuTensorMapEncodeTiled failed (%d): base %p rank %d", (int)r, base, rank);
+      for (int i = 0; i < rank; ++i) std::fprintf(stderr, " dim%d=%llu box%d=%u", i, (unsigned long long)gd[i], i, bx[i]);
+      for (int i = 0; i + 1 < rank; ++i) std::fprintf(stderr, " stride%d=%llu", i, (unsigned long long)gs[i]);
+      std::fprintf(stderr, "\n");
+    }
+    return (int)cudaErrorInvalidValue;
+  }
+  return BEVPOOL_OK;
 }
 
 // ---- device side -------------------------------------------------------------------------------

@@ -117,33 +117,43 @@ class LiftSplatGeometry:
 
 def rig_variant(device) -> Optional[int]:
     """Accumulation-order variant of the plan kernel that reproduces the reference's (torch's) indices bit for
-    bit on ``device``, or None.  Proven once per device per process on ~1.5 M points: two frustum shapes x
-    randomised rigs (arbitrary yaw / pitch / roll, lever arms, focal lengths) + the level aiMotive rig."""
+    bit on ``device``, or None.  Proven once per device per process on ~10 M points chosen to discriminate
+    between the orders (they only differ in the last bit of a coordinate, which flips a truncated index for about
+    one point in 10^5): the shipped aiMotive frustum (depths to 206 m, 44 x 80 x 409) under randomised rigs
+    (arbitrary yaw / pitch / roll, lever arms, focal lengths) on the 0.8 m grid and on a 0.2 m grid, plus the level
+    4-camera rig.  A variant is accepted only with ZERO mismatching points; the order used by cuBLAS' batched
+    4x4 @ 4x1 product on B200 (two k-slices) is tried first."""
     device = torch.device(device)
     key = device.index if device.index is not None else torch.cuda.current_device()
     if key in _VARIANT_CACHE:
         return _VARIANT_CACHE[key]
-    from ...configs import CFG_2
+    from ...configs import CFG_2, CFG_AIM
     from ... import synthetic
     gen = torch.Generator().manual_seed(1234)
     cases = []
-    g1 = LiftSplatGeometry.from_config(CFG_2, device)
+    g_aim = LiftSplatGeometry.from_config(CFG_AIM, device)
+    s2e, k = _random_rigs(1, 2, gen)
+    cases.append((g_aim, s2e.to(device), k.to(device)))
+    g_fine = LiftSplatGeometry((-204.8, 204.8, 0.2), (-25.6, 25.6, 0.2), (-5.0, 3.0, 8.0), CFG_AIM.d_bound, CFG_AIM.final_dim,
+                               CFG_AIM.downsample_factor, device)
+    s2e, k = _random_rigs(1, 1, gen)
+    cases.append((g_fine, s2e.to(device), k.to(device)))
+    g2 = LiftSplatGeometry.from_config(CFG_2, device)
     s2e, k = _random_rigs(2, 4, gen)
-    cases.append((g1, s2e.to(device), k.to(device)))
+    cases.append((g2, s2e.to(device), k.to(device)))
     kk = torch.eye(4)
     kk[0, 0] = kk[1, 1] = CFG_2.focal_px
     kk[0, 2], kk[1, 2] = CFG_2.final_dim[1] / 2, CFG_2.final_dim[0] / 2
     level = torch.stack([synthetic.cam2ego(y + 1.7) for y in CFG_2.cam_yaws_deg])[None]
-    cases.append((g1, level.to(device), kk[None, None].repeat(1, 4, 1, 1).to(device)))
-    g2 = LiftSplatGeometry((-51.2, 51.2, 0.4), (-51.2, 51.2, 0.4), (-5.0, 3.0, 8.0), (2.0, 58.0, 0.5), (256, 704), 16, device)
-    s2e, k = _random_rigs(1, 3, gen)
-    cases.append((g2, s2e.to(device), k.to(device)))
+    cases.append((g2, level.to(device), kk[None, None].repeat(1, 4, 1, 1).to(device)))
     refs = [(g, g.combine(a, b), g.geom_xyz(a, b)) for g, a, b in cases]
     found = None
-    for v in range(_lib.lib().bevpool_rig_num_variants()):
+    order = [2] + [v for v in range(_lib.lib().bevpool_rig_num_variants()) if v != 2]
+    for v in order:
         if all(torch.equal(g.rig_geom(cmb, v), ref) for g, cmb, ref in refs):
             found = v
             break
+    del refs
     _VARIANT_CACHE[key] = found
     return found
 

@@ -1,7 +1,12 @@
 """Which accumulation order of the rig plan kernel reproduces torch's geometry on this device?
 Prints, per variant, the number of points whose (x, y, z) cell index differs from mm_training_b200.geometry
 computed by torch on the GPU and on the CPU (run on the GPU box)."""
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mm_training_b200 import _lib, synthetic
 from mm_training_b200.configs import CFG_2, CFG_AIM
 from mm_training_b200.ops.voxel_pooling.rig import LiftSplatGeometry, _random_rigs
