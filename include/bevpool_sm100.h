@@ -121,8 +121,8 @@ int bevpool_fused_backward(const void *plan, const void *grad_out_nhwc, const vo
  * consecutive samples (default: all) -- the total run count cell_start[B*X*Y] always suffices.
  * workspace: bevpool_forward_workspace_bytes(channels) bytes, as for the other forward entry points.
  * The backward entry points above accept a run plan unchanged (they only read cell_of_point).   */
-int bevpool_runplan_sizes(int batch, int64_t num_points, int num_voxel_x, int num_voxel_y,
-                          size_t *plan_bytes, size_t *temp_bytes);
+int bevpool_runplan_sizes(int batch, int num_cams, int depth_bins, int feat_h, int feat_w, int num_voxel_x,
+                          int num_voxel_y, size_t *plan_bytes, size_t *temp_bytes);
 int bevpool_runplan_build(const int32_t *geom_xyz, int batch, int num_cams, int depth_bins, int feat_h,
                           int feat_w, int num_voxel_x, int num_voxel_y, int num_voxel_z, void *plan,
                           void *temp, void *stream);
@@ -130,6 +130,12 @@ int bevpool_runplan_views(const void *plan, int batch, int64_t num_points, int n
                           int num_voxel_y, const int32_t **cell_of_point, const int32_t **cell_start,
                           const int32_t **sorted_ids, const int32_t **sorted_cells,
                           const int32_t **run_code);
+/* pair records of a run plan: int32x4 per (sample, image, depth bin, 16-row block, column), in that order --
+ * {in-sample cell of the pair's first kept row or -1, rows in that cell (bits 0..15) | kept rows elsewhere (bits
+ * 16..31), slot of the run starting at the first kept row, number of runs in the pair}.  The fused kernels read
+ * these 16 bytes per 16 points instead of cell_of_point / run_code wherever a pair holds a single run.          */
+int bevpool_runplan_pair_records(const void *plan, int batch, int64_t num_points, int num_voxel_x,
+                                 int num_voxel_y, const void **pair_rec);
 int bevpool_fused_forward_runs(const void *plan, const void *depth, const void *context_nhwc,
                                void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
                                int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
@@ -145,8 +151,10 @@ int bevpool_fused_forward_runs_nchw(const void *plan, const void *depth, const v
                                     void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
                                     int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
                                     void *run_rows, int64_t run_rows_capacity, void *workspace, void *stream);
-int bevpool_fused_backward_nchw(const void *plan, const void *grad_out_nhwc, const void *depth,
-                                const void *context_nchw, void *grad_depth, void *grad_context_nchw,
+/* backward on a RUN plan (pair records): context / grad_context as pixel rows (B*N, H, W, C) or, with
+ * context_is_nchw != 0, as (B*N, C, H, W).  bevpool_fused_backward above accepts any plan (point plans included). */
+int bevpool_fused_backward_runs(const void *plan, const void *grad_out_nhwc, const void *depth,
+                                const void *context, void *grad_depth, void *grad_context, int context_is_nchw,
                                 int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
                                 int channels, int num_voxel_x, int num_voxel_y, void *stream);
 

@@ -143,7 +143,7 @@ __device__ __forceinline__ uint32_t fastdiv(uint32_t n, const FastDiv &f) {
 // sorted_cells[k] its global output row b*G + cell; only the first K = cell_start[B*G] entries
 // of both are defined.
 struct PlanLayout {
-  size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, off_run_code, bytes;
+  size_t off_cell_of_point, off_cell_start, off_sorted_ids, off_sorted_cells, off_run_code, off_pair_rec, bytes;
 };
 struct PlanHeader {       // first 256 bytes of a plan buffer, written by the builders (one thread of the key kernel)
   int32_t magic, kind, status, batch, num_voxel_x, num_voxel_y, num_voxel_z, reserved;
@@ -163,7 +163,17 @@ constexpr int32_t kPlanMagic = 0x42455631;  // "BEV1"
 constexpr int kRunHB = 16;
 constexpr int32_t kRunDropped = -1, kRunCont = -2;
 
-__host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points, int X, int Y, bool runs = false) {
+// Run plans also carry one PAIR RECORD per (image, depth bin, 16-row block, column) -- int4 {primary cell, masks,
+// primary slot, number of runs}: the in-sample cell of the pair's first kept row (-1: nothing kept), the rows lying
+// in that cell (bits 0..15) and the kept rows lying elsewhere (bits 16..31), the slot of the run that starts at the
+// first kept row, and how many runs the pair holds.  For a level camera (one run per pair) the record is all the
+// fused kernels need per pair: they read 16 bytes per 16 points instead of cell_of_point / run_code (128 bytes)
+// and do no per-row voting; pairs with stray rows fall back to the per-point arrays.
+__host__ __device__ inline int64_t plan_num_pairs(int num_cams, int D, int H, int W) {
+  return (int64_t)num_cams * D * ((H + kRunHB - 1) / kRunHB) * W;
+}
+__host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points, int X, int Y, bool runs = false,
+                                                  int64_t pairs_per_sample = 0) {
   PlanLayout L;
   const size_t P = (size_t)batch * (size_t)num_points;
   const size_t G = (size_t)batch * (size_t)X * (size_t)Y;
@@ -174,12 +184,15 @@ __host__ __device__ inline PlanLayout plan_layout(int batch, int64_t num_points,
   L.off_sorted_cells = o;  o = align_up(o + P * 4 + 64, 256);   // + slack: readers prefetch a batch past K
   L.off_run_code = o;
   if (runs) o = align_up(o + P * 4, 256);
+  L.off_pair_rec = align_up(L.off_run_code + P * 4, 256);       // (run plans only; position independent of its size)
+  if (runs) o = align_up(L.off_pair_rec + (size_t)batch * (size_t)pairs_per_sample * 16, 256);
   L.bytes = o;
   return L;
 }
 
 struct PlanView {
   const int32_t *cell_of_point, *cell_start, *sorted_ids, *sorted_cells, *run_code;
+  const int4 *pair_rec;
 };
 inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X, int Y) {
   PlanLayout L = plan_layout(batch, num_points, X, Y);
@@ -188,12 +201,13 @@ inline PlanView plan_view(const void *plan, int batch, int64_t num_points, int X
                   reinterpret_cast<const int32_t *>(b + L.off_cell_start),
                   reinterpret_cast<const int32_t *>(b + L.off_sorted_ids),
                   reinterpret_cast<const int32_t *>(b + L.off_sorted_cells),
-                  reinterpret_cast<const int32_t *>(b + L.off_run_code)};
+                  reinterpret_cast<const int32_t *>(b + L.off_run_code),
+                  reinterpret_cast<const int4 *>(b + L.off_pair_rec)};
 }
 
 // pool_bwd2.cu: column kernel of the fused backward (fp32, g8 channel counts, W % 4 == 0); reads context and writes
 // the context gradient either as pixel rows (B*N, H, W, C) or, through TMA tensor maps, as NCHW (B*N, C, H, W)
-int launch_fused_backward_col(const int32_t *cell_of_point, const float *grad_rows, const float *depth,
+int launch_fused_backward_col(const int32_t *cell_of_point, const int4 *pair_rec, const float *grad_rows, const float *depth,
                               const float *ctx, float *grad_depth, float *grad_ctx, bool nchw, int batch, int num_cams,
                               int D, int H, int W, int C, int64_t cells_per_sample, cudaStream_t s);
 bool fused_backward_col_supported(int C, int W, const void *depth, const void *grad_depth, const void *cell_of_point);

@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(kRigThreads)
 plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int X, int Y, int Z, int64_t num_points,
                     int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code, uint32_t *__restrict__ counts,
                     int32_t *__restrict__ head_cells, int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
-                    uint32_t *__restrict__ sample_total, int warps_per_sample, int slot_cap, PlanHeader *hdr, PlanHeader hv) {
+                    uint32_t *__restrict__ sample_total, int warps_per_sample, int slot_cap, int4 *__restrict__ pair_rec,
+                    PlanHeader *hdr, PlanHeader hv) {
   pdl_wait();
   pdl_trigger();
   const int b = blockIdx.y;
@@ -532,7 +533,8 @@ plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int
   const int64_t col_base = (int64_t)b * num_points + ((int64_t)n * D + d) * H * W + w;
   const unsigned lt = (1u << lane) - 1u;
   uint32_t filled = 0;                 // heads this warp has written so far (warp-uniform)
-  int prev = -2;
+  int prev = -2, primary = -1, nheads = 0;
+  uint32_t fastm = 0u, keptm = 0u;
 #pragma unroll 4
   for (int r = 0; r < kRunHB; ++r) {
     const int h = hb * kRunHB + r;
@@ -549,6 +551,12 @@ plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int
       const int64_t gp = col_base + (int64_t)h * W;
       cell_of_point[gp] = cell;
       run_code[gp] = code;          // heads: overwritten with their slot by K4
+      if (cell >= 0) {
+        if (primary < 0) primary = cell;
+        keptm |= 1u << r;
+        if (cell == primary) fastm |= 1u << r;
+        nheads += code >= 0;
+      }
     }
     const bool head = code >= 0;
     const unsigned bal = __ballot_sync(0xffffffffu, head);
@@ -560,6 +568,7 @@ plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int
     }
     filled += __popc(bal);
   }
+  if (valid) pair_rec[(int64_t)b * pairs + q] = make_int4(primary, (int)(fastm | ((keptm & ~fastm) << 16)), -1, nheads);
   __shared__ uint32_t s_cta_total;
   if (threadIdx.x == 0) s_cta_total = 0u;
   __syncthreads();
@@ -590,6 +599,40 @@ rig_geom_kernel(RigParams rp, int num_cams, int D, int H, int W, int64_t total, 
   geom[gp * 3 + 0] = rig_quantise(rig_dot4<kVariant>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
   geom[gp * 3 + 1] = rig_quantise(rig_dot4<kVariant>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
   geom[gp * 3 + 2] = rig_quantise(rig_dot4<kVariant>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
+}
+
+// Pair records of a plan built from geom_xyz: one thread per (image, bin, 16-row block, column), walking the rows
+// of cell_of_point / run_code that K1 wrote (lanes = consecutive columns: coalesced).  Runs before K4, which adds
+// the primary slot.
+__global__ void __launch_bounds__(256)
+pair_records_kernel(const int32_t *__restrict__ cell_of_point, const int32_t *__restrict__ run_code, int num_cams, int D,
+                    int H, int W, int HB, int64_t num_points, int4 *__restrict__ pair_rec) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.y;
+  const int64_t pairs = (int64_t)num_cams * D * HB * W;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= pairs) return;
+  int64_t t = q;
+  const int w = (int)(t % W); t /= W;
+  const int hb = (int)(t % HB); t /= HB;             // t = n * D + d
+  const int64_t col_base = (int64_t)b * num_points + t * H * W + w;
+  int primary = -1, nheads = 0;
+  uint32_t fastm = 0u, keptm = 0u;
+#pragma unroll 4
+  for (int r = 0; r < kRunHB; ++r) {
+    const int h = hb * kRunHB + r;
+    if (h >= H) break;
+    const int64_t gp = col_base + (int64_t)h * W;
+    const int cell = __ldg(cell_of_point + gp);
+    if (cell >= 0) {
+      if (primary < 0) primary = cell;
+      keptm |= 1u << r;
+      if (cell == primary) fastm |= 1u << r;
+      nheads += __ldg(run_code + gp) >= 0;           // head codes are >= 0 both before and after K4
+    }
+  }
+  pair_rec[(int64_t)b * pairs + q] = make_int4(primary, (int)(fastm | ((keptm & ~fastm) << 16)), -1, nheads);
 }
 
 // K2: exclusive scan of the per-cell run counts, one independent look-back chain per SAMPLE (a single
@@ -731,11 +774,29 @@ run_place_kernel(const int32_t *__restrict__ head_cells, const int32_t *__restri
 // (none for camera rigs: the aiMotive shapes peak at 54 runs per cell) are queued for K5 by the thread
 // that holds the segment's first entry, so no thread ever walks a long segment.
 constexpr uint32_t kRunSmallCell = 64;
+
+struct PairDims {            // how a global point id decomposes into (sample, image*bin, row, column)
+  FastDiv div_w, div_h, div_np;
+  int HB, W;
+  int64_t pairs_per_sample;
+};
+// head point `id` got `slot`: if it is the first kept row of its pair, record the slot there
+__device__ __forceinline__ void record_primary_slot(int4 *__restrict__ pair_rec, const PairDims &pd, int32_t id, int32_t slot) {
+  const uint32_t b = fastdiv((uint32_t)id, pd.div_np);
+  const uint32_t p = (uint32_t)id - b * pd.div_np.div;          // point inside the sample
+  const uint32_t rowi = fastdiv(p, pd.div_w);                   // (n*D + d) * H + h
+  const uint32_t w = p - rowi * pd.div_w.div;
+  const uint32_t nd = fastdiv(rowi, pd.div_h);
+  const uint32_t h = rowi - nd * pd.div_h.div;
+  const int64_t q = (int64_t)b * pd.pairs_per_sample + ((int64_t)nd * pd.HB + h / kRunHB) * pd.W + w;
+  const uint32_t masks = (uint32_t)pair_rec[q].y;
+  if ((masks & 0xffffu) && (uint32_t)(__ffs(masks & 0xffffu) - 1) == (h % kRunHB)) pair_rec[q].z = slot;
+}
 __global__ void __launch_bounds__(256)
 run_finish_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__restrict__ placed_ids,
                   const int32_t *__restrict__ placed_cells, int64_t total_cells, int32_t *__restrict__ sorted_ids,
                   int32_t *__restrict__ sorted_cells, int32_t *__restrict__ run_code, int32_t *__restrict__ big_list,
-                  uint32_t *__restrict__ big_count) {
+                  uint32_t *__restrict__ big_count, int4 *__restrict__ pair_rec, PairDims pd) {
   pdl_wait();
   pdl_trigger();
   const uint32_t total = cell_start[total_cells];
@@ -752,6 +813,7 @@ run_finish_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__rest
     sorted_ids[s + rank] = id;
     sorted_cells[s + rank] = gc;
     run_code[id] = (int32_t)(s + rank);
+    record_primary_slot(pair_rec, pd, id, (int32_t)(s + rank));
   }
 }
 
@@ -760,7 +822,7 @@ __global__ void __launch_bounds__(256)
 run_finish_big_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__restrict__ placed_ids,
                       const int32_t *__restrict__ big_list, const uint32_t *__restrict__ big_count,
                       int32_t *__restrict__ sorted_ids, int32_t *__restrict__ sorted_cells,
-                      int32_t *__restrict__ run_code) {
+                      int32_t *__restrict__ run_code, int4 *__restrict__ pair_rec, PairDims pd) {
   pdl_wait();
   pdl_trigger();
   constexpr int kTile = 2048;
@@ -784,6 +846,7 @@ run_finish_big_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__
         sorted_ids[s + rank] = id;
         sorted_cells[s + rank] = (int32_t)gc;
         run_code[id] = (int32_t)(s + rank);
+        record_primary_slot(pair_rec, pd, id, (int32_t)(s + rank));
       }
     }
   }
@@ -1062,12 +1125,14 @@ static RunTempLayout run_temp_layout_rig(int batch, int N, int D, int H, int W, 
                          32 * (H < kRunHB ? H : kRunHB));
 }
 
-extern "C" int bevpool_runplan_sizes(int batch, int64_t num_points, int X, int Y, size_t *plan_bytes,
-                                     size_t *temp_bytes) {
+extern "C" int bevpool_runplan_sizes(int batch, int num_cams, int depth_bins, int feat_h, int feat_w, int X, int Y,
+                                     size_t *plan_bytes, size_t *temp_bytes) {
+  if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  const int64_t num_points = (int64_t)num_cams * depth_bins * feat_h * feat_w;
   int rc = check_plan_dims(batch, num_points, X, Y);
   if (rc) return rc;
   if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
-  *plan_bytes = plan_layout(batch, num_points, X, Y, true).bytes;
+  *plan_bytes = plan_layout(batch, num_points, X, Y, true, plan_num_pairs(num_cams, depth_bins, feat_h, feat_w)).bytes;
   *temp_bytes = run_temp_layout_geom(batch, num_points, X, Y).bytes;
   return BEVPOOL_OK;
 }
@@ -1079,15 +1144,23 @@ extern "C" int bevpool_runplan_rig_sizes(int batch, int num_cams, int depth_bins
   int rc = check_plan_dims(batch, num_points, X, Y);
   if (rc) return rc;
   if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
-  *plan_bytes = plan_layout(batch, num_points, X, Y, true).bytes;
+  *plan_bytes = plan_layout(batch, num_points, X, Y, true, plan_num_pairs(num_cams, depth_bins, feat_h, feat_w)).bytes;
   *temp_bytes = run_temp_layout_rig(batch, num_cams, depth_bins, feat_h, feat_w, X, Y).bytes;
   return BEVPOOL_OK;
 }
 
 // K2..K5 of a run plan: per-cell run counts + per-warp head lists (K1's output) -> CSR, sorted run list, slots
-static int run_plan_finish(const RunTempLayout &TL, const PlanLayout &PL, int batch, int64_t cells, char *pb, char *tb,
-                           cudaStream_t stream) {
+static int run_plan_finish(const RunTempLayout &TL, const PlanLayout &PL, int batch, int64_t cells, int num_cams, int D,
+                           int H, int W, char *pb, char *tb, cudaStream_t stream) {
   const int64_t total_cells = (int64_t)batch * cells;
+  int4 *pair_rec = reinterpret_cast<int4 *>(pb + PL.off_pair_rec);
+  PairDims pd;
+  pd.div_w = make_fastdiv((uint32_t)W);
+  pd.div_h = make_fastdiv((uint32_t)H);
+  pd.div_np = make_fastdiv((uint32_t)((int64_t)num_cams * D * H * W));
+  pd.HB = (H + kRunHB - 1) / kRunHB;
+  pd.W = W;
+  pd.pairs_per_sample = plan_num_pairs(num_cams, D, H, W);
   uint32_t *cell_start = reinterpret_cast<uint32_t *>(pb + PL.off_cell_start);
   int32_t *sorted_ids = reinterpret_cast<int32_t *>(pb + PL.off_sorted_ids);
   int32_t *sorted_cells = reinterpret_cast<int32_t *>(pb + PL.off_sorted_cells);
@@ -1117,10 +1190,10 @@ static int run_plan_finish(const RunTempLayout &TL, const PlanLayout &PL, int ba
   int32_t *big_list = reinterpret_cast<int32_t *>(tb + TL.off_big_list);
   uint32_t *big_count = reinterpret_cast<uint32_t *>(tb + TL.off_big_count);
   BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_kernel, dim3(kSMs * 8), dim3(256), 0, stream,
-      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count));
+      cell_start, placed, placed_cells, total_cells, sorted_ids, sorted_cells, run_code, big_list, big_count, pair_rec, pd));
   BEVPOOL_LAUNCH_CHECK();
   BEVPOOL_RETURN_IF_CUDA(launch_pdl(run_finish_big_kernel, dim3(kSMs * 2), dim3(256), 0, stream,
-                                    cell_start, placed, big_list, big_count, sorted_ids, sorted_cells, run_code));
+                                    cell_start, placed, big_list, big_count, sorted_ids, sorted_cells, run_code, pair_rec, pd));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -1136,7 +1209,8 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
   if (batch > 65535) return BEVPOOL_E_RANGE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t cells = (int64_t)X * Y;
-  const PlanLayout PL = plan_layout(batch, num_points, X, Y, true);
+  const int64_t pairs = plan_num_pairs(num_cams, depth_bins, feat_h, feat_w);
+  const PlanLayout PL = plan_layout(batch, num_points, X, Y, true, pairs);
   const RunTempLayout TL = run_temp_layout_geom(batch, num_points, X, Y);
   char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
   const int T = (int)ceil_div64(num_points, kSortTile);
@@ -1149,7 +1223,12 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
       make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h), static_cast<PlanHeader *>(plan),
       make_plan_header(kPlanKindRuns, batch, num_points, X, Y, Z)));
   BEVPOOL_LAUNCH_CHECK();
-  return run_plan_finish(TL, PL, batch, cells, pb, tb, stream);
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(pair_records_kernel, dim3((unsigned)ceil_div64(pairs, 256), (unsigned)batch), dim3(256), 0, stream,
+      (const int32_t *)reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
+      (const int32_t *)reinterpret_cast<int32_t *>(pb + PL.off_run_code), num_cams, depth_bins, feat_h, feat_w,
+      (int)ceil_div64(feat_h, kRunHB), num_points, reinterpret_cast<int4 *>(pb + PL.off_pair_rec)));
+  BEVPOOL_LAUNCH_CHECK();
+  return run_plan_finish(TL, PL, batch, cells, num_cams, depth_bins, feat_h, feat_w, pb, tb, stream);
 }
 
 constexpr int kRigVariants = 6;
@@ -1195,7 +1274,7 @@ extern "C" int bevpool_runplan_build_rig(const float *combine, const float *frus
   if ((rc = make_rig_params(&rp, combine, frustum_x, frustum_y, frustum_d, lower_host, voxel_size_host))) return rc;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t cells = (int64_t)X * Y;
-  const PlanLayout PL = plan_layout(batch, num_points, X, Y, true);
+  const PlanLayout PL = plan_layout(batch, num_points, X, Y, true, plan_num_pairs(num_cams, depth_bins, feat_h, feat_w));
   const RunTempLayout TL = run_temp_layout_rig(batch, num_cams, depth_bins, feat_h, feat_w, X, Y);
   char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
   const int HB = (int)ceil_div64(feat_h, kRunHB);
@@ -1208,11 +1287,11 @@ extern "C" int bevpool_runplan_build_rig(const float *combine, const float *frus
       reinterpret_cast<int32_t *>(pb + PL.off_run_code), reinterpret_cast<uint32_t *>(tb + TL.off_counts),
       reinterpret_cast<int32_t *>(tb + TL.off_head_cells), reinterpret_cast<int32_t *>(tb + TL.off_head_ids),
       reinterpret_cast<int32_t *>(tb + TL.off_warp_count), reinterpret_cast<uint32_t *>(tb + TL.off_sample_total),
-      TL.slices_per_sample, TL.slot_cap, static_cast<PlanHeader *>(plan),
+      TL.slices_per_sample, TL.slot_cap, reinterpret_cast<int4 *>(pb + PL.off_pair_rec), static_cast<PlanHeader *>(plan),
       make_plan_header(kPlanKindRuns, batch, num_points, X, Y, Z))));
   BEVPOOL_RETURN_IF_CUDA(le);
   BEVPOOL_LAUNCH_CHECK();
-  return run_plan_finish(TL, PL, batch, cells, pb, tb, stream);
+  return run_plan_finish(TL, PL, batch, cells, num_cams, depth_bins, feat_h, feat_w, pb, tb, stream);
 }
 
 extern "C" int bevpool_rig_geom(const float *combine, const float *frustum_x, const float *frustum_y,
@@ -1257,6 +1336,15 @@ extern "C" int bevpool_runplan_views(const void *plan, int batch, int64_t num_po
   if (sorted_ids) *sorted_ids = v.sorted_ids;
   if (sorted_cells) *sorted_cells = v.sorted_cells;
   if (run_code) *run_code = v.run_code;
+  return BEVPOOL_OK;
+}
+
+extern "C" int bevpool_runplan_pair_records(const void *plan, int batch, int64_t num_points, int X, int Y,
+                                            const void **pair_rec) {
+  int rc = check_plan_dims(batch, num_points, X, Y);
+  if (rc) return rc;
+  if (!plan || !pair_rec) return BEVPOOL_E_ARG;
+  *pair_rec = plan_view(plan, batch, num_points, X, Y).pair_rec;
   return BEVPOOL_OK;
 }
 

@@ -577,25 +577,26 @@ static int fused_forward_t(const void *plan, const void *depth, const void *ctx,
 template <typename T>
 static int fused_backward_t(const void *plan, const void *grad, const void *depth, const void *ctx,
                             void *gdepth, void *gctx, int B, int N, int D, int H, int W, int C, int X,
-                            int Y, cudaStream_t s, bool nchw = false) {
+                            int Y, cudaStream_t s, bool nchw = false, bool runs = false) {
   const int64_t Np = (int64_t)N * D * H * W;
   const PlanView pv = plan_view(plan, B, Np, X, Y);
   const int C4 = C >> 2;
   (void)nchw;
+  (void)runs;
   const T *g = static_cast<const T *>(grad), *dp = static_cast<const T *>(depth), *cx = static_cast<const T *>(ctx);
   T *gd = static_cast<T *>(gdepth), *gc = static_cast<T *>(gctx);
   const int64_t cells = (int64_t)X * Y;
   if constexpr (std::is_same<T, float>::value) {
     if (g8_supported(C) && g8_enabled()) {
-      // 2: column kernel (pool_bwd2.cu; needs W % 4 == 0), 1: tile kernel (pool_bwd.cu; any W, C <= 96)
+      // run plans (pair records): column kernel (pool_bwd2.cu; needs W % 4 == 0); else tile kernel (pool_bwd.cu; C <= 96)
       static const int which = env_int("BEVPOOL_BW_KERNEL", 2);
-      if (which == 2 && fused_backward_col_supported(C, W, dp, gd, pv.cell_of_point))
-        return launch_fused_backward_col(pv.cell_of_point, g, dp, cx, gd, gc, nchw, B, N, D, H, W, C, cells, s);
+      if (runs && which == 2 && fused_backward_col_supported(C, W, dp, gd, pv.cell_of_point))
+        return launch_fused_backward_col(pv.cell_of_point, pv.pair_rec, g, dp, cx, gd, gc, nchw, B, N, D, H, W, C, cells, s);
       if (!nchw && fused_backward_tile_supported(C))
         return launch_fused_backward_tile(pv.cell_of_point, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
     }
   }
-  if (nchw) return BEVPOOL_E_CHANNELS;      // the NCHW entry point exists only on the column kernel
+  if (nchw) return BEVPOOL_E_CHANNELS;      // the NCHW layout exists only on the column kernel
   if (C4 <= 32) return launch_fused_backward_cpl<T, 1>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
   if (C4 <= 64) return launch_fused_backward_cpl<T, 2>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
   return launch_fused_backward_cpl<T, 4>(pv, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
@@ -673,22 +674,22 @@ extern "C" int bevpool_fused_backward(const void *plan, const void *grad_out_nhw
   BEVPOOL_DISPATCH_DTYPE(dtype, (fused_backward_t<T>(plan, grad_out_nhwc, depth, context_nhwc, grad_depth, grad_context_nhwc, batch, num_cams, depth_bins, feat_h, feat_w, channels, X, Y, s)));
 }
 
-extern "C" int bevpool_fused_backward_nchw(const void *plan, const void *grad_out_nhwc, const void *depth,
-                                           const void *context_nchw, void *grad_depth, void *grad_context_nchw,
-                                           int dtype, int batch, int num_cams, int depth_bins, int feat_h,
-                                           int feat_w, int channels, int X, int Y, void *stream) {
+extern "C" int bevpool_fused_backward_runs(const void *plan, const void *grad_out_nhwc, const void *depth,
+                                           const void *context, void *grad_depth, void *grad_context,
+                                           int context_is_nchw, int dtype, int batch, int num_cams, int depth_bins,
+                                           int feat_h, int feat_w, int channels, int X, int Y, void *stream) {
   if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
   const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
   int rc = check_plan_dims(batch, np, X, Y);
   if (rc) return rc;
   if (dtype != BEVPOOL_F32) return BEVPOOL_E_DTYPE;
   if (!g8_supported(channels)) return BEVPOOL_E_CHANNELS;
-  if (!plan || !grad_out_nhwc || !depth || !context_nchw || !grad_depth || !grad_context_nchw) return BEVPOOL_E_ARG;
-  if (!aligned16(grad_out_nhwc) || !aligned16(context_nchw) || !aligned16(grad_context_nchw) || (feat_w % 4) != 0 ||
-      !aligned16(depth) || !aligned16(grad_depth))
-    return BEVPOOL_E_ALIGN;
-  return fused_backward_t<float>(plan, grad_out_nhwc, depth, context_nchw, grad_depth, grad_context_nchw, batch, num_cams,
-                                 depth_bins, feat_h, feat_w, channels, X, Y, static_cast<cudaStream_t>(stream), true);
+  if (!plan || !grad_out_nhwc || !depth || !context || !grad_depth || !grad_context) return BEVPOOL_E_ARG;
+  if (!aligned16(grad_out_nhwc) || !aligned16(context) || !aligned16(grad_context)) return BEVPOOL_E_ALIGN;
+  if (context_is_nchw && ((feat_w % 4) != 0 || !aligned16(depth) || !aligned16(grad_depth))) return BEVPOOL_E_ALIGN;
+  return fused_backward_t<float>(plan, grad_out_nhwc, depth, context, grad_depth, grad_context, batch, num_cams,
+                                 depth_bins, feat_h, feat_w, channels, X, Y, static_cast<cudaStream_t>(stream),
+                                 context_is_nchw != 0, true);
 }
 
 extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nhwc, int dtype,

@@ -7,26 +7,28 @@
 // ascending-d order (bit-stable).
 //
 // Why a second kernel (ncu of fused_backward_tile_kernel, profiles/r01zz_ncu_kernels.txt): that kernel is
-// bound by instruction issue, not by HBM -- 81 M warp instructions per 32 frames of which 12 M are FFMA2,
-// 117 registers, 24 % occupancy, 46 % issue utilisation.  A lane there owns ONE pixel x C/4 channels, so
-// every gradient-row quarter it reads from shared memory (5 LDS.128) feeds only 20 FFMA2, and the per-bin
-// bookkeeping (scalar fetches, find-first-set walk, two-step shuffle reduction) is paid per 8 pixels.
-// Here
+// bound by instruction issue and dependent-instruction latency, not by HBM -- 81 M warp instructions per 32
+// frames of which 12 M are FFMA2, 117 registers, 24 % occupancy.  A lane there owns ONE pixel x C/4 channels, so
+// every gradient-row quarter it reads from shared memory (5 LDS.128) feeds only 20 FFMA2, the per-bin
+// bookkeeping (scalar fetches, find-first-set walk, shuffle reduction) is paid per 8 pixels, and every chunk
+// starts with 8 ballots + 8 shuffles per thread to find the primary cells.  Here
+//  * the per-pair bookkeeping comes from the PLAN: one 16-byte pair record per (bin, column) -- primary cell,
+//    mask of the rows in it, mask of kept rows elsewhere (common.cuh) -- instead of 16 rows of cell_of_point and
+//    a vote; the staging threads only transpose the depths;
 //  * warp = one image column x all 16 rows; lane = (4 consecutive rows, channel eighth): a gradient-row
 //    eighth (2 LDS.128 + 1 LDS.64 at C = 80, the same addresses for the four row groups = one wavefront
-//    each) feeds 40 FFMA2, and the per-bin bookkeeping is paid per 16 pixels;
-//  * the four dot products a lane holds are reduced over the 8 lanes of its group with a transposing
-//    butterfly: 4 shuffles per (bin, column) instead of 2 x 2 per half column;
-//  * the depth values arrive transposed ([bin][column][row]: one LDS.128 per lane) together with a 16-bit
-//    "rows in the primary cell" mask per (bin, column), both produced by the staging threads while they
-//    look for the primary cells, so the reduction loop has no per-row scalar fetches and no bit scans;
-//  * 128-thread CTAs, 3 per SM: latency is hidden by the 40 independent FFMA2 per bin rather than by
-//    occupancy;
+//    each) feeds 40 FFMA2, and the depths arrive transposed ([bin][column][row]: one LDS.128 per lane);
+//  * the cross-lane half of the dot products is taken out of the FMA loop: a lane parks its four partial
+//    sums in shared memory (one STS.128 per bin) and, once per 4 bins, the warp sums them with independent
+//    LDS.128 + FADD and a single exchange (phase B) -- no dependent shuffle chain per bin, so the FFMA2 of
+//    consecutive bins overlap;
+//  * 128-thread CTAs, 3 per SM;
 //  * context is read from the caller's NCHW tensor and the context gradient written back NCHW through
 //    TMA tensor maps (cp.async.bulk.tensor, boxes of 4 columns x 16 rows x C channels): the two layout
 //    passes (bevpool_transpose, 15 us each per 32 frames) are gone.
 // Correct for any geometry: rows of a (bin, column) that do not fall into its primary cell (tilted
-// cameras, random geometry) take a per-row path that gathers their gradient row from global memory.
+// cameras, random geometry) gather their own gradient row from global memory (their cell comes from
+// cell_of_point).  Needs a RUN plan (pair records).
 #include "common.cuh"
 #include "pool_g8.cuh"
 #include "tma.cuh"
@@ -34,46 +36,57 @@
 namespace bevpool {
 
 constexpr int kBcTW = 4;                            // image columns per CTA = warps per CTA
-constexpr int kBcTH = 16;                           // image rows per CTA
+constexpr int kBcTH = 16;                           // image rows per CTA = one 16-row block of the plan's pair records
 constexpr int kBcDC = 16;                           // depth bins per chunk
+constexpr int kBcMC = 4;                            // depth bins per mini-chunk (partial dot products parked in shared memory)
 constexpr int kBcThreads = 32 * kBcTW;
 constexpr int kBcDepStride = kBcTW * kBcTH + 16;    // floats per bin of the transposed depth stage (+16: the two
                                                     // half-warps of a staging warp hit disjoint banks)
+constexpr int kBcPartStride = 36;                   // floats per (bin, row group) of the partial-dot buffer: 8 lanes x 4
+                                                    // rows + 4 of padding, so the 8 groups a quarter-warp reads differ in bank
+static_assert(kBcTH == kRunHB, "the backward tile is one row block of the plan");
 
 template <int NV2>
 struct BcSmem {
   static constexpr int C = 16 * NV2;
   static constexpr size_t kRowFloats = (size_t)kBcDC * kBcTW * C;                  // one stage of gradient rows
   static constexpr size_t off_g = 0;                                                  // [2][bin][column][channel]; also the context / context-gradient TMA box
-  static constexpr size_t off_cell = off_g + 2 * kRowFloats * 4;                      // int4   [2][bin][row]   (4 columns)
-  static constexpr size_t off_dep = off_cell + 2 * kBcDC * kBcTH * 16;                // float4 [2][bin][row]
-  static constexpr size_t off_depT = off_dep + 2 * kBcDC * kBcTH * 16;                // float  [2][bin][kBcDepStride]
-  static constexpr size_t off_mask = off_depT + 2 * kBcDC * kBcDepStride * 4;         // uint32 [2][bin][column]
-  static constexpr size_t off_pc = off_mask + 2 * kBcDC * kBcTW * 4;                  // int    [2][bin][column]
-  static constexpr size_t off_res = off_pc + 2 * kBcDC * kBcTW * 4;                   // float4 [bin][row]
-  static constexpr size_t off_bar = off_res + kBcDC * kBcTH * 16;
+  static constexpr size_t off_dep = off_g + 2 * kRowFloats * 4;                       // float4 [2][bin][row]   (4 columns), as copied
+  static constexpr size_t off_rec = off_dep + 2 * kBcDC * kBcTH * 16;                 // int4   [2][bin][column] pair records
+  static constexpr size_t off_depT = off_rec + 2 * kBcDC * kBcTW * 16;                // float  [2][bin][kBcDepStride], masked + transposed
+  static constexpr size_t off_part = off_depT + 2 * kBcDC * kBcDepStride * 4;         // float  [warp][bin of mini-chunk][row group][kBcPartStride]
+  static constexpr size_t off_res = off_part + kBcTW * kBcMC * 4 * kBcPartStride * 4; // float  [bin][kBcDepStride] = [bin][column][row]: grad_depth of the chunk
+  static constexpr size_t off_mask = off_res + kBcDC * kBcDepStride * 4;              // uint32 [2][bin][column]: the records' row masks, copied by prep
+  static constexpr size_t off_bar = off_mask + 2 * kBcDC * kBcTW * 4;
   static constexpr size_t bytes = off_bar + 16;
 };
 
-// transposing butterfly over the 8 lanes of a group: in = 4 partial sums per lane, out = the full sum of
-// value (l8 >> 1) (both lanes of a pair hold it).  Fixed association order.
-__device__ __forceinline__ float reduce4_over8(const float (&s)[4], int l8) {
-  constexpr unsigned kFull = 0xffffffffu;
-  const bool hi4 = (l8 & 4) != 0;
-  const float t0 = (hi4 ? s[2] : s[0]) + __shfl_xor_sync(kFull, hi4 ? s[0] : s[2], 4);
-  const float t1 = (hi4 ? s[3] : s[1]) + __shfl_xor_sync(kFull, hi4 ? s[1] : s[3], 4);
-  const bool hi2 = (l8 & 2) != 0;
-  const float u = (hi2 ? t1 : t0) + __shfl_xor_sync(kFull, hi2 ? t0 : t1, 2);
-  return u + __shfl_xor_sync(kFull, u, 1);
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <int NV2, bool kNchw>
 __global__ void __launch_bounds__(kBcThreads, (NV2 <= 5 ? 3 : 2))
 fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_constant__ CUtensorMap gctx_map,
-                          const int32_t *__restrict__ cell_of_point, const float *__restrict__ grad_rows,
-                          const float *__restrict__ depth, const float *__restrict__ ctx_nhwc,
-                          float *__restrict__ grad_depth, float *__restrict__ grad_ctx_nhwc, int num_cams, int D,
-                          int H, int W, int64_t cells_per_sample, int tiles_h, int tiles_w) {
+                          const int32_t *__restrict__ cell_of_point, const int4 *__restrict__ pair_rec,
+                          const float *__restrict__ grad_rows, const float *__restrict__ depth,
+                          const float *__restrict__ ctx_nhwc, float *__restrict__ grad_depth,
+                          float *__restrict__ grad_ctx_nhwc, int num_cams, int D, int H, int W,
+                          int64_t cells_per_sample, int tiles_h, int tiles_w) {
   pdl_wait();
   pdl_trigger();
   using S = BcSmem<NV2>;
@@ -82,12 +95,12 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
   constexpr int kRowFloats = (int)S::kRowFloats;
   extern __shared__ __align__(128) unsigned char s_raw[];
   float *s_g = reinterpret_cast<float *>(s_raw + S::off_g);
-  int4 (*s_cell)[kBcDC][kBcTH] = reinterpret_cast<int4 (*)[kBcDC][kBcTH]>(s_raw + S::off_cell);
   float4 (*s_dep)[kBcDC][kBcTH] = reinterpret_cast<float4 (*)[kBcDC][kBcTH]>(s_raw + S::off_dep);
+  int4 (*s_rec)[kBcDC][kBcTW] = reinterpret_cast<int4 (*)[kBcDC][kBcTW]>(s_raw + S::off_rec);
   float *s_depT = reinterpret_cast<float *>(s_raw + S::off_depT);
+  float *s_part = reinterpret_cast<float *>(s_raw + S::off_part);
+  float *s_res = reinterpret_cast<float *>(s_raw + S::off_res);
   uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_raw + S::off_mask);
-  int *s_pc = reinterpret_cast<int *>(s_raw + S::off_pc);
-  float4 (*s_res)[kBcTH] = reinterpret_cast<float4 (*)[kBcTH]>(s_raw + S::off_res);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_raw + S::off_bar);
 
   const int tid = threadIdx.x, lane = tid & 31, wl = tid >> 5;      // warp = image column of the tile
@@ -101,6 +114,9 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
   const int64_t img_base = (int64_t)bn * D * HW;
   const float *gbase = grad_rows + (int64_t)(bn / num_cams) * cells_per_sample * C;
   const int nchunks = (D + kBcDC - 1) / kBcDC;
+  // pair records of this tile: index (((bn * D + d) * tiles_h + th) * W + w0 + column)
+  const int4 *rec_base = pair_rec + ((int64_t)bn * D * tiles_h + th) * W + w0;
+  const int64_t rec_bin_stride = (int64_t)tiles_h * W;
 
   // ---- context tile: TMA box [channel][row][4 columns] of the NCHW tensor (rows beyond H read as zeros)
   if (kNchw) {
@@ -115,77 +131,77 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
     }
   }
 
-  // staging role: a half-warp = the 16 rows of one bin; a thread stages bins sd and sd + 8
+  // staging role: a half-warp = the 16 rows of one bin; a thread stages bins sd and sd + 8.  Threads 0..63 also
+  // fetch the chunk's 16 x 4 pair records.
   const int sh = tid & 15, sd = tid >> 4;
   const bool srow = h0 + sh < H;
   const int64_t sbase = img_base + (int64_t)(h0 + sh) * W + w0;
 
-  auto issue_cells = [&](int c) {            // (cell, depth) segments of chunk c -> raw stage c & 1
+  auto issue_meta = [&](int c) {             // depth segments + pair records of chunk c -> stage c & 1
     if (c < nchunks) {
 #pragma unroll
       for (int pass = 0; pass < 2; ++pass) {
         const int bin = sd + 8 * pass, d = c * kBcDC + bin;
-        int4 *dc = &s_cell[c & 1][bin][sh];
         float4 *dd = &s_dep[c & 1][bin][sh];
-        if (srow && d < D) {
-          const int64_t gp = sbase + (int64_t)d * HW;
-          cp_async16(dc, cell_of_point + gp);
-          cp_async16(dd, depth + gp);
-        } else {
-          *dc = make_int4(-1, -1, -1, -1);
-          *dd = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        if (srow && d < D) cp_async16(dd, depth + sbase + (int64_t)d * HW);
+        else *dd = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid < kBcDC * kBcTW) {
+        const int bin = tid >> 2, col = tid & 3, d = c * kBcDC + bin;
+        int4 *dr = &s_rec[c & 1][bin][col];
+        if (d < D && w0 + col < W) cp_async16(dr, rec_base + (int64_t)d * rec_bin_stride + col);
+        else *dr = make_int4(-1, 0, -1, 0);
       }
     }
     cp_async_commit();
   };
-  // primary cell of every (bin, column) of chunk c, the mask of rows lying in it (low 16 bits) and of kept
-  // rows lying elsewhere (high 16 bits), and the depths transposed to [bin][column][row]
+  // depths of chunk c transposed to [bin][column][row], zero for rows outside the pair's primary cell, and the row
+  // masks copied out of the record stage (which the copies of chunk c + 2 overwrite while chunk c is being reduced);
+  // returns whether this thread saw a kept pair
   auto prep = [&](int c) -> int {
     if (c >= nchunks) return 0;
-    const int st = c & 1, half = lane & 16;
+    const int st = c & 1;
     int any = 0;
+    if (tid < kBcDC * kBcTW) s_mask[st * kBcDC * kBcTW + tid] = (uint32_t)s_rec[st][tid >> 2][tid & 3].y;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int bin = sd + 8 * pass;
-      const int4 pc = s_cell[st][bin][sh];
       const float4 pd = s_dep[st][bin][sh];
+      const int m0 = s_rec[st][bin][0].y, m1 = s_rec[st][bin][1].y, m2 = s_rec[st][bin][2].y, m3 = s_rec[st][bin][3].y;
       float *dT = s_depT + (st * kBcDC + bin) * kBcDepStride + sh;
-      auto one = [&](int cv, float dv, int col) {
-        const unsigned m = (__ballot_sync(kFull, cv >= 0) >> half) & 0xffffu;
-        const int v = __shfl_sync(kFull, cv, half + (m ? __ffs(m) - 1 : 0));
-        const bool fast = cv >= 0 && cv == v;
-        const unsigned fm = (__ballot_sync(kFull, fast) >> half) & 0xffffu;
-        dT[col * kBcTH] = fast ? dv : 0.f;
-        if (sh == 0) {
-          s_mask[(st * kBcDC + bin) * kBcTW + col] = fm | ((m & ~fm) << 16);
-          s_pc[(st * kBcDC + bin) * kBcTW + col] = m ? v : -1;
-        }
-        any |= (int)m;
-      };
-      one(pc.x, pd.x, 0);
-      one(pc.y, pd.y, 1);
-      one(pc.z, pd.z, 2);
-      one(pc.w, pd.w, 3);
+      dT[0 * kBcTH] = (m0 >> sh) & 1 ? pd.x : 0.f;
+      dT[1 * kBcTH] = (m1 >> sh) & 1 ? pd.y : 0.f;
+      dT[2 * kBcTH] = (m2 >> sh) & 1 ? pd.z : 0.f;
+      dT[3 * kBcTH] = (m3 >> sh) & 1 ? pd.w : 0.f;
+      any |= (m0 | m1 | m2 | m3);
     }
     return any;
   };
-  auto issue_rows = [&](int c, int live) {   // gradient rows of chunk c's primary cells -> row stage c & 1
+  // gradient rows of chunk c's primary cells -> row stage c & 1.  Thread = (row slot tid >> 3 of 16, eighth tid & 7):
+  // for each of its 4 rows (slot, slot + 16, ...) the float4s eighth, eighth + 8, eighth + 16 of the row (< C/4).
+  auto issue_rows = [&](int c, int live) {
     if (c < nchunks && live) {
-      const int *pcs = s_pc + (c & 1) * kBcDC * kBcTW;
-      float4 *dst = reinterpret_cast<float4 *>(s_g + (c & 1) * kRowFloats);
+      const int4 *recs = &s_rec[c & 1][0][0];
+      float *dst0 = s_g + (c & 1) * kRowFloats;
+      const int rs = tid >> 3, e8 = tid & 7;
 #pragma unroll
-      for (int i = tid; i < kBcDC * kBcTW * C4; i += kBcThreads) {
-        const int row = i / C4, v = i - row * C4;
-        const int cell = pcs[row];
-        if (cell >= 0) cp_async16(dst + i, reinterpret_cast<const float4 *>(gbase + (int64_t)cell * C) + v);
+      for (int k = 0; k < kBcDC * kBcTW / 16; ++k) {
+        const int row = rs + 16 * k;
+        const int cell = recs[row].x;
+        if (cell >= 0) {
+          const float4 *src = reinterpret_cast<const float4 *>(gbase + (int64_t)cell * C) + e8;
+          float4 *dst = reinterpret_cast<float4 *>(dst0 + row * C) + e8;
+#pragma unroll
+          for (int v = 0; v < (C4 + 7) / 8; ++v)
+            if (e8 + 8 * v < C4) cp_async16(dst + 8 * v, src + 8 * v);
+        }
       }
     }
     cp_async_commit();
   };
 
-  issue_cells(0);
-  issue_cells(1);
+  issue_meta(0);
+  issue_meta(1);
 
   // ---- this lane's context rows: 4 pixels (rows 4*rg + j of column wl) x NREG channels
   float cx[4][NREG], gacc[4][NREG];
@@ -207,41 +223,85 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
         g8_load_row<NV2, true>(reinterpret_cast<const char *>(ctx_nhwc + ((int64_t)bn * HW + h * W + w0 + wl) * C), l8, cx[j]);
     }
   }
-  for (int i = tid; i < kBcDC * kBcTH; i += kBcThreads) (&s_res[0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < kBcDC * kBcDepStride; i += kBcThreads) s_res[i] = 0.f;
 
   cp_async_wait_1();
-  __syncthreads();                           // cells(0) visible; the context box is no longer needed
+  __syncthreads();                           // meta(0) visible; the context box is no longer needed
   int live_cur = __syncthreads_or(prep(0));
   issue_rows(0, live_cur);
 
+  float *part_w = s_part + wl * (kBcMC * 4 * kBcPartStride);          // this warp's partial-dot buffer
   for (int c = 0; c < nchunks; ++c) {
-    // in flight here: cells(c+1), rows(c)
+    // in flight here: meta(c+1), rows(c)
     cp_async_wait_all();
     __syncthreads();
     const int live_next = __syncthreads_or(prep(c + 1));
     issue_rows(c + 1, live_next);
-    issue_cells(c + 2);                      // into the raw stage prep(c) consumed an iteration ago
+    issue_meta(c + 2);                       // into the stage prep(c) consumed an iteration ago
 
     if (live_cur) {
       const int st = c & 1;
-      const float *g_col = s_g + st * kRowFloats + wl * C;
-      const float *dT = s_depT + st * kBcDC * kBcDepStride + wl * kBcTH + 4 * rg;
-      const uint32_t *mk = s_mask + st * kBcDC * kBcTW + wl;
-#pragma unroll 4
-      for (int b = 0; b < kBcDC; ++b) {
-        const uint32_t m = mk[b * kBcTW];
-        if (m == 0u) continue;                                  // warp-uniform: no kept row in this (bin, column)
-        const uint32_t fast = m & 0xffffu, slow = m >> 16;
-        if (fast) {
-          float g[NREG];
-          g8_lds_row<NV2>(g_col + b * (kBcTW * C), l8, g);
-          const float4 dp4 = *reinterpret_cast<const float4 *>(dT + b * kBcDepStride);
+      // masks of the chunk's 16 bins for this warp's column: lane b holds bin b's
+      const uint32_t m_lane = lane < kBcDC ? s_mask[(st * kBcDC + lane) * kBcTW + wl] : 0u;
+      uint32_t live = __ballot_sync(kFull, m_lane != 0u);
+      if (live) {                                                     // warp-uniform
+        // ONE copy of the loop body walks the kept bins (accumulators stay in place across the back edge); the
+        // operands of the next kept bin are fetched from shared memory before the current bin's 40 FFMA2 are issued.
+        // Every 4 bins (and at the end) phase B turns the parked partial sums into grad_depth values.
+        // Shared-memory operands are addressed through two per-lane byte addresses kept opaque to the compiler
+        // (it otherwise re-derives them from the thread index inside the loop to save registers).
+        const uint32_t g_addr = opaque_u32(smem_u32(s_g + st * kRowFloats + wl * C) + 16u * l8);
+        const uint32_t g_addr2 = opaque_u32(smem_u32(s_g + st * kRowFloats + wl * C + 32 * (NV2 / 2)) + 8u * l8);
+        const uint32_t d_addr = opaque_u32(smem_u32(s_depT + st * kBcDC * kBcDepStride + wl * kBcTH + 4 * rg));
+        const uint32_t p_addr = opaque_u32(smem_u32(part_w + rg * kBcPartStride + 4 * l8));
+        uint32_t binpack = 0u;
+        int nslot = 0;
+        auto fetch = [&](int b, float (&g)[NREG], float4 &dp4) {
+          const uint32_t ga = g_addr + (uint32_t)b * (kBcTW * C * 4);
+#pragma unroll
+          for (int k = 0; k < NV2 / 2; ++k) {
+            const float4 t = lds_f4(ga + 128 * k);
+            g[4 * k + 0] = t.x; g[4 * k + 1] = t.y; g[4 * k + 2] = t.z; g[4 * k + 3] = t.w;
+          }
+          if (NV2 & 1) {
+            const float2 t = lds_f2(g_addr2 + (uint32_t)b * (kBcTW * C * 4));
+            g[4 * (NV2 / 2) + 0] = t.x; g[4 * (NV2 / 2) + 1] = t.y;
+          }
+          dp4 = lds_f4(d_addr + (uint32_t)b * (kBcDepStride * 4));
+        };
+        auto phase_b = [&]() {
+          __syncwarp();
+          const int pair = lane >> 1, half = lane & 1, kk = pair >> 2, prg = pair & 3;
+          const int bq = (int)((binpack >> (4 * kk)) & 0xfu);
+          const uint32_t mq = __shfl_sync(kFull, m_lane, bq);
+          const float4 *pp = reinterpret_cast<const float4 *>(part_w + pair * kBcPartStride + 16 * half);
+          const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
+          float4 t;
+          t.x = (p0.x + p1.x) + (p2.x + p3.x);
+          t.y = (p0.y + p1.y) + (p2.y + p3.y);
+          t.z = (p0.z + p1.z) + (p2.z + p3.z);
+          t.w = (p0.w + p1.w) + (p2.w + p3.w);
+          t.x += __shfl_xor_sync(kFull, t.x, 1);
+          t.y += __shfl_xor_sync(kFull, t.y, 1);
+          t.z += __shfl_xor_sync(kFull, t.z, 1);
+          t.w += __shfl_xor_sync(kFull, t.w, 1);
+          if (half == 0 && kk < nslot) {
+            const uint32_t keep = (mq >> (4 * prg)) & 0xfu;         // rows of this group lying in the bin's primary cell
+            t.x = (keep & 1u) ? t.x : 0.f;
+            t.y = (keep & 2u) ? t.y : 0.f;
+            t.z = (keep & 4u) ? t.z : 0.f;
+            t.w = (keep & 8u) ? t.w : 0.f;
+            *reinterpret_cast<float4 *>(s_res + bq * kBcDepStride + wl * kBcTH + 4 * prg) = t;
+          }
+          __syncwarp();
+          binpack = 0u;
+          nslot = 0;
+        };
+        // body: reduce bin b.  Branch-free over the rows: dot products of rows outside the primary cell are computed
+        // and never stored, and their staged depth is 0, so their accumulators receive +-0 (exact for finite gradients).
+        auto body = [&](int b, const float (&g)[NREG], const float4 &dp4) {
           const float dp[4] = {dp4.x, dp4.y, dp4.z, dp4.w};
-          const uint32_t mine = (fast >> (4 * rg)) & 0xfu;
-          // Branch-free: the dot products of rows outside the primary cell are computed and discarded, and their
-          // staged depth is 0, so their accumulators receive +-0 (exact for finite gradients; see DESIGN.md 4.4 for
-          // the non-finite case).  40 independent FFMA2 per bin hide the shared-memory latency of the next bin.
-          float s[4];
+          float sv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
@@ -252,37 +312,66 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
             }
             axpy_row<NREG>(gacc[j], dp[j], g);
             const float2 dab = __fadd2_rn(da, db);
-            s[j] = dab.x + dab.y;
+            sv[j] = dab.x + dab.y;
           }
-          const float tot = reduce4_over8(s, l8);
-          const int p = l8 >> 1;
-          if (!(l8 & 1) && ((mine >> p) & 1u))
-            reinterpret_cast<float *>(&s_res[b][4 * rg + p])[wl] = tot;
+          sts_f4(p_addr + (uint32_t)nslot * (4 * kBcPartStride * 4), make_float4(sv[0], sv[1], sv[2], sv[3]));
+          binpack |= (uint32_t)b << (4 * nslot);
+          ++nslot;
+        };
+        const uint32_t slow_bins = __ballot_sync(kFull, (m_lane >> 16) != 0u);
+        float ga[NREG], gb[NREG];
+        float4 da4, db4;
+        int ba = __ffs(live) - 1, bb = ba;
+        live &= live - 1u;
+        fetch(ba, ga, da4);
+        while (true) {                                                // warp-uniform; two roles, no register rotation
+          const bool more_a = live != 0u;
+          if (more_a) {
+            bb = __ffs(live) - 1;
+            live &= live - 1u;
+            fetch(bb, gb, db4);
+          }
+          body(ba, ga, da4);
+          if (nslot == kBcMC || !more_a) phase_b();
+          if (!more_a) break;
+          const bool more_b = live != 0u;
+          if (more_b) {
+            ba = __ffs(live) - 1;
+            live &= live - 1u;
+            fetch(ba, ga, da4);
+          }
+          body(bb, gb, db4);
+          if (nslot == kBcMC || !more_b) phase_b();
+          if (!more_b) break;
         }
-        if (slow) {
-          // rows of this (bin, column) that are kept but lie outside the primary cell: gather their own row
+        // ---- kept rows outside their pair's primary cell (tilted cameras, random geometry; none for a level
+        // camera): every such row gathers its own gradient row from global memory.  After the loop above, so that
+        // phase B's zeros for these rows are already in place.
+        for (uint32_t sl = slow_bins; sl; sl &= sl - 1u) {            // warp-uniform
+          const int b = __ffs(sl) - 1;
+          const uint32_t slow = __shfl_sync(kFull, m_lane, b) >> 16;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (((slow >> j) & 0x1111u) == 0u) continue;        // warp-uniform
+            if (((slow >> j) & 0x1111u) == 0u) continue;              // warp-uniform
             const bool p = (slow >> (4 * rg + j)) & 1u;
             float dot = 0.f;
             if (p) {
               const int64_t gp = img_base + (int64_t)(c * kBcDC + b) * HW + (int64_t)(h0 + 4 * rg + j) * W + w0 + wl;
               const int cell = __ldg(cell_of_point + gp);
               const float dv = __ldg(depth + gp);
-              float g[NREG];
-              g8_load_row<NV2, false>(reinterpret_cast<const char *>(gbase + (int64_t)cell * C), l8, g);
+              float gs[NREG];
+              g8_load_row<NV2, false>(reinterpret_cast<const char *>(gbase + (int64_t)cell * C), l8, gs);
               float2 da = make_float2(0.f, 0.f);
 #pragma unroll
               for (int r = 0; r < NREG; r += 2)
-                da = __ffma2_rn(make_float2(g[r], g[r + 1]), make_float2(cx[j][r], cx[j][r + 1]), da);
+                da = __ffma2_rn(make_float2(gs[r], gs[r + 1]), make_float2(cx[j][r], cx[j][r + 1]), da);
               dot = da.x + da.y;
-              axpy_row<NREG>(gacc[j], dv, g);
+              axpy_row<NREG>(gacc[j], dv, gs);
             }
             dot += __shfl_xor_sync(kFull, dot, 4);
             dot += __shfl_xor_sync(kFull, dot, 2);
             dot += __shfl_xor_sync(kFull, dot, 1);
-            if (p && l8 == 0) reinterpret_cast<float *>(&s_res[b][4 * rg + j])[wl] = dot;
+            if (p && l8 == 0) s_res[b * kBcDepStride + wl * kBcTH + 4 * rg + j] = dot;
           }
         }
       }
@@ -292,8 +381,11 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int bin = sd + 8 * pass, d = c * kBcDC + bin;
-      if (srow && d < D) stg_stream_f4(reinterpret_cast<float4 *>(grad_depth + sbase + (int64_t)d * HW), s_res[bin][sh]);
-      if (live_cur) s_res[bin][sh] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float *rp = s_res + bin * kBcDepStride + sh;
+      if (srow && d < D)
+        stg_stream_f4(reinterpret_cast<float4 *>(grad_depth + sbase + (int64_t)d * HW),
+                      make_float4(rp[0], rp[kBcTH], rp[2 * kBcTH], rp[3 * kBcTH]));
+      if (live_cur) rp[0] = rp[kBcTH] = rp[2 * kBcTH] = rp[3 * kBcTH] = 0.f;
     }
     live_cur = live_next;
   }
@@ -325,18 +417,14 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
 
 template <int NV2, bool kNchw>
 static int launch_bc(const CUtensorMap &ctx_map, const CUtensorMap &gctx_map, const int32_t *cell_of_point,
-                     const float *grad_rows, const float *depth, const float *ctx_nhwc, float *grad_depth,
+                     const int4 *pair_rec, const float *grad_rows, const float *depth, const float *ctx_nhwc, float *grad_depth,
                      float *grad_ctx_nhwc, int num_cams, int D, int H, int W, int64_t cells_per_sample, int64_t ctas,
                      int tiles_h, int tiles_w, cudaStream_t s) {
   constexpr size_t smem = BcSmem<NV2>::bytes;
-  static bool configured = false;
-  if (!configured) {
-    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_col_kernel<NV2, kNchw>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_col_kernel<NV2, kNchw>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BEVPOOL_RETURN_IF_CUDA(launch_pdl(fused_backward_col_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kBcThreads), smem, s,
-                                    ctx_map, gctx_map, cell_of_point, grad_rows, depth, ctx_nhwc, grad_depth, grad_ctx_nhwc,
+                                    ctx_map, gctx_map, cell_of_point, pair_rec, grad_rows, depth, ctx_nhwc, grad_depth, grad_ctx_nhwc,
                                     num_cams, D, H, W, cells_per_sample, tiles_h, tiles_w));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
@@ -347,7 +435,7 @@ bool fused_backward_col_supported(int C, int W, const void *depth, const void *g
 }
 
 // context / grad_context: NCHW (B*N, C, H, W) when `nchw`, else pixel rows (B*N, H, W, C)
-int launch_fused_backward_col(const int32_t *cell_of_point, const float *grad_rows, const float *depth,
+int launch_fused_backward_col(const int32_t *cell_of_point, const int4 *pair_rec, const float *grad_rows, const float *depth,
                               const float *ctx, float *grad_depth, float *grad_ctx, bool nchw, int batch, int num_cams,
                               int D, int H, int W, int C, int64_t cells_per_sample, cudaStream_t s) {
   const int64_t tiles_h = ceil_div64(H, kBcTH), tiles_w = ceil_div64(W, kBcTW);
@@ -363,7 +451,7 @@ int launch_fused_backward_col(const int32_t *cell_of_point, const float *grad_ro
     if ((rc = make_tensor_map_f32(&gctx_map, grad_ctx, 4, dims, strides, box))) return rc;
   }
   int rc = BEVPOOL_OK;
-#define BEVPOOL_BC_ARGS ctx_map, gctx_map, cell_of_point, grad_rows, depth, ctx, grad_depth, grad_ctx, num_cams, D, H, W, \
+#define BEVPOOL_BC_ARGS ctx_map, gctx_map, cell_of_point, pair_rec, grad_rows, depth, ctx, grad_depth, grad_ctx, num_cams, D, H, W, \
                         cells_per_sample, ctas, (int)tiles_h, (int)tiles_w, s
   if (nchw) { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, true>(BEVPOOL_BC_ARGS))); }
   else { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, false>(BEVPOOL_BC_ARGS))); }

@@ -43,6 +43,13 @@ inline int make_tensor_map_f32(CUtensorMap *map, const void *base, int rank, con
                                const uint64_t *strides_bytes, const uint32_t *box) {
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enc) return (int)cudaErrorNotSupported;
+  // The encoder is a driver entry point and wants the primary context current on the calling thread; a thread that
+  // has only used the runtime lazily (autograd's backward threads) may not have bound it yet.
+  static thread_local bool context_bound = false;
+  if (!context_bound) {
+    cudaFree(nullptr);
+    context_bound = true;
+  }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }

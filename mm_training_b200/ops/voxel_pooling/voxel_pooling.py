@@ -95,7 +95,7 @@ class PoolingPlan:
             N, D, H, W = (int(v) for v in frustum)
             assert N * D * H * W == self.num_points, 'frustum shape does not match geom_xyz'
             if geom_xyz.data_ptr() % 16 == 0:
-                _lib.check(L.bevpool_runplan_sizes(self.batch, self.num_points, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
+                _lib.check(L.bevpool_runplan_sizes(self.batch, N, D, H, W, X, Y, ctypes.byref(pb), ctypes.byref(tb)),
                            'bevpool_runplan_sizes')
                 self.mode, self.frustum = 'runs', (N, D, H, W)
         if self.mode == 'points':
@@ -188,6 +188,21 @@ class PoolingPlan:
         """run plans: int32 (B, Np) -- slot of the run for its first point, -2 continuation, -1 dropped."""
         assert self.mode == 'runs'
         return self._views()[4].view(self.batch, self.num_points)
+
+    @property
+    def pair_records(self) -> torch.Tensor:
+        """run plans: int32 (B, N, D, ceil(H/16), W, 4) = {primary cell | -1, rows in it | kept rows elsewhere << 16,
+        slot of the run that starts at the first kept row, number of runs} per (image, bin, 16-row block, column)."""
+        assert self.mode == 'runs'
+        N, D, H, W = self.frustum
+        HB = (H + 15) // 16
+        X, Y, _ = self.voxel_num
+        q = ctypes.c_void_p()
+        _lib.check(_lib.lib().bevpool_runplan_pair_records(self.ptr, self.batch, self.num_points, X, Y, ctypes.byref(q)),
+                   'bevpool_runplan_pair_records')
+        o = (q.value - self.ptr) // 4
+        n = self.batch * N * D * HB * W * 4
+        return self.buffer.view(torch.int32)[o:o + n].view(self.batch, N, D, HB, W, 4)
 
     def pos_memo(self) -> torch.Tensor:
         """The reference's ``pos_memo`` (voxel_pooling.py:40): int32 (B, Np, 3) = (b, y, x) or -1."""
@@ -347,20 +362,27 @@ def fused_backward(plan: PoolingPlan, grad_output: torch.Tensor, depth: torch.Te
     with torch.cuda.device(depth.device):
         rows = _grad_rows_nhwc(grad_output, plan)
         grad_depth = torch.empty_like(depth)
-        if context_rows is None and _nchw_direct(context, depth):
+        runs = plan.mode == 'runs' and runs_supported(C, depth.dtype)
+        if runs and context_rows is None and _nchw_direct(context, depth):
             grad_context = torch.empty_like(context)
-            _lib.check(_lib.lib().bevpool_fused_backward_nchw(
+            _lib.check(_lib.lib().bevpool_fused_backward_runs(
                 plan.ptr, rows.data_ptr(), depth.data_ptr(), context.data_ptr(), grad_depth.data_ptr(),
-                grad_context.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
-                _lib.stream_ptr(depth.device)), 'bevpool_fused_backward_nchw')
+                grad_context.data_ptr(), 1, _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_backward_runs')
             return grad_depth, grad_context
         channels_last = context.permute(0, 2, 3, 1).is_contiguous()
         ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
         grad_ctx_nhwc = torch.empty(BN, H, W, C, dtype=context.dtype, device=context.device)
-        _lib.check(_lib.lib().bevpool_fused_backward(
-            plan.ptr, rows.data_ptr(), depth.data_ptr(), ctx_nhwc.data_ptr(), grad_depth.data_ptr(),
-            grad_ctx_nhwc.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
-            _lib.stream_ptr(depth.device)), 'bevpool_fused_backward')
+        if runs:
+            _lib.check(_lib.lib().bevpool_fused_backward_runs(
+                plan.ptr, rows.data_ptr(), depth.data_ptr(), ctx_nhwc.data_ptr(), grad_depth.data_ptr(),
+                grad_ctx_nhwc.data_ptr(), 0, _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_backward_runs')
+        else:
+            _lib.check(_lib.lib().bevpool_fused_backward(
+                plan.ptr, rows.data_ptr(), depth.data_ptr(), ctx_nhwc.data_ptr(), grad_depth.data_ptr(),
+                grad_ctx_nhwc.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_backward')
         if channels_last:
             grad_context = grad_ctx_nhwc.permute(0, 3, 1, 2)
         else:
