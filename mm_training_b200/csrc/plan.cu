@@ -328,110 +328,6 @@ __device__ __forceinline__ int cell_of_xyz(int x, int y, int z, int X, int Y, in
   return (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) ? y * X + x : -1;
 }
 
-constexpr int kRunWarpSlots = kSortItems * 32;   // points (= upper bound of run heads) one warp of K1 handles
-
-__global__ void __launch_bounds__(kSortThreads)
-plan_key_runs_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X, int Y, int Z,
-                     int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code,
-                     uint32_t *__restrict__ counts, int32_t *__restrict__ head_cells,
-                     int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
-                     uint32_t *__restrict__ sample_total, int tiles_per_sample, FastDiv div_w, FastDiv div_h,
-                     PlanHeader *hdr, PlanHeader hv) {
-  pdl_wait();
-  pdl_trigger();
-  const int b = blockIdx.y, tile = blockIdx.x;
-  if (b == 0 && tile == 0 && threadIdx.x == 0) *hdr = hv;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t sample_base = (int64_t)b * num_points;
-  const int64_t tile_base = (int64_t)tile * kSortTile;
-  const int64_t cells = (int64_t)X * Y;
-  const int W = (int)div_w.div, H = (int)div_h.div;
-  const bool vec = ((sample_base + tile_base) & 3) == 0 && (W & 3) == 0;   // quads are 16-byte aligned and stay in one row
-  const int64_t region = (((int64_t)b * tiles_per_sample + tile) * kSortWarps + warp) * kRunWarpSlots;
-  uint32_t filled = 0;                 // heads this warp has written so far (warp-uniform)
-#pragma unroll
-  for (int q = 0; q < kSortItems / 4; ++q) {
-    const int64_t p0 = tile_base + ((int64_t)q * kSortThreads + threadIdx.x) * 4;
-    const int64_t gp0 = sample_base + p0;
-    int cell[4], code[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { cell[k] = -1; code[k] = kRunDropped; }
-    if (p0 < num_points) {
-      if (vec && p0 + 3 < num_points) {
-        const int4 *src = reinterpret_cast<const int4 *>(geom + gp0 * 3);
-        const int4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
-        cell[0] = cell_of_xyz(a0.x, a0.y, a0.z, X, Y, Z);
-        cell[1] = cell_of_xyz(a0.w, a1.x, a1.y, X, Y, Z);
-        cell[2] = cell_of_xyz(a1.z, a1.w, a2.x, X, Y, Z);
-        cell[3] = cell_of_xyz(a2.y, a2.z, a2.w, X, Y, Z);
-        const uint32_t row = fastdiv((uint32_t)p0, div_w);
-        const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
-        int pcell[4] = {-1, -1, -1, -1};
-        if ((h % kRunHB) != 0 && (cell[0] >= 0 || cell[1] >= 0 || cell[2] >= 0 || cell[3] >= 0)) {
-          const int4 *ps = reinterpret_cast<const int4 *>(geom + (gp0 - W) * 3);   // the row above: an L1/L2 hit
-          const int4 b0 = __ldg(ps), b1 = __ldg(ps + 1), b2 = __ldg(ps + 2);
-          pcell[0] = cell_of_xyz(b0.x, b0.y, b0.z, X, Y, Z);
-          pcell[1] = cell_of_xyz(b0.w, b1.x, b1.y, X, Y, Z);
-          pcell[2] = cell_of_xyz(b1.z, b1.w, b2.x, X, Y, Z);
-          pcell[3] = cell_of_xyz(b2.y, b2.z, b2.w, X, Y, Z);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          code[k] = cell[k] < 0 ? kRunDropped : (pcell[k] != cell[k] ? cell[k] : kRunCont);
-        *reinterpret_cast<int4 *>(cell_of_point + gp0) = make_int4(cell[0], cell[1], cell[2], cell[3]);
-        *reinterpret_cast<int4 *>(run_code + gp0) = make_int4(code[0], code[1], code[2], code[3]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (p0 + k >= num_points) continue;
-          const int32_t *g = geom + (gp0 + k) * 3;
-          cell[k] = cell_of_xyz(__ldg(g), __ldg(g + 1), __ldg(g + 2), X, Y, Z);
-          if (cell[k] >= 0) {
-            const uint32_t row = fastdiv((uint32_t)(p0 + k), div_w);
-            const int h = (int)(row - fastdiv(row, div_h) * (uint32_t)H);
-            int pc = -1;
-            if ((h % kRunHB) != 0) {
-              const int32_t *pg = g - (int64_t)W * 3;
-              pc = cell_of_xyz(__ldg(pg), __ldg(pg + 1), __ldg(pg + 2), X, Y, Z);
-            }
-            code[k] = pc != cell[k] ? cell[k] : kRunCont;
-          }
-          cell_of_point[gp0 + k] = cell[k];
-          run_code[gp0 + k] = code[k];
-        }
-      }
-    }
-    // warp compaction of this round's heads (order inside the slice is irrelevant: K4 orders by id)
-    const uint32_t mine = (code[0] >= 0) + (code[1] >= 0) + (code[2] >= 0) + (code[3] >= 0);
-    uint32_t incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    uint32_t pos = filled + incl - mine;
-    filled += __shfl_sync(0xffffffffu, incl, 31);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (code[k] >= 0) {
-        head_cells[region + pos] = code[k];
-        head_ids[region + pos] = (int32_t)(gp0 + k);
-        atomicAdd(counts + (int64_t)b * cells + code[k], 1u);
-        ++pos;
-      }
-    }
-  }
-  __shared__ uint32_t s_cta_total;
-  if (threadIdx.x == 0) s_cta_total = 0u;
-  __syncthreads();
-  if (lane == 0) {
-    warp_count[((int64_t)b * tiles_per_sample + tile) * kSortWarps + warp] = (int32_t)filled;
-    if (filled) atomicAdd(&s_cta_total, filled);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0 && s_cta_total) atomicAdd(sample_total + b, s_cta_total);   // one global atomic per CTA
-}
-
 // ==== run plan straight from the camera rig (no geom_xyz tensor) ===================================
 // Replaces layers/backbones/lss_fpn.py:328-361 (get_geometry) + :461-462 (quantisation) of the reference as
 // the producer of the cell indices: the (B, N, D, H, W, 3) float and int32 tensors are never written or read.
@@ -495,9 +391,12 @@ __device__ __forceinline__ int rig_quantise(float e, float lo, float vs, float i
 
 constexpr int kRigThreads = 256;
 
+// kVariant >= 0: cells from the rig (RigParams); kVariant == -1: cells from the caller's geom_xyz tensor (same walk:
+// lanes = consecutive columns, so the 12-byte points of a row are read as one 384-byte span per warp).
 template <int kVariant>
 __global__ void __launch_bounds__(kRigThreads)
-plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int X, int Y, int Z, int64_t num_points,
+plan_key_rig_kernel(RigParams rp, const int32_t *__restrict__ geom, int num_cams, int D, int H, int W, int HB, int X, int Y,
+                    int Z, int64_t num_points,
                     int32_t *__restrict__ cell_of_point, int32_t *__restrict__ run_code, uint32_t *__restrict__ counts,
                     int32_t *__restrict__ head_cells, int32_t *__restrict__ head_ids, int32_t *__restrict__ warp_count,
                     uint32_t *__restrict__ sample_total, int warps_per_sample, int slot_cap, int4 *__restrict__ pair_rec,
@@ -518,16 +417,17 @@ plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int
     d = (int)(t % D);
     n = (int)(t / D);
   }
-  float m0[4], m1[4], m2[4];
-  {
+  float m0[4] = {0.f, 0.f, 0.f, 0.f}, m1[4] = {0.f, 0.f, 0.f, 0.f}, m2[4] = {0.f, 0.f, 0.f, 0.f};
+  float dd = 0.f, px = 0.f;
+  if (kVariant >= 0) {
     const float4 *mp = reinterpret_cast<const float4 *>(rp.combine + ((int64_t)b * num_cams + n) * 16);
     const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
     m0[0] = r0.x; m0[1] = r0.y; m0[2] = r0.z; m0[3] = r0.w;
     m1[0] = r1.x; m1[1] = r1.y; m1[2] = r1.z; m1[3] = r1.w;
     m2[0] = r2.x; m2[1] = r2.y; m2[2] = r2.z; m2[3] = r2.w;
+    dd = __ldg(rp.fd + d);
+    px = __fmul_rn(__ldg(rp.fx + w), dd);
   }
-  const float dd = __ldg(rp.fd + d);
-  const float px = __fmul_rn(__ldg(rp.fx + w), dd);
   const int64_t cells = (int64_t)X * Y;
   const int64_t region = ((int64_t)b * warps_per_sample + (int64_t)blockIdx.x * (kRigThreads / 32) + warp) * slot_cap;
   const int64_t col_base = (int64_t)b * num_points + ((int64_t)n * D + d) * H * W + w;
@@ -541,14 +441,22 @@ plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int
     const bool act = valid && h < H;
     int cell = -1, code = kRunDropped;
     if (act) {
-      const float py = __fmul_rn(__ldg(rp.fy + h), dd);
-      const int ix = rig_quantise(rig_dot4<kVariant>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
-      const int iy = rig_quantise(rig_dot4<kVariant>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
-      const int iz = rig_quantise(rig_dot4<kVariant>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
+      const int64_t gp = col_base + (int64_t)h * W;
+      int ix, iy, iz;
+      if (kVariant >= 0) {
+        const float py = __fmul_rn(__ldg(rp.fy + h), dd);
+        ix = rig_quantise(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
+        iy = rig_quantise(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
+        iz = rig_quantise(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
+      } else {
+        const int32_t *g = geom + gp * 3;
+        ix = ldg_stream_i32(g);
+        iy = ldg_stream_i32(g + 1);
+        iz = ldg_stream_i32(g + 2);
+      }
       cell = cell_of_xyz(ix, iy, iz, X, Y, Z);
       code = cell < 0 ? kRunDropped : (cell != prev ? cell : kRunCont);
       prev = cell;
-      const int64_t gp = col_base + (int64_t)h * W;
       cell_of_point[gp] = cell;
       run_code[gp] = code;          // heads: overwritten with their slot by K4
       if (cell >= 0) {
@@ -563,7 +471,8 @@ plan_key_rig_kernel(RigParams rp, int num_cams, int D, int H, int W, int HB, int
     if (head) {
       const int64_t pos = region + filled + __popc(bal & lt);
       head_cells[pos] = code;
-      head_ids[pos] = (int32_t)(col_base + (int64_t)h * W);
+      // bit 31: this head is the first kept row of its pair (K4 then records its slot in the pair record)
+      head_ids[pos] = (int32_t)(col_base + (int64_t)h * W) | (keptm == (1u << r) ? (int32_t)0x80000000 : 0);
       atomicAdd(counts + (int64_t)b * cells + code, 1u);
     }
     filled += __popc(bal);
@@ -599,40 +508,6 @@ rig_geom_kernel(RigParams rp, int num_cams, int D, int H, int W, int64_t total, 
   geom[gp * 3 + 0] = rig_quantise(rig_dot4<kVariant>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
   geom[gp * 3 + 1] = rig_quantise(rig_dot4<kVariant>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
   geom[gp * 3 + 2] = rig_quantise(rig_dot4<kVariant>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
-}
-
-// Pair records of a plan built from geom_xyz: one thread per (image, bin, 16-row block, column), walking the rows
-// of cell_of_point / run_code that K1 wrote (lanes = consecutive columns: coalesced).  Runs before K4, which adds
-// the primary slot.
-__global__ void __launch_bounds__(256)
-pair_records_kernel(const int32_t *__restrict__ cell_of_point, const int32_t *__restrict__ run_code, int num_cams, int D,
-                    int H, int W, int HB, int64_t num_points, int4 *__restrict__ pair_rec) {
-  pdl_wait();
-  pdl_trigger();
-  const int b = blockIdx.y;
-  const int64_t pairs = (int64_t)num_cams * D * HB * W;
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= pairs) return;
-  int64_t t = q;
-  const int w = (int)(t % W); t /= W;
-  const int hb = (int)(t % HB); t /= HB;             // t = n * D + d
-  const int64_t col_base = (int64_t)b * num_points + t * H * W + w;
-  int primary = -1, nheads = 0;
-  uint32_t fastm = 0u, keptm = 0u;
-#pragma unroll 4
-  for (int r = 0; r < kRunHB; ++r) {
-    const int h = hb * kRunHB + r;
-    if (h >= H) break;
-    const int64_t gp = col_base + (int64_t)h * W;
-    const int cell = __ldg(cell_of_point + gp);
-    if (cell >= 0) {
-      if (primary < 0) primary = cell;
-      keptm |= 1u << r;
-      if (cell == primary) fastm |= 1u << r;
-      nheads += __ldg(run_code + gp) >= 0;           // head codes are >= 0 both before and after K4
-    }
-  }
-  pair_rec[(int64_t)b * pairs + q] = make_int4(primary, (int)(fastm | ((keptm & ~fastm) << 16)), -1, nheads);
 }
 
 // K2: exclusive scan of the per-cell run counts, one independent look-back chain per SAMPLE (a single
@@ -789,9 +664,9 @@ __device__ __forceinline__ void record_primary_slot(int4 *__restrict__ pair_rec,
   const uint32_t nd = fastdiv(rowi, pd.div_h);
   const uint32_t h = rowi - nd * pd.div_h.div;
   const int64_t q = (int64_t)b * pd.pairs_per_sample + ((int64_t)nd * pd.HB + h / kRunHB) * pd.W + w;
-  const uint32_t masks = (uint32_t)pair_rec[q].y;
-  if ((masks & 0xffffu) && (uint32_t)(__ffs(masks & 0xffffu) - 1) == (h % kRunHB)) pair_rec[q].z = slot;
+  pair_rec[q].z = slot;
 }
+constexpr int32_t kHeadIdMask = 0x7fffffff;       // head ids carry "first kept row of its pair" in bit 31
 __global__ void __launch_bounds__(256)
 run_finish_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__restrict__ placed_ids,
                   const int32_t *__restrict__ placed_cells, int64_t total_cells, int32_t *__restrict__ sorted_ids,
@@ -807,13 +682,13 @@ run_finish_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__rest
       if (pos == s) big_list[atomicAdd(big_count, 1u)] = gc;     // (order of the queue is irrelevant)
       continue;
     }
-    const int32_t id = placed_ids[pos];
+    const int32_t idf = placed_ids[pos], id = idf & kHeadIdMask;
     uint32_t rank = 0;
-    for (uint32_t j = s; j < e; ++j) rank += placed_ids[j] < id;
+    for (uint32_t j = s; j < e; ++j) rank += (placed_ids[j] & kHeadIdMask) < id;
     sorted_ids[s + rank] = id;
     sorted_cells[s + rank] = gc;
     run_code[id] = (int32_t)(s + rank);
-    record_primary_slot(pair_rec, pd, id, (int32_t)(s + rank));
+    if (idf < 0) record_primary_slot(pair_rec, pd, id, (int32_t)(s + rank));
   }
 }
 
@@ -833,12 +708,12 @@ run_finish_big_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__
     const uint32_t s = cell_start[gc], n = cell_start[gc + 1] - s;
     for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
       const uint32_t i = i0 + threadIdx.x;
-      const int32_t id = i < n ? placed_ids[s + i] : INT32_MAX;
+      const int32_t idf = i < n ? placed_ids[s + i] : INT32_MAX, id = idf & kHeadIdMask;
       uint32_t rank = 0;
       for (uint32_t j0 = 0; j0 < n; j0 += kTile) {
         __syncthreads();
         const uint32_t m = min((uint32_t)kTile, n - j0);
-        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) s_ids[j] = placed_ids[s + j0 + j];
+        for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) s_ids[j] = placed_ids[s + j0 + j] & kHeadIdMask;
         __syncthreads();
         for (uint32_t j = 0; j < m; ++j) rank += s_ids[j] < id;
       }
@@ -846,7 +721,7 @@ run_finish_big_kernel(const uint32_t *__restrict__ cell_start, const int32_t *__
         sorted_ids[s + rank] = id;
         sorted_cells[s + rank] = (int32_t)gc;
         run_code[id] = (int32_t)(s + rank);
-        record_primary_slot(pair_rec, pd, id, (int32_t)(s + rank));
+        if (idf < 0) record_primary_slot(pair_rec, pd, id, (int32_t)(s + rank));
       }
     }
   }
@@ -1115,9 +990,6 @@ static RunTempLayout run_temp_layout(int batch, int64_t num_points, int X, int Y
   L.bytes = o;
   return L;
 }
-static RunTempLayout run_temp_layout_geom(int batch, int64_t num_points, int X, int Y) {
-  return run_temp_layout(batch, num_points, X, Y, (int)ceil_div64(num_points, kSortTile) * kSortWarps, kRunWarpSlots);
-}
 static RunTempLayout run_temp_layout_rig(int batch, int N, int D, int H, int W, int X, int Y) {
   const int HB = (int)ceil_div64(H, kRunHB);
   const int64_t pairs = (int64_t)N * D * HB * W;
@@ -1133,7 +1005,7 @@ extern "C" int bevpool_runplan_sizes(int batch, int num_cams, int depth_bins, in
   if (rc) return rc;
   if (!plan_bytes || !temp_bytes) return BEVPOOL_E_ARG;
   *plan_bytes = plan_layout(batch, num_points, X, Y, true, plan_num_pairs(num_cams, depth_bins, feat_h, feat_w)).bytes;
-  *temp_bytes = run_temp_layout_geom(batch, num_points, X, Y).bytes;
+  *temp_bytes = run_temp_layout_rig(batch, num_cams, depth_bins, feat_h, feat_w, X, Y).bytes;
   return BEVPOOL_OK;
 }
 
@@ -1205,28 +1077,24 @@ extern "C" int bevpool_runplan_build(const int32_t *geom, int batch, int num_cam
   int rc = check_plan_dims(batch, num_points, X, Y);
   if (rc) return rc;
   if (!geom || !plan || !temp || Z <= 0) return BEVPOOL_E_ARG;
-  if (!aligned16(plan) || !aligned16(temp) || !aligned16(geom)) return BEVPOOL_E_ALIGN;
+  if (!aligned16(plan) || !aligned16(temp)) return BEVPOOL_E_ALIGN;
   if (batch > 65535) return BEVPOOL_E_RANGE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t cells = (int64_t)X * Y;
   const int64_t pairs = plan_num_pairs(num_cams, depth_bins, feat_h, feat_w);
   const PlanLayout PL = plan_layout(batch, num_points, X, Y, true, pairs);
-  const RunTempLayout TL = run_temp_layout_geom(batch, num_points, X, Y);
+  const RunTempLayout TL = run_temp_layout_rig(batch, num_cams, depth_bins, feat_h, feat_w, X, Y);
   char *pb = static_cast<char *>(plan), *tb = static_cast<char *>(temp);
-  const int T = (int)ceil_div64(num_points, kSortTile);
+  const int HB = (int)ceil_div64(feat_h, kRunHB);
+  const dim3 grid((unsigned)ceil_div64(pairs, kRigThreads), (unsigned)batch);
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl(plan_key_runs_kernel, dim3(T, batch), dim3(kSortThreads), 0, stream,
-      geom, num_points, X, Y, Z, reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(plan_key_rig_kernel<-1>, grid, dim3(kRigThreads), 0, stream, RigParams{}, geom, num_cams,
+      depth_bins, feat_h, feat_w, HB, X, Y, Z, num_points, reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
       reinterpret_cast<int32_t *>(pb + PL.off_run_code), reinterpret_cast<uint32_t *>(tb + TL.off_counts),
       reinterpret_cast<int32_t *>(tb + TL.off_head_cells), reinterpret_cast<int32_t *>(tb + TL.off_head_ids),
-      reinterpret_cast<int32_t *>(tb + TL.off_warp_count), reinterpret_cast<uint32_t *>(tb + TL.off_sample_total), T,
-      make_fastdiv((uint32_t)feat_w), make_fastdiv((uint32_t)feat_h), static_cast<PlanHeader *>(plan),
+      reinterpret_cast<int32_t *>(tb + TL.off_warp_count), reinterpret_cast<uint32_t *>(tb + TL.off_sample_total),
+      TL.slices_per_sample, TL.slot_cap, reinterpret_cast<int4 *>(pb + PL.off_pair_rec), static_cast<PlanHeader *>(plan),
       make_plan_header(kPlanKindRuns, batch, num_points, X, Y, Z)));
-  BEVPOOL_LAUNCH_CHECK();
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl(pair_records_kernel, dim3((unsigned)ceil_div64(pairs, 256), (unsigned)batch), dim3(256), 0, stream,
-      (const int32_t *)reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
-      (const int32_t *)reinterpret_cast<int32_t *>(pb + PL.off_run_code), num_cams, depth_bins, feat_h, feat_w,
-      (int)ceil_div64(feat_h, kRunHB), num_points, reinterpret_cast<int4 *>(pb + PL.off_pair_rec)));
   BEVPOOL_LAUNCH_CHECK();
   return run_plan_finish(TL, PL, batch, cells, num_cams, depth_bins, feat_h, feat_w, pb, tb, stream);
 }
@@ -1282,7 +1150,7 @@ extern "C" int bevpool_runplan_build_rig(const float *combine, const float *frus
   const dim3 grid((unsigned)ceil_div64(pairs, kRigThreads), (unsigned)batch);
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, TL.zero_bytes, stream));
   cudaError_t le = cudaSuccess;
-  BEVPOOL_RIG_DISPATCH(variant, (le = launch_pdl(plan_key_rig_kernel<V>, grid, dim3(kRigThreads), 0, stream, rp, num_cams,
+  BEVPOOL_RIG_DISPATCH(variant, (le = launch_pdl(plan_key_rig_kernel<V>, grid, dim3(kRigThreads), 0, stream, rp, (const int32_t *)nullptr, num_cams,
       depth_bins, feat_h, feat_w, HB, X, Y, Z, num_points, reinterpret_cast<int32_t *>(pb + PL.off_cell_of_point),
       reinterpret_cast<int32_t *>(pb + PL.off_run_code), reinterpret_cast<uint32_t *>(tb + TL.off_counts),
       reinterpret_cast<int32_t *>(tb + TL.off_head_cells), reinterpret_cast<int32_t *>(tb + TL.off_head_ids),
