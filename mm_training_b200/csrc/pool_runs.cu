@@ -34,18 +34,23 @@ static int env_int_runs(const char *name, int dflt) {
   return e && e[0] ? std::atoi(e) : dflt;
 }
 
-constexpr int kRaTW = 4;                     // image columns per CTA = one 16-byte segment
-constexpr int kRaDC = 16;                    // depth bins per staged chunk
-constexpr int kRaStages = 3;                 // chunks of (code, depth) in shared memory: one reduced, two in flight
-constexpr int kRaThreads = 256;
+constexpr int kRaTW = 4;                     // image columns per CTA = warps per CTA = one 16-byte depth segment
+constexpr int kRaDC = 16;                    // depth bins per staged chunk: 4 groups x 4 bins per warp
+constexpr int kRaStages = 3;                 // chunks of (depth, records) in shared memory: one reduced, two in flight
+constexpr int kRaThreads = 32 * kRaTW;
 constexpr int kRaZeroCells = 32;             // cells covered by the zeroed shared-memory buffer
+constexpr int kRaDepStride = kRaTW * kRunHB + 16;   // floats per bin of the transposed depth stage (see pool_bwd2.cu)
 
-// one (depth bin, column) pair of an 8-lane group: codes / depths of its 16 rows (lane l8 holds rows l8 and
-// l8 + 8), the group's kept-row and first-of-run masks
-struct RunCol {
-  int c_lo, c_hi;
-  float p_lo, p_hi;
-  unsigned km, hm;
+template <int NV2>
+struct RaSmem {
+  static constexpr int C = 16 * NV2;
+  static constexpr size_t off_ctx = 0;                                                   // float [row][column][channel]
+  static constexpr size_t off_dep = off_ctx + (size_t)kRunHB * kRaTW * C * 4;            // float4 [stage][bin][row] (4 columns), as copied
+  static constexpr size_t off_rec = off_dep + (size_t)kRaStages * kRaDC * kRunHB * 16;   // int4 [stage][bin][column] pair records
+  static constexpr size_t off_depT = off_rec + (size_t)kRaStages * kRaDC * kRaTW * 16;   // float [bin][kRaDepStride]: masked, [column][row]
+  static constexpr size_t off_zero = off_depT + (size_t)kRaDC * kRaDepStride * 4;        // kRaZeroCells * C zeros
+  static constexpr size_t off_bar = off_zero + (size_t)kRaZeroCells * C * 4;
+  static constexpr size_t bytes = off_bar + 16;
 };
 
 // In-place layout change of a TMA box of the NCHW context tensor, [channel][16 rows][4 columns], into pixel
@@ -77,28 +82,35 @@ __device__ __forceinline__ void nchw_box_to_rows(float *s_ctx, int tid) {
 }
 
 // ---- stage A ----------------------------------------------------------------------------------
-// CTA = (image, 4 columns x 16 rows, one of `d_split` depth ranges), walked in chunks of 32 depth bins.
-// warp = (column wl, 8 consecutive bins per round): every 8-lane group walks the rows of TWO
-// (bin, column) pairs, so one shared-memory read of a context row (one wavefront for the whole warp:
-// all four groups read the same row) feeds 8 depth (x) context products.
+// CTA = (image, 4 columns x one 16-row block, one of `d_split` depth ranges), walked in chunks of 16 depth bins;
+// 128 threads.  warp = image column; every 8-lane group reduces FOUR (bin, column) pairs at once, lane = channel
+// eighth: one shared-memory read of a context row eighth (2 LDS.128 + 1 LDS.64 at C = 80; the four groups read the
+// same addresses = one wavefront each) feeds 20 FFMA2.  Everything per-pair comes from the plan's 16-byte PAIR
+// RECORD (kept-row masks, slot of the pair's run, number of runs): the kernel reads no per-point index array and
+// does no voting.  The staging threads transpose the depths to [bin][column][row] and zero the rows that are not
+// kept, so the reduction loop is branch-free over the rows (4 depths = one LDS.128).  Pairs holding several runs
+// (tilted cameras, random geometry) take a per-row path that reads run_code from global memory.
 template <int NV2, bool kNchw>
 __global__ void __launch_bounds__(kRaThreads, 4)
 frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t *__restrict__ run_code,
-                      const float *__restrict__ depth, const float *__restrict__ ctx_nhwc, float *__restrict__ run_rows,
+                      const int4 *__restrict__ pair_rec, const float *__restrict__ depth,
+                      const float *__restrict__ ctx_nhwc, float *__restrict__ run_rows,
                       const int32_t *__restrict__ cell_start, float *__restrict__ out, int32_t *__restrict__ status,
                       int img0, int64_t cell_base, int64_t num_cells, int D, int H, int W, int d_split, int d_per_cta,
                       int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints) {
   pdl_wait();
   pdl_trigger();
+  using S = RaSmem<NV2>;
   constexpr int C = 16 * NV2, NREG = 2 * NV2;
   constexpr unsigned kFull = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char s_raw[];
-  float *s_ctx = reinterpret_cast<float *>(s_raw);                                  // [row][column][channel]
-  int4 (*s_code)[kRaDC][kRunHB] = reinterpret_cast<int4 (*)[kRaDC][kRunHB]>(s_ctx + kRunHB * kRaTW * C);   // [stage][bin][row] x 4 columns
-  float4 (*s_dep)[kRaDC][kRunHB] = reinterpret_cast<float4 (*)[kRaDC][kRunHB]>(s_code + kRaStages);
-  float *s_zero = reinterpret_cast<float *>(s_dep + kRaStages);                     // kRaZeroCells * C zeros
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_zero + kRaZeroCells * C);
-  const int tid = threadIdx.x, lane = tid & 31, l8 = lane & 7, grp = lane >> 3, warp = tid >> 5;
+  float *s_ctx = reinterpret_cast<float *>(s_raw + S::off_ctx);
+  float4 (*s_dep)[kRaDC][kRunHB] = reinterpret_cast<float4 (*)[kRaDC][kRunHB]>(s_raw + S::off_dep);
+  int4 (*s_rec)[kRaDC][kRaTW] = reinterpret_cast<int4 (*)[kRaDC][kRaTW]>(s_raw + S::off_rec);
+  float *s_depT = reinterpret_cast<float *>(s_raw + S::off_depT);
+  float *s_zero = reinterpret_cast<float *>(s_raw + S::off_zero);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_raw + S::off_bar);
+  const int tid = threadIdx.x, lane = tid & 31, l8 = lane & 7, grp = lane >> 3, wl = tid >> 5;
   int bid = blockIdx.x;
   const int ts = bid % d_split; bid /= d_split;
   const int th = bid % tiles_h; bid /= tiles_h;
@@ -148,7 +160,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
     const int64_t blocks = (num_cells + kRaZeroCells - 1) / kRaZeroCells;
     const int64_t per_cta = (blocks + gridDim.x - 1) / gridDim.x;
     const int64_t blk_begin = (int64_t)blockIdx.x * per_cta, blk_end = min(blocks, blk_begin + per_cta);
-    for (int64_t blk = blk_begin + warp; blk < blk_end; blk += kWarps) {
+    for (int64_t blk = blk_begin + wl; blk < blk_end; blk += kWarps) {
       const int64_t off = blk * kRaZeroCells;
       const int ncell = (int)min((int64_t)kRaZeroCells, num_cells - off);
       const int64_t c0 = cell_base + off;
@@ -171,43 +183,49 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
     if (issued_bulk) tma_store_commit();
   }
 
-  // staging role: thread = (bin sd, row sh) of a chunk, 4 columns
+  // staging role: a half-warp = the 16 rows of one bin; a thread stages bins sd and sd + 8.  Threads 0..63 also
+  // fetch the chunk's 16 x 4 pair records.
   const int sh = tid & 15, sd = tid >> 4;
   const bool srow = h0 + sh < H;
   const int64_t sbase = (int64_t)bn * D * HW + (int64_t)(h0 + sh) * W + w0;
   const int nchunks = (d_end - d_begin + kRaDC - 1) / kRaDC;
+  const int4 *rec_base = pair_rec + ((int64_t)bn * D * tiles_h + th) * W + w0;
+  const int64_t rec_bin_stride = (int64_t)tiles_h * W;
 
-  // (code, depth) segments of chunk c -> stage c % 3, as asynchronous 16-byte copies
-  auto issue_chunk = [&](int cidx) {
+  auto issue_chunk = [&](int cidx) {         // depth segments + pair records of chunk cidx -> stage cidx % 3
     if (cidx < nchunks) {
-      const int st = cidx % kRaStages, d = d_begin + cidx * kRaDC + sd;
-      int4 *dc = &s_code[st][sd][sh];
-      float4 *dd = &s_dep[st][sd][sh];
-      if (srow && d < d_end) {
-        const int64_t gp = sbase + (int64_t)d * HW;
-        if (vec) {
-          cp_async16(dc, run_code + gp);
-          cp_async16(dd, depth + gp);
+      const int st = cidx % kRaStages;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int bin = sd + 8 * pass, d = d_begin + cidx * kRaDC + bin;
+        float4 *dd = &s_dep[st][bin][sh];
+        if (srow && d < d_end) {
+          const int64_t gp = sbase + (int64_t)d * HW;
+          if (vec) {
+            cp_async16(dd, depth + gp);
+          } else {
+            float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w0 + 0 < W) pd.x = __ldg(depth + gp + 0);
+            if (w0 + 1 < W) pd.y = __ldg(depth + gp + 1);
+            if (w0 + 2 < W) pd.z = __ldg(depth + gp + 2);
+            if (w0 + 3 < W) pd.w = __ldg(depth + gp + 3);
+            *dd = pd;
+          }
         } else {
-          int4 pc = make_int4(kRunDropped, kRunDropped, kRunDropped, kRunDropped);
-          float4 pd = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (w0 + 0 < W) { pc.x = __ldg(run_code + gp + 0); pd.x = __ldg(depth + gp + 0); }
-          if (w0 + 1 < W) { pc.y = __ldg(run_code + gp + 1); pd.y = __ldg(depth + gp + 1); }
-          if (w0 + 2 < W) { pc.z = __ldg(run_code + gp + 2); pd.z = __ldg(depth + gp + 2); }
-          if (w0 + 3 < W) { pc.w = __ldg(run_code + gp + 3); pd.w = __ldg(depth + gp + 3); }
-          *dc = pc;
-          *dd = pd;
+          *dd = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else {
-        *dc = make_int4(kRunDropped, kRunDropped, kRunDropped, kRunDropped);
-        *dd = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (tid < kRaDC * kRaTW) {
+        const int bin = tid >> 2, col = tid & 3, d = d_begin + cidx * kRaDC + bin;
+        int4 *dr = &s_rec[st][bin][col];
+        if (d < d_end && w0 + col < W) cp_async16(dr, rec_base + (int64_t)d * rec_bin_stride + col);
+        else *dr = make_int4(-1, 0, -1, 0);
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    cp_async_commit();
   };
 
   const int64_t slot0 = __ldg(cell_start + cell_base);
-  const int wl = warp & 3, dh = warp >> 2;
   const float *ctx_col = s_ctx + wl * C;
   const uint64_t pol_rows = l2_policy_evict_last();
   auto store_run = [&](int64_t slot, const float (&acc)[NREG]) {
@@ -218,11 +236,6 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
       *status = kPlanStatusRowOverflow;      // the caller's run_rows scratch is smaller than the run count (stale max_runs hint)
     }
   };
-  auto warp_union = [&](unsigned m) -> unsigned {       // any-group union of a per-group mask (warp-uniform)
-    m |= __shfl_xor_sync(kFull, m, 8);
-    m |= __shfl_xor_sync(kFull, m, 16);
-    return m;
-  };
 
   issue_chunk(0);
   issue_chunk(1);
@@ -231,86 +244,103 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
     asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk cidx has landed (cidx + 1 may still be in flight)
     __syncthreads();                                        // ... for every thread; and chunk cidx - 1 is fully reduced
     issue_chunk(cidx + 2);                                  // into the stage chunk cidx - 1 just left
+    const int st = cidx % kRaStages;
+    // depths of the chunk transposed to [bin][column][row], zero for rows that are not kept
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int bin = sd + 8 * pass;
+      const float4 pd = s_dep[st][bin][sh];
+      const unsigned m0 = (unsigned)s_rec[st][bin][0].y, m1 = (unsigned)s_rec[st][bin][1].y;
+      const unsigned m2 = (unsigned)s_rec[st][bin][2].y, m3 = (unsigned)s_rec[st][bin][3].y;
+      float *dT = s_depT + bin * kRaDepStride + sh;
+      dT[0 * kRunHB] = ((m0 | (m0 >> 16)) >> sh) & 1u ? pd.x : 0.f;
+      dT[1 * kRunHB] = ((m1 | (m1 >> 16)) >> sh) & 1u ? pd.y : 0.f;
+      dT[2 * kRunHB] = ((m2 | (m2 >> 16)) >> sh) & 1u ? pd.z : 0.f;
+      dT[3 * kRunHB] = ((m3 | (m3 >> 16)) >> sh) & 1u ? pd.w : 0.f;
+    }
     if (!ctx_ready) {                                       // first chunk: the context tile must have landed
       mbar_wait(s_bar, 0);
       ctx_ready = true;
       if (kNchw) nchw_box_to_rows<C>(s_ctx, tid);
     }
-    const int st = cidx % kRaStages;
-    auto load_col = [&](int dl, RunCol &q) {
-      const int *cw = reinterpret_cast<const int *>(&s_code[st][dl][0]) + wl;
-      const float *pw = reinterpret_cast<const float *>(&s_dep[st][dl][0]) + wl;
-      q.c_lo = cw[4 * l8];
-      q.c_hi = cw[4 * (8 + l8)];
-      q.p_lo = pw[4 * l8];
-      q.p_hi = pw[4 * (8 + l8)];
-      const unsigned k_lo = __ballot_sync(kFull, q.c_lo != kRunDropped), k_hi = __ballot_sync(kFull, q.c_hi != kRunDropped);
-      const unsigned h_lo = __ballot_sync(kFull, q.c_lo >= 0), h_hi = __ballot_sync(kFull, q.c_hi >= 0);
-      q.km = ((k_lo >> (8 * grp)) & 0xffu) | (((k_hi >> (8 * grp)) & 0xffu) << 8);
-      q.hm = ((h_lo >> (8 * grp)) & 0xffu) | (((h_hi >> (8 * grp)) & 0xffu) << 8);
-    };
-    {
-      const int dl = dh * (kRaDC / 2) + 2 * grp;            // this group's bins: dl, dl + 1 (8 bins per warp)
-      RunCol a, b;
-      load_col(dl, a);
-      load_col(dl + 1, b);
-      const unsigned any = warp_union(a.km | b.km);
-      if (any == 0u) continue;
-      float acc_a[NREG], acc_b[NREG];
+    __syncthreads();                                        // transposed depths visible
+
+    // this group's four pairs: bins 4*grp .. 4*grp+3 of column wl
+    int4 rec[4];
+    unsigned km[4];
 #pragma unroll
-      for (int r = 0; r < NREG; ++r) acc_a[r] = acc_b[r] = 0.f;
-      const bool single = __popc(a.hm) <= 1 && __popc(b.hm) <= 1;
-      if (__all_sync(kFull, single)) {
-        // fast path (level camera): at most one run per (bin, column) pair -> no per-row bookkeeping
+    for (int p = 0; p < 4; ++p) {
+      rec[p] = s_rec[st][4 * grp + p][wl];
+      km[p] = ((unsigned)rec[p].y | ((unsigned)rec[p].y >> 16)) & 0xffffu;
+    }
+    unsigned any = km[0] | km[1] | km[2] | km[3];
+    any |= __shfl_xor_sync(kFull, any, 8);
+    any |= __shfl_xor_sync(kFull, any, 16);
+    if (any == 0u) continue;                                // warp-uniform: nothing kept in this column's 16 bins
+    const bool single = rec[0].w <= 1 && rec[1].w <= 1 && rec[2].w <= 1 && rec[3].w <= 1;
+    const float *dT = s_depT + (4 * grp) * kRaDepStride + wl * kRunHB;
+    if (__all_sync(kFull, single)) {
+      // fast path (level camera): one run per pair.  Branch-free over the rows: the depth of a row that is not kept is 0.
+      float acc[4][NREG];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int r = 0; r < NREG; ++r) acc[p][r] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRunHB / 4; ++k) {
+        if (((any >> (4 * k)) & 0xfu) == 0u) continue;      // warp-uniform
+        float4 dp[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) dp[p] = *reinterpret_cast<const float4 *>(dT + p * kRaDepStride + 4 * k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int h = 4 * k + j;
+          if (!((any >> h) & 1u)) continue;                 // warp-uniform
+          float v[NREG];
+          g8_lds_row<NV2>(ctx_col + h * (kRaTW * C), l8, v);
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            axpy_row<NREG>(acc[p], j == 0 ? dp[p].x : (j == 1 ? dp[p].y : (j == 2 ? dp[p].z : dp[p].w)), v);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (km[p]) store_run((int64_t)rec[p].z - slot0, acc[p]);
+    } else {
+      // general geometry: several runs per pair; walk the rows of one pair at a time with the run boundaries
+      // from run_code (first row of a run: its slot; continuation: kRunCont)
+#pragma unroll 1
+      for (int p = 0; p < 4; ++p) {
+        unsigned kmp = km[p];
+        unsigned any_p = kmp | __shfl_xor_sync(kFull, kmp, 8);
+        any_p |= __shfl_xor_sync(kFull, any_p, 16);
+        if (any_p == 0u) continue;                          // warp-uniform
+        const int d = d_begin + cidx * kRaDC + 4 * grp + p;
+        const int64_t gp0 = (int64_t)bn * D * HW + (int64_t)d * HW + (int64_t)h0 * W + w0 + wl;
+        float acc[NREG];
+#pragma unroll
+        for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
+        int64_t slot = -1;
 #pragma unroll
         for (int h = 0; h < kRunHB; ++h) {
-          if (!((any >> h) & 1u)) continue;                     // warp-uniform
-          const float da = __shfl_sync(kFull, h < 8 ? a.p_lo : a.p_hi, h & 7, 8);
-          const float db = __shfl_sync(kFull, h < 8 ? b.p_lo : b.p_hi, h & 7, 8);
-          if (((a.km | b.km) >> h) & 1u) {
+          if (!((any_p >> h) & 1u)) continue;               // warp-uniform
+          if ((kmp >> h) & 1u) {
+            const int cv = __ldg(run_code + gp0 + (int64_t)h * W);
+            const float dv = dT[p * kRaDepStride + h];
+            if (cv >= 0) {                                   // first row of a run
+              store_run(slot, acc);
+              if (slot >= 0) {
+#pragma unroll
+                for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
+              }
+              slot = (int64_t)cv - slot0;
+            }
             float v[NREG];
             g8_lds_row<NV2>(ctx_col + h * (kRaTW * C), l8, v);
-            if ((a.km >> h) & 1u) axpy_row<NREG>(acc_a, da, v);
-            if ((b.km >> h) & 1u) axpy_row<NREG>(acc_b, db, v);
+            axpy_row<NREG>(acc, dv, v);
           }
         }
-        // the run's slot sits in the code of its first row
-        const int ha = a.hm ? __ffs(a.hm) - 1 : 0, hb = b.hm ? __ffs(b.hm) - 1 : 0;
-        const int sa_lo = __shfl_sync(kFull, a.c_lo, ha & 7, 8), sa_hi = __shfl_sync(kFull, a.c_hi, ha & 7, 8);
-        const int sb_lo = __shfl_sync(kFull, b.c_lo, hb & 7, 8), sb_hi = __shfl_sync(kFull, b.c_hi, hb & 7, 8);
-        if (a.hm) store_run((int64_t)(ha < 8 ? sa_lo : sa_hi) - slot0, acc_a);
-        if (b.hm) store_run((int64_t)(hb < 8 ? sb_lo : sb_hi) - slot0, acc_b);
-      } else {
-        // general geometry: several runs per pair; walk the rows once per pair with explicit run boundaries
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const RunCol &q = pass == 0 ? a : b;
-          const unsigned any_q = warp_union(q.km);
-          float acc[NREG];
-#pragma unroll
-          for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
-          int64_t slot = -1;
-#pragma unroll
-          for (int h = 0; h < kRunHB; ++h) {
-            if (!((any_q >> h) & 1u)) continue;                 // warp-uniform
-            const int cv = __shfl_sync(kFull, h < 8 ? q.c_lo : q.c_hi, h & 7, 8);
-            const float dv = __shfl_sync(kFull, h < 8 ? q.p_lo : q.p_hi, h & 7, 8);
-            if ((q.km >> h) & 1u) {
-              if (cv >= 0) {                                     // first row of a run
-                store_run(slot, acc);
-                if (slot >= 0) {
-#pragma unroll
-                  for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
-                }
-                slot = (int64_t)cv - slot0;
-              }
-              float v[NREG];
-              g8_lds_row<NV2>(ctx_col + h * (kRaTW * C), l8, v);
-              axpy_row<NREG>(acc, dv, v);
-            }
-          }
-          store_run(slot, acc);
-        }
+        store_run(slot, acc);
       }
     }
   }
@@ -333,11 +363,12 @@ static int launch_stage_a(const CUtensorMap &ctx_map, const PlanView &pv, const 
   const int splits = (int)ceil_div64(D, d_per_cta);
   const int64_t ctas = (int64_t)nb * num_cams * tiles_w * tiles_h * splits;
   if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
-  const size_t smem = (size_t)kRunHB * kRaTW * C * 4 + (size_t)kRaStages * kRaDC * kRunHB * 32 + (size_t)kRaZeroCells * C * 4 + 16;
+  (void)C;
+  const size_t smem = RaSmem<NV2>::bytes;
   if (smem > 48 * 1024)
     BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2, kNchw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
-      ctx_map, pv.run_code, dp, cx, rr, pv.cell_start, out, status, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
+      ctx_map, pv.run_code, pv.pair_rec, dp, cx, rr, pv.cell_start, out, status, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
       tiles_w, capacity, vec, fill, hints));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
