@@ -397,12 +397,14 @@ grad_rows_kernel(const int32_t *__restrict__ cell_start, const E *__restrict__ g
 // Same contract as grad_rows_kernel (rows of occupied 32-cell tiles only).  A tile of 32 consecutive cells of
 // one BEV row is ONE tensor-map box of the NCHW gradient -- 32 x-cells x C channels, 128-byte rows -- landing in
 // shared memory as [channel][cell]; it is turned into [cell][channel] by a diagonal walk (lane l moves element
-// (channel c0 + l/2, cell l): reads hit 32 distinct banks, writes (16*cell + channel) mod 32 do too) and leaves
-// as ONE contiguous bulk store of 32 rows (32 * C * 4 bytes: the tile's rows are adjacent in the NHWC
-// buffer).  No LSU traffic to global memory at all; CTAs loop over tiles so that empty tiles (80 % of the
-// aiMotive grid) cost two cached loads, not a CTA launch.
+// (channel c0 + l/2, cell l): reads hit 32 distinct banks, writes (16*cell + channel) mod 32 do too at C = 80) and
+// leaves as ONE contiguous bulk store of 32 rows (32 * C * 4 bytes: the tile's rows are adjacent in the NHWC
+// buffer).  No LSU traffic to global memory at all.  A CTA owns every gridDim-th tile: it first finds the
+// occupied ones among them in ONE parallel round of cell_start loads (80 % of the aiMotive grid is empty), then
+// streams them through a 2-deep ring: the box of tile i+1 is in flight while tile i is transposed and stored.
 constexpr int kGtCells = 32;
 constexpr int kGtThreads = 128;
+constexpr int kGtStages = 2;
 template <int C>
 __global__ void __launch_bounds__(kGtThreads)
 grad_rows_tma_kernel(const __grid_constant__ CUtensorMap grad_map, const int32_t *__restrict__ cell_start,
@@ -410,45 +412,80 @@ grad_rows_tma_kernel(const __grid_constant__ CUtensorMap grad_map, const int32_t
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(128) unsigned char gt_raw[];
-  float *s_in = reinterpret_cast<float *>(gt_raw);                 // [C][32]
-  float *s_out = s_in + C * kGtCells;                              // [32][C]
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_out + C * kGtCells);
+  float *s_in = reinterpret_cast<float *>(gt_raw);                 // [stage][C][32]
+  float *s_out = s_in + kGtStages * C * kGtCells;                  // [stage][32][C]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_out + kGtStages * C * kGtCells);   // [stage]
+  int *s_list = reinterpret_cast<int *>(s_bar + kGtStages);        // occupied tiles of this CTA (as k: tile = blockIdx.x + k * gridDim.x)
+  __shared__ int s_count;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t tiles = (int64_t)batch * Y * tiles_x;
   if (tid == 0) {
-    mbar_init(s_bar, 1);
+    for (int i = 0; i < kGtStages; ++i) mbar_init(s_bar + i, 1);
     fence_proxy_async();
+    s_count = 0;
   }
   __syncthreads();
-  const int64_t tiles = (int64_t)batch * Y * tiles_x;
-  uint32_t phase = 0;
-  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const int tx = (int)(t % tiles_x);
-    const int64_t by = t / tiles_x;                                // b * Y + y
-    const int64_t c0 = by * X + (int64_t)tx * kGtCells;           // first cell (global row index)
-    const int ncell = min(kGtCells, X - tx * kGtCells);
-    if (__ldg(cell_start + c0 + ncell) == __ldg(cell_start + c0)) continue;      // CTA-uniform: nothing landed here
-    const int y = (int)(by % Y), b = (int)(by / Y);
-    if (tid == 0) {
-      mbar_expect_tx(s_bar, (uint32_t)(C * kGtCells * 4));
-      tma_load_4d(s_in, &grad_map, tx * kGtCells, y, 0, b, s_bar);
+  // ---- occupied tiles of this CTA, in ascending order (a warp-ordered compaction)
+  const int per_cta = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  for (int k0 = 0; k0 < per_cta; k0 += kGtThreads) {
+    const int k = k0 + tid;
+    bool occ = false;
+    if (k < per_cta) {
+      const int64_t t = blockIdx.x + (int64_t)k * gridDim.x;
+      const int tx = (int)(t % tiles_x);
+      const int64_t c0 = (t / tiles_x) * X + (int64_t)tx * kGtCells;
+      const int ncell = min(kGtCells, X - tx * kGtCells);
+      occ = __ldg(cell_start + c0 + ncell) != __ldg(cell_start + c0);
     }
-    mbar_wait(s_bar, phase);
-    phase ^= 1u;
-    // diagonal transpose: warp w handles channel offsets c0 = w, w + 4, ...
-    for (int cb = warp; cb < C; cb += kGtThreads / 32) {
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    for (int w = 0; w < kGtThreads / 32; ++w) {                    // warps append in order
+      if (w == warp) {
+        const int base = s_count;
+        if (occ) s_list[base + __popc(m & ((1u << lane) - 1u))] = k;
+        __syncwarp();
+        if (lane == 0) s_count = base + __popc(m);
+      }
+      __syncthreads();
+    }
+  }
+  const int n = s_count;
+  auto issue = [&](int i) {                                        // box of the i-th occupied tile -> stage i % 2
+    if (i < n && tid == 0) {
+      const int64_t t = blockIdx.x + (int64_t)s_list[i] * gridDim.x;
+      const int tx = (int)(t % tiles_x);
+      const int64_t by = t / tiles_x;
+      const int st = i % kGtStages;
+      mbar_expect_tx(s_bar + st, (uint32_t)(C * kGtCells * 4));
+      tma_load_4d(s_in + st * C * kGtCells, &grad_map, tx * kGtCells, (int)(by % Y), 0, (int)(by / Y), s_bar + st);
+    }
+  };
+  issue(0);
+  for (int i = 0; i < n; ++i) {
+    const int st = i % kGtStages;
+    issue(i + 1);                                                  // its stage was drained in iteration i - 1
+    const int64_t t = blockIdx.x + (int64_t)s_list[i] * gridDim.x;
+    const int tx = (int)(t % tiles_x);
+    const int64_t c0 = (t / tiles_x) * X + (int64_t)tx * kGtCells;
+    const int ncell = min(kGtCells, X - tx * kGtCells);
+    mbar_wait(s_bar + st, (uint32_t)((i / kGtStages) & 1));
+    // the bulk store that last read this output stage (iteration i - 2) must have drained it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    const float *in = s_in + st * C * kGtCells;
+    float *outp = s_out + st * C * kGtCells;
+    for (int cb = warp; cb < C; cb += kGtThreads / 32) {           // diagonal transpose
       int c = cb + (lane >> 1);
       c = c >= C ? c - C : c;
-      s_out[lane * C + c] = s_in[c * kGtCells + lane];
+      outp[lane * C + c] = in[c * kGtCells + lane];
     }
     fence_proxy_async();
-    __syncthreads();
+    __syncthreads();                                               // s_out[st] complete; s_in[st] free for tile i + 2
     if (tid == 0) {
-      tma_store_1d(rows + c0 * C, s_out, (uint32_t)(ncell * C * 4));
+      tma_store_1d(rows + c0 * C, outp, (uint32_t)(ncell * C * 4));
       tma_store_commit();
-      tma_store_wait_read();                                       // s_out is rewritten by the next tile
     }
-    __syncthreads();
   }
+  if (tid == 0) tma_store_wait_read();                             // shared memory must outlive the stores reading it
 }
 
 // ---- (batch, R, Cc) -> (batch, Cc, R) tiled transpose ----------------------------------
@@ -712,10 +749,12 @@ extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, vo
     if ((rc = make_tensor_map_f32(&gmap, grad_out_nchw, 4, dims, strides, box))) return rc;
     const int tiles_x = (int)ceil_div64(X, kGtCells);
     const int64_t tiles = (int64_t)batch * Y * tiles_x;
-    const size_t smem = (size_t)2 * channels * kGtCells * 4 + 16;
-    const int per_sm = (int)((size_t)200 * 1024 / (smem + 1024));
-    int64_t ctas = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 12 ? 12 : per_sm));
+    const int per_sm_cap = (int)((size_t)220 * 1024 / ((size_t)2 * kGtStages * channels * kGtCells * 4 + 2048));
+    const int per_sm = per_sm_cap < 1 ? 1 : (per_sm_cap > 8 ? 8 : per_sm_cap);
+    int64_t ctas = (int64_t)sm_count() * per_sm;
     ctas = ctas > tiles ? tiles : ctas;
+    const int64_t list_len = ceil_div64(tiles, ctas);
+    const size_t smem = (size_t)2 * kGtStages * channels * kGtCells * 4 + kGtStages * 8 + (size_t)list_len * 4 + 16;
     cudaError_t le = cudaSuccess;
 #define BEVPOOL_GT_LAUNCH(CC)                                                                                          \
     do {                                                                                                               \

@@ -39,7 +39,8 @@ constexpr int kRaDC = 16;                    // depth bins per staged chunk: 4 g
 constexpr int kRaStages = 3;                 // chunks of (depth, records) in shared memory: one reduced, two in flight
 constexpr int kRaThreads = 32 * kRaTW;
 constexpr int kRaZeroCells = 32;             // cells covered by the zeroed shared-memory buffer
-constexpr int kRaDepStride = kRaTW * kRunHB + 16;   // floats per bin of the transposed depth stage (see pool_bwd2.cu)
+constexpr int kRaDepStride = kRaTW * kRunHB + 8;    // floats per bin of the transposed depth stage: the four groups of a warp read
+                                                    // bins grp, grp + 4, ... -> 16-byte segments 8 banks apart, no conflicts
 
 template <int NV2>
 struct RaSmem {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void nchw_box_to_rows(float *s_ctx, int tid) {
 
 // ---- stage A ----------------------------------------------------------------------------------
 // CTA = (image, 4 columns x one 16-row block, one of `d_split` depth ranges), walked in chunks of 16 depth bins;
-// 128 threads.  warp = image column; every 8-lane group reduces FOUR (bin, column) pairs at once, lane = channel
+// 128 threads.  warp = image column; every 8-lane group reduces FOUR (bin, column) pairs at once (bins grp + 4p), lane = channel
 // eighth: one shared-memory read of a context row eighth (2 LDS.128 + 1 LDS.64 at C = 80; the four groups read the
 // same addresses = one wavefront each) feeds 20 FFMA2.  Everything per-pair comes from the plan's 16-byte PAIR
 // RECORD (kept-row masks, slot of the pair's run, number of runs): the kernel reads no per-point index array and
@@ -149,40 +150,6 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
     }
   }
 
-  // ---- zero-fill of this CTA's share of the empty BEV cells.  A block of 32 cells that is entirely
-  // empty (most of the grid) is ONE 10-KB TMA bulk store from the zero buffer; a mixed block is
-  // written with ordinary 16-byte stores (many small bulk copies would serialise in the copy engine
-  // and delay the context tiles queued behind them).  One block per warp per round, so the
-  // cell_start loads of a CTA's blocks are all in flight together.
-  bool issued_bulk = false;
-  if (fill) {
-    constexpr int kWarps = kRaThreads / 32, C4 = C / 4;
-    const int64_t blocks = (num_cells + kRaZeroCells - 1) / kRaZeroCells;
-    const int64_t per_cta = (blocks + gridDim.x - 1) / gridDim.x;
-    const int64_t blk_begin = (int64_t)blockIdx.x * per_cta, blk_end = min(blocks, blk_begin + per_cta);
-    for (int64_t blk = blk_begin + wl; blk < blk_end; blk += kWarps) {
-      const int64_t off = blk * kRaZeroCells;
-      const int ncell = (int)min((int64_t)kRaZeroCells, num_cells - off);
-      const int64_t c0 = cell_base + off;
-      const int cs = __ldg(cell_start + c0 + min(lane, ncell)), ce = __ldg(cell_start + c0 + min(lane + 1, ncell));
-      const unsigned em = __ballot_sync(kFull, lane < ncell && ce == cs);
-      if (ncell == kRaZeroCells && em == kFull) {
-        if (lane == 0) {
-          if (hints) tma_store_1d_hint(out + c0 * C, s_zero, kRaZeroCells * C * 4, l2_policy_evict_first());
-          else tma_store_1d(out + c0 * C, s_zero, kRaZeroCells * C * 4);
-          issued_bulk = true;
-        }
-      } else if (em) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
-#pragma unroll 4
-        for (int i = lane; i < ncell * C4; i += 32)
-          if ((em >> (i / C4)) & 1u) stg_stream_f4(o4 + i, z);
-      }
-    }
-    if (issued_bulk) tma_store_commit();
-  }
-
   // staging role: a half-warp = the 16 rows of one bin; a thread stages bins sd and sd + 8.  Threads 0..63 also
   // fetch the chunk's 16 x 4 pair records.
   const int sh = tid & 15, sd = tid >> 4;
@@ -239,6 +206,58 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
 
   issue_chunk(0);
   issue_chunk(1);
+
+  // ---- zero-fill of this CTA's share of the empty BEV cells (after the first chunks' copies are in flight, so
+  // that its own dependent loads overlap with them).  A block of 32 cells that is entirely empty (most of the
+  // grid) is ONE 10-KB TMA bulk store from the zero buffer; a mixed block is written with ordinary 16-byte stores
+  // (many small bulk copies would serialise in the copy engine and delay the context tiles queued behind them).
+  // A warp takes every 4th block of the CTA's share; the cell_start entries of up to 4 of its blocks are fetched
+  // before the first is examined.
+  bool issued_bulk = false;
+  if (fill) {
+    constexpr int kWarps = kRaThreads / 32, C4 = C / 4, kAhead = 4;
+    const int64_t blocks = (num_cells + kRaZeroCells - 1) / kRaZeroCells;
+    const int64_t per_cta = (blocks + gridDim.x - 1) / gridDim.x;
+    const int64_t blk_begin = (int64_t)blockIdx.x * per_cta, blk_end = min(blocks, blk_begin + per_cta);
+    for (int64_t blk0 = blk_begin + wl; blk0 < blk_end; blk0 += kWarps * kAhead) {
+      int cs[kAhead], ce[kAhead];
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) {
+        const int64_t blk = blk0 + (int64_t)a * kWarps;
+        cs[a] = ce[a] = 0;
+        if (blk < blk_end) {
+          const int64_t off = blk * kRaZeroCells;
+          const int ncell = (int)min((int64_t)kRaZeroCells, num_cells - off);
+          cs[a] = __ldg(cell_start + cell_base + off + min(lane, ncell));
+          ce[a] = __ldg(cell_start + cell_base + off + min(lane + 1, ncell));
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < kAhead; ++a) {
+        const int64_t blk = blk0 + (int64_t)a * kWarps;
+        if (blk >= blk_end) break;                           // warp-uniform
+        const int64_t off = blk * kRaZeroCells;
+        const int ncell = (int)min((int64_t)kRaZeroCells, num_cells - off);
+        const int64_t c0 = cell_base + off;
+        const unsigned em = __ballot_sync(kFull, lane < ncell && ce[a] == cs[a]);
+        if (ncell == kRaZeroCells && em == kFull) {
+          if (lane == 0) {
+            if (hints) tma_store_1d_hint(out + c0 * C, s_zero, kRaZeroCells * C * 4, l2_policy_evict_first());
+            else tma_store_1d(out + c0 * C, s_zero, kRaZeroCells * C * 4);
+            issued_bulk = true;
+          }
+        } else if (em) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
+#pragma unroll 4
+          for (int i = lane; i < ncell * C4; i += 32)
+            if ((em >> (i / C4)) & 1u) stg_stream_f4(o4 + i, z);
+        }
+      }
+    }
+    if (issued_bulk) tma_store_commit();
+  }
+
   bool ctx_ready = false;
   for (int cidx = 0; cidx < nchunks; ++cidx) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");   // chunk cidx has landed (cidx + 1 may still be in flight)
@@ -265,12 +284,12 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
     }
     __syncthreads();                                        // transposed depths visible
 
-    // this group's four pairs: bins 4*grp .. 4*grp+3 of column wl
+    // this group's four pairs: bins grp, grp + 4, grp + 8, grp + 12 of column wl
     int4 rec[4];
     unsigned km[4];
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      rec[p] = s_rec[st][4 * grp + p][wl];
+      rec[p] = s_rec[st][grp + 4 * p][wl];
       km[p] = ((unsigned)rec[p].y | ((unsigned)rec[p].y >> 16)) & 0xffffu;
     }
     unsigned any = km[0] | km[1] | km[2] | km[3];
@@ -278,7 +297,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
     any |= __shfl_xor_sync(kFull, any, 16);
     if (any == 0u) continue;                                // warp-uniform: nothing kept in this column's 16 bins
     const bool single = rec[0].w <= 1 && rec[1].w <= 1 && rec[2].w <= 1 && rec[3].w <= 1;
-    const float *dT = s_depT + (4 * grp) * kRaDepStride + wl * kRunHB;
+    const float *dT = s_depT + grp * kRaDepStride + wl * kRunHB;       // pair p: + 4 * p * kRaDepStride
     if (__all_sync(kFull, single)) {
       // fast path (level camera): one run per pair.  Branch-free over the rows: the depth of a row that is not kept is 0.
       float acc[4][NREG];
@@ -291,7 +310,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
         if (((any >> (4 * k)) & 0xfu) == 0u) continue;      // warp-uniform
         float4 dp[4];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) dp[p] = *reinterpret_cast<const float4 *>(dT + p * kRaDepStride + 4 * k);
+        for (int p = 0; p < 4; ++p) dp[p] = *reinterpret_cast<const float4 *>(dT + 4 * p * kRaDepStride + 4 * k);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int h = 4 * k + j;
@@ -315,7 +334,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
         unsigned any_p = kmp | __shfl_xor_sync(kFull, kmp, 8);
         any_p |= __shfl_xor_sync(kFull, any_p, 16);
         if (any_p == 0u) continue;                          // warp-uniform
-        const int d = d_begin + cidx * kRaDC + 4 * grp + p;
+        const int d = d_begin + cidx * kRaDC + grp + 4 * p;
         const int64_t gp0 = (int64_t)bn * D * HW + (int64_t)d * HW + (int64_t)h0 * W + w0 + wl;
         float acc[NREG];
 #pragma unroll
@@ -326,7 +345,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
           if (!((any_p >> h) & 1u)) continue;               // warp-uniform
           if ((kmp >> h) & 1u) {
             const int cv = __ldg(run_code + gp0 + (int64_t)h * W);
-            const float dv = dT[p * kRaDepStride + h];
+            const float dv = dT[4 * p * kRaDepStride + h];
             if (cv >= 0) {                                   // first row of a run
               store_run(slot, acc);
               if (slot >= 0) {
