@@ -276,6 +276,10 @@ def main():
     ap.add_argument('--e2e-chunk', type=int, default=4, help='frames per chunk of the host-buffer pipeline')
     ap.add_argument('--plan', default='runs', choices=['runs', 'points'],
                     help="what the plan sorts: 'runs' (vertical point runs, two-stage forward) or 'points'")
+    ap.add_argument('--geometry', default='auto', choices=['auto', 'rig', 'geom'],
+                    help="where the plan's cell indices come from: 'rig' = built on the device from sensor2ego @ inv(intrin) "
+                         "(no geom_xyz tensor; needs an accumulation order proven bit-exact on this device), 'geom' = from the "
+                         "reference's int32 geom_xyz tensor, 'auto' = rig when proven")
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip e2e / cpu / reference-CUDA side measurements')
     args = ap.parse_args()
@@ -343,11 +347,35 @@ def main():
     probe = build_plan(geom, vn, frustum=frustum)      # eager, once: the run count sizes the scratch rows
     max_runs = probe.num_sorted if probe.mode == 'runs' else None
     plan_mode = probe.mode
+
+    # geometry source of the plan: the rig path replaces lss_fpn.py:328-361,461-462 as well --
+    # the (B, N, D, H, W, 3) tensors are never made; combine = sensor2ego @ inverse(intrin) (B*N 4x4 matrices) stays in
+    # torch, outside the captured step (torch.inverse is not capturable), everything per point is in the key kernel
+    from mm_training_b200.ops.voxel_pooling import LiftSplatGeometry, PoolingPlan, rig_variant
+    variant, rig_exact, lsg, combine = None, None, None, None
+    if args.geometry != 'geom' and plan_mode == 'runs':
+        variant = rig_variant(dev)
+        if variant is None and args.geometry == 'rig':
+            raise SystemExit('no rig variant reproduces torch on this device')
+    if variant is not None:
+        lsg = LiftSplatGeometry.from_config(cfg, dev)
+        s2e, intrin = synthetic.camera_rig_mats(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=1 + rank)
+        combine = lsg.combine(s2e, intrin)
+        rp = PoolingPlan.from_rig(lsg, combine, variant)
+        rig_exact = bool(torch.equal(rp.cell_of_point, probe.cell_of_point) and torch.equal(rp.sorted_ids, probe.sorted_ids)
+                         and torch.equal(rp.run_code, probe.run_code))
+        assert rig_exact, 'rig plan differs from the geom_xyz plan'
+        del rp
     del probe
 
+    def make_plan():
+        # cold plan every step: cell index + sort are redone (no sync: max_runs is known)
+        if variant is not None:
+            return PoolingPlan.from_rig(lsg, combine, variant, max_runs)
+        return build_plan(geom, vn, frustum=frustum, max_runs=max_runs)
+
     def step():
-        # cold plan every step: cell index + sort are redone from geom_xyz (no sync: max_runs is known)
-        plan = build_plan(geom, vn, frustum=frustum, max_runs=max_runs)
+        plan = make_plan()
         out = fused_forward(plan, depth, ctx)          # NCHW context read through a TMA tensor map
         gd, gc = fused_backward(plan, go, depth, ctx)  # NCHW incoming gradient; grad_context written NCHW like ctx
         return plan, out, gd, gc
@@ -448,7 +476,8 @@ def main():
 
     # ---- per-kernel timing (CUDA events on the launching stream), same inputs, warm
     stages = {}
-    stages['plan_build'] = time_cuda(lambda: build_plan(geom, vn, frustum=frustum, max_runs=max_runs), 20, 3)
+    stages['plan_build'] = time_cuda(make_plan, 20, 3)
+    stages['plan_build_from_geom_xyz'] = time_cuda(lambda: build_plan(geom, vn, frustum=frustum, max_runs=max_runs), 20, 3)
     stages['fused_forward(+ctx transpose)'] = time_cuda(lambda: fused_forward(plan, depth, ctx), 20, 3)
     stages['fused_backward(+grad transpose)'] = time_cuda(lambda: fused_backward(plan, go, depth, ctx), 20, 3)
     ctx_nhwc = ctx.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
@@ -460,7 +489,7 @@ def main():
     # ---- the same step when the caller keeps context and gradient channels_last (zero-copy layouts: no
     # context / context-gradient transposes, no gradient-row pass); reported beside the headline, not as it
     def step_cl():
-        p = build_plan(geom, vn, frustum=frustum, max_runs=max_runs)
+        p = make_plan()
         o = fused_forward(p, depth, ctx_nhwc)
         return o, fused_backward(p, go_nhwc, depth, ctx_nhwc)
     cl_ms = None
@@ -496,6 +525,9 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': dict(workload, launch='cuda_graph_replay' if graph is not None else 'eager',
                            kept_points_per_frame=kept_per_frame, plan=plan_mode,
+                           geometry=('rig: cell indices derived on the device from sensor2ego @ inv(intrin), variant %d, bit-exact '
+                                     'vs the reference ops (checked in this run)' % variant) if variant is not None
+                           else 'geom_xyz: int32 tensor made by the reference ops',
                            sorted_entries_per_frame=(max_runs / B if max_runs else kept_per_frame)),
             'roofline': roofline,
             'step_roofline': {'algorithmic_bytes_per_frame': bytes_['step'], 'achieved': step_gbs, 'unit': 'GB/s',

@@ -324,8 +324,9 @@ plan_key_msd_kernel(const int32_t *__restrict__ geom, int64_t num_points, int X,
 //                             writes sorted_ids / sorted_cells and each head's slot into run_code
 // The result does not depend on the order the atomics happened in: a deterministic, stable sort.
 __device__ __forceinline__ int cell_of_xyz(int x, int y, int z, int X, int Y, int Z) {
-  // reference bounds test, voxel_pooling_forward_cuda.cu:24; z gates only (:32-33)
-  return (x >= 0 && x < X && y >= 0 && y < Y && z >= 0 && z < Z) ? y * X + x : -1;
+  // reference bounds test, voxel_pooling_forward_cuda.cu:24; z gates only (:32-33).  0 <= v < N as ONE unsigned compare.
+  const bool kept = ((unsigned)x < (unsigned)X) & ((unsigned)y < (unsigned)Y) & ((unsigned)z < (unsigned)Z);
+  return kept ? y * X + x : -1;
 }
 
 // ==== run plan straight from the camera rig (no geom_xyz tensor) ===================================
@@ -380,13 +381,30 @@ __device__ __forceinline__ float rig_dot4(const float (&m)[4], float px, float p
 
 // trunc((e - lo) / vs) with IEEE semantics.  The quotient by reciprocal is within 2 ulp of the true quotient:
 // when it is farther than that from every integer it truncates to the same value, otherwise (a fraction of a
-// percent of the points) the exact division decides.
+// percent of the points) the exact division decides.  rig_quantise3 does the three coordinates of a point with ONE
+// branch to the exact path.
 __device__ __forceinline__ int rig_quantise(float e, float lo, float vs, float inv_vs) {
   const float t = __fsub_rn(e, lo);
   const float qf = __fmul_rn(t, inv_vs);
   const float fr = fabsf(qf - rintf(qf));
   if (fr > 1e-3f && fabsf(qf) < 4194304.f) return __float2int_rz(qf);
   return __float2int_rz(__fdiv_rn(t, vs));
+}
+__device__ __forceinline__ void rig_quantise3(float ex, float ey, float ez, const RigParams &rp, int &ix, int &iy, int &iz) {
+  const float tx = __fsub_rn(ex, rp.lo[0]), ty = __fsub_rn(ey, rp.lo[1]), tz = __fsub_rn(ez, rp.lo[2]);
+  const float qx = __fmul_rn(tx, rp.inv_vs[0]), qy = __fmul_rn(ty, rp.inv_vs[1]), qz = __fmul_rn(tz, rp.inv_vs[2]);
+  const float fx = fabsf(qx - rintf(qx)), fy = fabsf(qy - rintf(qy)), fz = fabsf(qz - rintf(qz));
+  const float big = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+  // (NaN compares false -> exact path)
+  if (fminf(fminf(fx, fy), fz) > 1e-3f && big < 4194304.f) {
+    ix = __float2int_rz(qx);
+    iy = __float2int_rz(qy);
+    iz = __float2int_rz(qz);
+  } else {
+    ix = __float2int_rz(__fdiv_rn(tx, rp.vs[0]));
+    iy = __float2int_rz(__fdiv_rn(ty, rp.vs[1]));
+    iz = __float2int_rz(__fdiv_rn(tz, rp.vs[2]));
+  }
 }
 
 constexpr int kRigThreads = 256;
@@ -430,7 +448,7 @@ plan_key_rig_kernel(RigParams rp, const int32_t *__restrict__ geom, int num_cams
   }
   const int64_t cells = (int64_t)X * Y;
   const int64_t region = ((int64_t)b * warps_per_sample + (int64_t)blockIdx.x * (kRigThreads / 32) + warp) * slot_cap;
-  const int64_t col_base = (int64_t)b * num_points + ((int64_t)n * D + d) * H * W + w;
+  const int col_base = (int)((int64_t)b * num_points + ((int64_t)n * D + d) * H * W + w);     // B * Np < 2^31 (host check)
   const unsigned lt = (1u << lane) - 1u;
   uint32_t filled = 0;                 // heads this warp has written so far (warp-uniform)
   int prev = -2, primary = -1, nheads = 0;
@@ -441,18 +459,17 @@ plan_key_rig_kernel(RigParams rp, const int32_t *__restrict__ geom, int num_cams
     const bool act = valid && h < H;
     int cell = -1, code = kRunDropped;
     if (act) {
-      const int64_t gp = col_base + (int64_t)h * W;
+      const int gp = col_base + h * W;
       int ix, iy, iz;
       if (kVariant >= 0) {
         const float py = __fmul_rn(__ldg(rp.fy + h), dd);
-        ix = rig_quantise(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m0, px, py, dd), rp.lo[0], rp.vs[0], rp.inv_vs[0]);
-        iy = rig_quantise(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m1, px, py, dd), rp.lo[1], rp.vs[1], rp.inv_vs[1]);
-        iz = rig_quantise(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
+        rig_quantise3(rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m0, px, py, dd), rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m1, px, py, dd),
+                      rig_dot4<(kVariant < 0 ? 0 : kVariant)>(m2, px, py, dd), rp, ix, iy, iz);
       } else {
-        const int32_t *g = geom + gp * 3;
-        ix = ldg_stream_i32(g);
-        iy = ldg_stream_i32(g + 1);
-        iz = ldg_stream_i32(g + 2);
+        const int32_t *g = geom + (int64_t)gp * 3;
+        ix = __ldg(g);
+        iy = __ldg(g + 1);
+        iz = __ldg(g + 2);
       }
       cell = cell_of_xyz(ix, iy, iz, X, Y, Z);
       code = cell < 0 ? kRunDropped : (cell != prev ? cell : kRunCont);
@@ -472,7 +489,7 @@ plan_key_rig_kernel(RigParams rp, const int32_t *__restrict__ geom, int num_cams
       const int64_t pos = region + filled + __popc(bal & lt);
       head_cells[pos] = code;
       // bit 31: this head is the first kept row of its pair (K4 then records its slot in the pair record)
-      head_ids[pos] = (int32_t)(col_base + (int64_t)h * W) | (keptm == (1u << r) ? (int32_t)0x80000000 : 0);
+      head_ids[pos] = (col_base + h * W) | (keptm == (1u << r) ? (int32_t)0x80000000 : 0);
       atomicAdd(counts + (int64_t)b * cells + code, 1u);
     }
     filled += __popc(bal);

@@ -227,19 +227,19 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
 
   cp_async_wait_1();
   __syncthreads();                           // meta(0) visible; the context box is no longer needed
-  int live_cur = __syncthreads_or(prep(0));
-  issue_rows(0, live_cur);
+  prep(0);
+  issue_rows(0, 1);
 
   float *part_w = s_part + wl * (kBcMC * 4 * kBcPartStride);          // this warp's partial-dot buffer
   for (int c = 0; c < nchunks; ++c) {
     // in flight here: meta(c+1), rows(c)
     cp_async_wait_all();
     __syncthreads();
-    const int live_next = __syncthreads_or(prep(c + 1));
-    issue_rows(c + 1, live_next);
+    prep(c + 1);                             // (its outputs are read after the next iteration's barrier)
+    issue_rows(c + 1, 1);
     issue_meta(c + 2);                       // into the stage prep(c) consumed an iteration ago
 
-    if (live_cur) {
+    {
       const int st = c & 1;
       // masks of the chunk's 16 bins for this warp's column: lane b holds bin b's
       const uint32_t m_lane = lane < kBcDC ? s_mask[(st * kBcDC + lane) * kBcTW + wl] : 0u;
@@ -385,9 +385,8 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
       if (srow && d < D)
         stg_stream_f4(reinterpret_cast<float4 *>(grad_depth + sbase + (int64_t)d * HW),
                       make_float4(rp[0], rp[kBcTH], rp[2 * kBcTH], rp[3 * kBcTH]));
-      if (live_cur) rp[0] = rp[kBcTH] = rp[2 * kBcTH] = rp[3 * kBcTH] = 0.f;
+      rp[0] = rp[kBcTH] = rp[2 * kBcTH] = rp[3 * kBcTH] = 0.f;
     }
-    live_cur = live_next;
   }
   cp_async_wait_all();
 

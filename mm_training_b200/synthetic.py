@@ -28,11 +28,9 @@ def cam2ego(yaw_deg: float, t=(1.5, 0.0, 1.6)) -> torch.Tensor:
     return m
 
 
-def camera_rig(cfg: CameraPoolConfig, batch_size: int, device='cpu', yaw_jitter_deg: float = 0.0,
-               seed: int = 1):
-    """Returns (geom_xyz int32 (B,N,D,H,W,3), voxel_num int64[3]) for the rig of ``cfg``.
-    ``yaw_jitter_deg`` > 0 draws a per-sample yaw offset U(-j, j) (the "cold plan" runs)."""
-    frustum = geometry.create_frustum(cfg.final_dim, cfg.downsample_factor, cfg.d_bound).to(device)
+def camera_rig_mats(cfg: CameraPoolConfig, batch_size: int, device='cpu', yaw_jitter_deg: float = 0.0, seed: int = 1):
+    """(sensor2ego_mat, intrin_mat), both (B, N, 4, 4) float32: what ``LSSFPN.forward`` receives in ``mats_dict``
+    (``lss_fpn.py:469-474``).  ``yaw_jitter_deg`` > 0 draws a per-sample yaw offset U(-j, j) (the "cold plan" runs)."""
     k = torch.eye(4)
     k[0, 0] = cfg.focal_px
     k[1, 1] = cfg.focal_px
@@ -46,6 +44,15 @@ def camera_rig(cfg: CameraPoolConfig, batch_size: int, device='cpu', yaw_jitter_
         mats.append(torch.stack([cam2ego(y + j) for y in cfg.cam_yaws_deg]))
     s2e = torch.stack(mats).to(device)
     intrin = k[None, None].repeat(batch_size, n, 1, 1).to(device)
+    return s2e, intrin
+
+
+def camera_rig(cfg: CameraPoolConfig, batch_size: int, device='cpu', yaw_jitter_deg: float = 0.0,
+               seed: int = 1):
+    """Returns (geom_xyz int32 (B,N,D,H,W,3), voxel_num int64[3]) for the rig of ``cfg``: the reference's own
+    geometry ops (``mm_training_b200.geometry``) applied to ``camera_rig_mats``."""
+    frustum = geometry.create_frustum(cfg.final_dim, cfg.downsample_factor, cfg.d_bound).to(device)
+    s2e, intrin = camera_rig_mats(cfg, batch_size, device, yaw_jitter_deg, seed)
     voxel_size, voxel_coord, voxel_num = geometry.voxel_buffers(cfg.x_bound, cfg.y_bound, cfg.z_bound)
     pts = geometry.get_geometry(frustum, s2e, intrin)
     geom = geometry.quantise_geometry(pts, voxel_coord.to(device), voxel_size.to(device))
