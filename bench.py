@@ -227,11 +227,12 @@ def run_sweep(dev, peak_gbs, seed=7):
     return rows_out
 
 
-def run_lidar_side(dev, peak_gbs, sweeps: int = 8):
-    """Side measurement (not the headline metric): ``sweeps`` synthetic 200k-point long-range sweeps
-     through voxelize (+ fused HardSimpleVFE mean) and pillar scatter, and the
-    serial CPU restatement of mmcv's hard_voxelize on one sweep (mmcv's CPU kernel is single-threaded)."""
-    import numpy as np
+def run_lidar_side(dev, peak_gbs, sweeps: int = 32):
+    """Side measurement (not the headline metric; BASELINE.json configs[2]): ``sweeps`` synthetic 200k-point long-range
+    sweeps through hard voxelization + fused HardSimpleVFE mean + pillar scatter.  Three ways:
+    the mmdet3d-style call (exact-size tensors: one D2H sync for the voxel counts), the same work with padded
+    outputs (no sync) eagerly, and that replayed as one CUDA graph (the headline of this block); plus the serial
+    CPU restatement of mmcv's hard_voxelize on one sweep (mmcv's CPU kernel is single-threaded)."""
     from mm_training_b200.configs import CFG_3
     from mm_training_b200.ops.voxelize import Voxelization, pillar_scatter, voxelize
     v = CFG_3
@@ -240,14 +241,29 @@ def run_lidar_side(dev, peak_gbs, sweeps: int = 8):
     layer = Voxelization(list(v.voxel_size), list(v.point_cloud_range), v.max_num_points, v.max_voxels).eval()
     gx, gy, gz = (int(g) for g in layer.grid_size.tolist())
 
-    def run():
+    def run_exact():                                      # mmdet3d semantics: exact-size tensors (one D2H sync)
         voxels, num_points, coors, mean = voxelize(clouds, layer, mean_features=v.vfe_features)
-        canvas = pillar_scatter(mean, coors, sweeps, (gz, gy, gx))
+        canvas = pillar_scatter(mean, coors, sweeps, (gz, gy, gx), unique_coors=True)
         return voxels, canvas
-    voxels, canvas = run()
+
+    def run_padded():                                     # no sync: padded outputs + fused scatter
+        return voxelize(clouds, layer, mean_features=v.vfe_features, padded=True, scatter=True)
+    voxels, canvas = run_exact()
+    pad = run_padded()
     torch.cuda.synchronize()
+    assert torch.equal(pad[4], canvas) and torch.equal(pad[0][:voxels.shape[0]], voxels)
     M = voxels.shape[0] / sweeps
-    med, mn = time_cuda(run, 10, 3)                      # includes the one D2H sync of the voxel counts
+    exact_med, _ = time_cuda(run_exact, 10, 3)
+    eager_med, _ = time_cuda(run_padded, 10, 3)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        run_padded()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = run_padded()                               # noqa: F841
+    med, mn = time_cuda(g.replay, 20, 3)
     F, T = v.num_point_features, v.max_num_points
     vox_bytes = 4 * F * v.points_per_sweep + 4 * F * T * M + 20 * M
     sc_bytes = 4 * v.vfe_features * M + 16 * M + 4 * v.vfe_features * gz * gy * gx
@@ -256,10 +272,16 @@ def run_lidar_side(dev, peak_gbs, sweeps: int = 8):
     t0 = time.perf_counter()
     vr.hard_voxelize_c(clouds_np[0], list(v.voxel_size), list(v.point_cloud_range), T, v.max_voxels)
     cpu_s = time.perf_counter() - t0
+    del g, keep
     return {'workload': v.name, 'sweeps_per_step': sweeps, 'ms_per_step': med, 'sweeps_per_s': sweeps / (med * 1e-3),
             'points_per_s': sweeps * v.points_per_sweep / (med * 1e-3), 'voxels_per_sweep': M,
             'algorithmic_bytes_per_sweep': vox_bytes + sc_bytes, 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peak_gbs,
-            'what': 'voxelize(list of sweeps, mean_features=5) + pillar_scatter to (B, 5, 256, 2048), incl. 1 D2H sync',
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': peak_gbs, 'unit': 'GB/s', 'frac': gbs / peak_gbs,
+                         'bytes': 'SURVEY.md 8(d): 4*F*Np + 4*F*T*M + 20*M (voxelizer) + 4*Cv*M + 16*M + 4*Cv*gz*gy*gx (scatter) per sweep'},
+            'what': 'voxelize(list of sweeps, mean_features=5, padded=True, scatter=True): hard voxelization + HardSimpleVFE mean '
+                    '+ pillar scatter to (B, 5, 256, 2048) in one native call, no host sync, CUDA graph replay',
+            'eager_no_sync_ms': eager_med, 'mmdet3d_style_exact_size_ms': exact_med,
+            'parity': 'bit-exact vs oracle/hard_voxelize_ref.c (our restatement of mmcv 1.7.0; parity unpinned by the reference)',
             'cpu_hard_voxelize': {'sweeps_per_s': 1.0 / cpu_s, 'cores': 1, 'kind': 'port',
                                   'sample': '1 sweep, serial C restatement of mmcv hard_voxelize (oracle/)'}}
 

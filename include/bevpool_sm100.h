@@ -87,6 +87,18 @@ int bevpool_backward(const void *plan, const void *grad_out_nhwc, void *grad_fea
                      int dtype, int batch, int64_t num_points, int channels,
                      int num_voxel_x, int num_voxel_y, void *stream);
 
+/* The reference's native entry point in one call: same argument list as
+ * voxel_pooling_forward_kernel_launcher (ops/voxel_pooling/src/voxel_pooling_forward_cuda.cu:38-42, declared at
+ * voxel_pooling_forward.cpp:21-22) = plan + pos_memo + forward.  Scratch comes from cudaMallocAsync on `stream`
+ * (the one entry point that allocates: the reference signature has no workspace argument).  The library also
+ * exports the C++ symbol `voxel_pooling_forward_kernel_launcher(int x6, const int*, const float*, float*, int*,
+ * cudaStream_t)` itself, so the reference's voxel_pooling_forward.cpp links against libbevpool_sm100 unchanged.
+ * output_features (B, Y, X, C) is fully written (no pre-zeroing needed), pos_memo (B, Np, 3) fully written.        */
+int bevpool_voxel_pooling_forward_launcher(int batch_size, int num_points, int num_channels, int num_voxel_x,
+                                           int num_voxel_y, int num_voxel_z, const int *geom_xyz,
+                                           const float *input_features, float *output_features, int *pos_memo,
+                                           void *stream);
+
 /* ---- fused op: depth (x) context outer product never materialised ----------------
  * Replaces layers/backbones/lss_fpn.py:441-464 + the op.  Points are enumerated
  * (b, n, d, h, w) like the reference's (B, N, D, H, W, C) tensor, Np = N*D*H*W.
@@ -210,8 +222,15 @@ int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t r
  *     num_points (batch*max_voxels) int32
  *     voxel_base device int32[batch + 1] (written): row offsets; [batch] = total voxel count M
  *     voxel_mean optional (batch*max_voxels, mean_features) float32 = HardSimpleVFE, or NULL
- *   temp: bevvox_temp_bytes() bytes of scratch.                                          */
-int bevvox_temp_bytes(int batch, int64_t total_points, int max_voxels, int max_points,
+ *   temp: bevvox_temp_bytes() bytes of scratch.
+ * Grids of up to 2^26 cells per batch (the aiMotive pillar grid has 2^19 per sample) use a dense first-point table
+ * like mmcv's CPU kernel, larger ones a hash table; the outputs are identical.  `voxels` and `num_points` are fully
+ * overwritten (rows beyond voxel_base[batch] are zero on the dense path).  mean_features <= 16.
+ * bevvox_hard_voxelize_scatter (dense path only) takes the clouds either concatenated or as a DEVICE array of `batch`
+ * per-sample base pointers (points == NULL; the reference passes a list of tensors: no concatenation pass) and, with
+ * canvas != NULL, also writes the dense canvas (batch, mean_features, gz, gy, gx) of the fused HardSimpleVFE mean --
+ * voxelize -> VFE -> scatter of models/bev_depth.py:181-183 in one call.                                               */
+int bevvox_temp_bytes(int batch, int64_t total_points, const int *grid_host, int max_voxels, int max_points,
                       size_t *temp_bytes);
 int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int batch,
                          int64_t total_points, int64_t max_sample_points, int num_features,
@@ -219,6 +238,12 @@ int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int
                          const int *grid_host, int max_points, int max_voxels, float *voxels,
                          int32_t *coors, int32_t *num_points, int32_t *voxel_base,
                          float *voxel_mean, int mean_features, void *temp, void *stream);
+int bevvox_hard_voxelize_scatter(const float *points, const float *const *sample_ptrs,
+                                 const int32_t *sample_offsets, int batch, int64_t total_points,
+                                 int64_t max_sample_points, int num_features, const float *voxel_size_host,
+                                 const float *range_host, const int *grid_host, int max_points, int max_voxels,
+                                 float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_base,
+                                 float *voxel_mean, int mean_features, float *canvas, void *temp, void *stream);
 /* mmcv dynamic voxelization: coors (num_points, 3) int32 [z, y, x], -1 for out-of-range points */
 int bevvox_dynamic_voxelize(const float *points, int64_t num_points, int num_features,
                             const float *voxel_size_host, const float *range_host,
@@ -226,7 +251,9 @@ int bevvox_dynamic_voxelize(const float *points, int64_t num_points, int num_fea
 
 /* pillar scatter: voxel_features (M, C), coors (M, 4) [b, z, y, x] -> canvas (B, C, nz, ny, nx)
  * (== (B, C*nz, ny, nx)); every canvas element is written exactly once (no pre-zeroing).
- * index_map: scratch int32 (B*nz*ny*nx).  backward = gather of grad_canvas at coors.        */
+ * index_map: scratch int32 (B*nz*ny*nx), or NULL when the caller guarantees unique coordinates (the output of hard
+ * voxelization): then the canvas is zero-filled at DRAM speed and every (voxel, channel) is one store.
+ * backward = gather of grad_canvas at coors.                                                 */
 int pillar_scatter_forward(const void *voxel_features, const int32_t *coors, int64_t num_voxels,
                            int channels, int dtype, int batch, int nz, int ny, int nx,
                            void *canvas, int32_t *index_map, void *stream);

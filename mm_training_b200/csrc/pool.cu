@@ -15,6 +15,7 @@
 #include "pool_g8.cuh"
 #include "tma.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -806,4 +807,49 @@ extern "C" int bevpool_transpose(const void *in, void *out, int dtype, int batch
   }
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
+}
+
+
+// ==== the reference's own native entry point =========================================================================
+// ops/voxel_pooling/src/voxel_pooling_forward.cpp:21-22 declares, and :34 calls,
+//   void voxel_pooling_forward_kernel_launcher(int batch_size, int num_points, int num_channels, int num_voxel_x,
+//        int num_voxel_y, int num_voxel_z, const int *geom_xyz, const float *input_features,
+//        float *output_features, int *pos_memo, cudaStream_t stream);
+// (defined at voxel_pooling_forward_cuda.cu:38-56).  Exporting the same C++ symbol lets the reference's extension
+// link against this library instead of its own .cu with no source change.  One call = plan + pos_memo + forward.
+// The signature has no workspace argument, so the scratch buffers come from the stream-ordered allocator
+// (cudaMallocAsync / cudaFreeAsync: no synchronisation, capturable) -- the one place the library allocates.
+// Differences from the reference launcher: every cell of output_features is WRITTEN (the reference accumulates into
+// a buffer the caller pre-zeroes: identical result for the reference's caller, voxel_pooling.py:37-38), every row of
+// pos_memo is written ((b, y, x) or -1; the reference leaves the caller's -1 prefill), and a CUDA error is returned
+// / printed instead of exit(-1) (voxel_pooling_forward_cuda.cu:52-55).
+extern "C" int bevpool_voxel_pooling_forward_launcher(int batch_size, int num_points, int num_channels, int num_voxel_x,
+                                                      int num_voxel_y, int num_voxel_z, const int *geom_xyz,
+                                                      const float *input_features, float *output_features, int *pos_memo,
+                                                      void *stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  size_t plan_bytes = 0, temp_bytes = 0, ws_bytes = 0;
+  int rc = bevpool_plan_sizes(batch_size, num_points, num_voxel_x, num_voxel_y, &plan_bytes, &temp_bytes);
+  if (rc) return rc;
+  if ((rc = bevpool_forward_workspace_bytes(num_channels, &ws_bytes))) return rc;
+  const size_t a_plan = 0, a_temp = align_up(plan_bytes, 256), a_ws = a_temp + align_up(temp_bytes, 256);
+  char *scratch = nullptr;
+  BEVPOOL_RETURN_IF_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), a_ws + align_up(ws_bytes, 256), stream));
+  rc = bevpool_plan_build(geom_xyz, batch_size, num_points, num_voxel_x, num_voxel_y, num_voxel_z, scratch + a_plan,
+                          scratch + a_temp, stream);
+  if (!rc && pos_memo) rc = bevpool_plan_pos_memo(scratch + a_plan, batch_size, num_points, num_voxel_x, num_voxel_y, pos_memo, stream);
+  if (!rc) rc = bevpool_forward(scratch + a_plan, input_features, output_features, BEVPOOL_F32, batch_size, num_points,
+                                num_channels, num_voxel_x, num_voxel_y, scratch + a_ws, stream);
+  const cudaError_t fe = cudaFreeAsync(scratch, stream);
+  return rc ? rc : (int)fe;
+}
+
+void voxel_pooling_forward_kernel_launcher(int batch_size, int num_points, int num_channels, int num_voxel_x,
+                                           int num_voxel_y, int num_voxel_z, const int *geom_xyz,
+                                           const float *input_features, float *output_features, int *pos_memo,
+                                           cudaStream_t stream) {
+  const int rc = bevpool_voxel_pooling_forward_launcher(batch_size, num_points, num_channels, num_voxel_x, num_voxel_y,
+                                                        num_voxel_z, geom_xyz, input_features, output_features, pos_memo, stream);
+  if (rc) std::fprintf(stderr, "libbevpool_sm100: voxel_pooling_forward_kernel_launcher failed: %s (code %d)\n",
+                       bevpool_error_string(rc), rc);
 }

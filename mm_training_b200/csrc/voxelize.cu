@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include "scan.cuh"
 
+#include <cstdlib>
+
 namespace bevpool {
 
 constexpr unsigned long long kEmptyKey = ~0ull;
@@ -232,6 +234,308 @@ __global__ void scatter_backward_kernel(const T *__restrict__ grad_canvas, const
   grad_feats[e] = v;
 }
 
+// ==== dense-grid path (grids that fit a per-cell table: the aiMotive pillar grid is 2048 x 256 x 1) =================
+// The hash table is replaced by what mmcv's own CPU kernel uses, a dense cell -> first-point table, and the
+// pipeline shrinks to 4 kernels with no per-voxel index lists and no per-point prefix array:
+//   A vox_cell_kernel      points staged through shared memory with fully coalesced 4-byte loads (a point row is
+//                          F*4 = 20 bytes: no wider aligned access exists), global cell id per point,
+//                          warp-aggregated atomicMin -> first point of every cell
+//   B vox_scan_kernel      per sample: "first point of its cell" flags computed on the fly + decoupled look-back scan
+//                          = voxel numbering in point order; the creating point publishes vid_of_cell[cell] and
+//                          cell_of_vid[sample][vid]
+//   C vox_claim_kernel     per kept point: cell -> voxel number -> chain of atomicMax on the voxel's slot list
+//                          (max_points words holding 0x7fffffff - index, zero = empty: the list ends up holding the
+//                          max_points smallest indices in ascending order whatever the interleaving).  The lists are
+//                          a compact array that stays in L2 -- atomics on the padded voxel tensor itself (15 x F
+//                          floats per row, far larger than L2) ran at DRAM random-access speed, 4x slower
+//   D vox_finalize_kernel  one thread per voxel row: slot list -> point rows, count, coordinates, HardSimpleVFE mean
+//                          in slot order and, optionally, its pillar scatter into the dense canvas
+// `voxels` and the canvas are zeroed by cudaMemsetAsync (DRAM-speed fills: 93 % of a voxel tensor is padding), so
+// only real points are ever written by a kernel.  The clouds may be given as one concatenated tensor or as a device
+// array of per-sample pointers (no torch.cat of the batch).
+constexpr int kVcThreads = 256;
+constexpr int kVoxMaxF = 16;
+constexpr int32_t kVoxIdxBias = 0x7fffffff;          // slot word = kVoxIdxBias - point index  (> 0; 0 = empty)
+
+struct VoxPoints {                                   // point i of sample b (i global, begin = offsets[b])
+  const float *cat;                                  // concatenated (total, F), or
+  const float *const *per_sample;                    // device array of B base pointers
+  __device__ __forceinline__ const float *row(int b, int begin, int i, int F) const {
+    return per_sample ? per_sample[b] + (int64_t)(i - begin) * F : cat + (int64_t)i * F;
+  }
+};
+
+constexpr int kVcPer = 4;                          // points per thread: independent chains in flight, 4x fewer CTAs
+__global__ void __launch_bounds__(kVcThreads)
+vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
+                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell) {
+  extern __shared__ float s_pts[];                 // kVcPer * kVcThreads * F floats
+  const int b = blockIdx.y;
+  const int begin = offsets[b], end = offsets[b + 1];
+  const int tile0 = begin + blockIdx.x * (kVcThreads * kVcPer);
+  if (tile0 >= end) return;
+  const int npts = min(kVcThreads * kVcPer, end - tile0);
+  const float *src = pts.row(b, begin, tile0, F);
+  for (int e = threadIdx.x; e < npts * F; e += kVcThreads) s_pts[e] = ldg_stream_f32(src + e);
+  __syncthreads();
+  int gcell[kVcPer];
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) {
+    const int p = k * kVcThreads + threadIdx.x;     // consecutive lanes = consecutive points (index order inside a warp)
+    gcell[k] = -1;
+    if (p < npts) {
+      int x, y, z;
+      if (point_to_cell(s_pts + p * F, g, x, y, z)) gcell[k] = (int)((int64_t)b * cells + ((int64_t)z * g.gy + y) * g.gx + x);
+      point_gcell[tile0 + p] = gcell[k];
+    }
+  }
+  // one atomic per distinct cell of the warp: the lowest lane of a match group holds the lowest index
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) {
+    const unsigned peers = __match_any_sync(0xffffffffu, gcell[k]);
+    if (gcell[k] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(first + gcell[k], tile0 + k * kVcThreads + (int)threadIdx.x);
+  }
+}
+
+// Per SAMPLE (blockIdx.y) exclusive scan, in point order, of flag(i) = "i is the first point of its cell" = the voxel
+// number of every cell-creating point, which publishes it: vid_of_cell[global cell] = vid and cell_of_vid[b][vid] =
+// global cell (vid < max_voxels only).  The sample's number of distinct cells goes to totals[b].  One decoupled
+// look-back chain per sample (a single chain over the whole batch is latency-bound on its tile hand-offs).
+static __global__ void __launch_bounds__(kScanThreads)
+vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
+                const int32_t *__restrict__ first, int32_t *__restrict__ vid_of_cell, int32_t *__restrict__ cell_of_vid,
+                int max_voxels, uint32_t *__restrict__ totals, unsigned long long *status, unsigned int *tickets,
+                int tiles_per_sample) {
+  __shared__ uint32_t s_warp[kScanThreads / 32];
+  __shared__ uint32_t s_tile, s_prefix;
+  const int b = blockIdx.y;
+  const int begin = offsets[b], n = offsets[b + 1] - begin;
+  if (n == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) totals[b] = 0u;
+    return;
+  }
+  if ((int64_t)blockIdx.x * kScanTile >= n) return;      // tiles beyond this sample
+  if (threadIdx.x == 0) s_tile = atomicAdd(tickets + b, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long *st_b = status + (int64_t)b * tiles_per_sample;
+  const int warp_base = (int)tile * kScanTile + warp * 512;
+  int gcs[4][4];
+  uint4 v[4];
+  uint32_t excl[4];
+  uint32_t run = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int idx = warp_base + r * 128 + lane * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gcs[r][k] = idx + k < n ? point_gcell[begin + idx + k] : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int idx = warp_base + r * 128 + lane * 4;
+    uint32_t f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = (gcs[r][k] >= 0 && first[gcs[r][k]] == begin + idx + k) ? 1u : 0u;
+    v[r] = make_uint4(f[0], f[1], f[2], f[3]);
+    const uint32_t s = f[0] + f[1] + f[2] + f[3];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    excl[r] = run + incl - s;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) s_warp[warp] = run;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = lane < kScanThreads / 32 ? s_warp[lane] : 0u;
+    uint32_t incl = w;
+#pragma unroll
+    for (int o = 1; o < kScanThreads / 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, kScanThreads / 32 - 1);
+    if (lane < kScanThreads / 32) s_warp[lane] = incl - w;
+    uint32_t exclusive = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(st_b, kScanPrefix | total);
+    } else {
+      if (lane == 0) st_volatile_u64(st_b + tile, kScanAggregate | total);
+      int64_t look = (int64_t)tile - 1;
+      while (true) {
+        const int64_t idx = look - lane;
+        unsigned long long st;
+        do {
+          st = idx >= 0 ? ld_volatile_u64(st_b + idx) : kScanPrefix;
+        } while (__any_sync(0xffffffffu, (st >> 32) == 0ull));
+        const unsigned pm = __ballot_sync(0xffffffffu, (st >> 32) == 2ull);
+        const int firstp = pm ? __ffs(pm) - 1 : 32;
+        uint32_t contrib = lane <= firstp ? (uint32_t)(st & 0xffffffffull) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        exclusive += contrib;
+        if (pm) break;
+        look -= 32;
+      }
+      if (lane == 0) st_volatile_u64(st_b + tile, kScanPrefix | (uint64_t)(exclusive + total));
+    }
+    if (lane == 0) {
+      s_prefix = exclusive;
+      if ((int64_t)(tile + 1) * kScanTile >= n) totals[b] = exclusive + total;      // the sample's last tile
+    }
+  }
+  __syncthreads();
+  const uint32_t base = s_prefix + s_warp[warp];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    uint32_t o[4];
+    o[0] = base + excl[r];
+    o[1] = o[0] + v[r].x;
+    o[2] = o[1] + v[r].y;
+    o[3] = o[2] + v[r].z;
+    const uint32_t fl[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (fl[k]) {                                        // a creating point: o[k] is its cell's voxel number
+        vid_of_cell[gcs[r][k]] = (int32_t)o[k];
+        if (o[k] < (uint32_t)max_voxels) cell_of_vid[(int64_t)b * max_voxels + o[k]] = gcs[r][k];
+      }
+    }
+  }
+}
+
+// voxel_base[b] = rows of the samples before b (their voxel counts capped at max_voxels); one warp
+__global__ void vox_dense_base_kernel(const uint32_t *__restrict__ totals, int batch, int max_voxels,
+                                      int32_t *__restrict__ voxel_base) {
+  int run = 0;                                          // (lane 0 keeps the running base; batch is small)
+  for (int b0 = 0; b0 < batch; b0 += 32) {
+    const int b = b0 + (int)threadIdx.x;
+    const int v = b < batch ? min((int)totals[b], max_voxels) : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)threadIdx.x >= o) incl += t;
+    }
+    if (b < batch) voxel_base[b] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (threadIdx.x == 0) voxel_base[batch] = run;
+}
+
+__global__ void __launch_bounds__(256)
+vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
+                 const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base, int max_voxels,
+                 int max_points, int32_t *__restrict__ lists) {
+  const int b = blockIdx.y;
+  const int begin = offsets[b], end = offsets[b + 1];
+  const int i0 = begin + blockIdx.x * (256 * kVcPer) + threadIdx.x;
+  if (i0 - (int)threadIdx.x >= end) return;
+  const int base = voxel_base[b];
+  int gc[kVcPer], vid[kVcPer];
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) gc[k] = i0 + 256 * k < end ? point_gcell[i0 + 256 * k] : -1;
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) vid[k] = gc[k] >= 0 ? vid_of_cell[gc[k]] : max_voxels;
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) {
+    if (vid[k] >= max_voxels) continue;                  // out of range, or voxel cap: the whole cell is dropped
+    int *slot0 = lists + (int64_t)(base + vid[k]) * max_points;
+    int v = kVoxIdxBias - (i0 + 256 * k);
+    int old = atomicMax(slot0, v);
+    if (old == 0) continue;                              // first point of the voxel so far: done (the common case)
+    v = old < v ? old : v;                               // carry the later point to the next slot
+    // once the last slot holds an earlier point this one can never enter
+    if (max_points == 1 || *reinterpret_cast<volatile int *>(slot0 + (max_points - 1)) > v) continue;
+    for (int t = 1; t < max_points; ++t) {
+      old = atomicMax(slot0 + t, v);
+      if (old == 0) break;
+      v = old < v ? old : v;
+    }
+  }
+}
+
+// One thread per row of the padded output (batch * max_voxels rows): rows beyond the voxel count get num_points = 0
+// (their point slots were zeroed by the memset); a live row finds its sample (binary search in voxel_base), its
+// coordinates (cell_of_vid) and walks its slots: index word -> point row copied over the word, running sums for the
+// HardSimpleVFE mean in slot order, count = number of filled slots.
+__global__ void __launch_bounds__(256)
+vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
+                    const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists, int batch, int max_voxels,
+                    int max_points, float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
+                    const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
+                    float *__restrict__ canvas) {
+  extern __shared__ int s_vb[];                           // voxel_base, batch + 1 entries
+  for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
+  __syncthreads();
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (int64_t)batch * max_voxels) return;
+  if (row >= s_vb[batch]) {
+    num_points[row] = 0;
+    return;
+  }
+  int lo = 0, hi = batch;                                 // sample b: s_vb[b] <= row < s_vb[b + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_vb[mid] <= row) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int begin = offsets[b];
+  const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
+  const int64_t c = (int64_t)gc - (int64_t)b * cells;
+  const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+  reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
+  float *vrow = voxels + row * max_points * F;
+  const int32_t *list = lists + row * max_points;
+  float sum[kVoxMaxF];
+#pragma unroll
+  for (int k = 0; k < kVoxMaxF; ++k) sum[k] = 0.f;
+  int cnt = 0;
+  int word = list[0];
+  while (word != 0) {
+    float *dst = vrow + (int64_t)cnt * F;
+    const float *src = pts.row(b, begin, kVoxIdxBias - word, F);
+    ++cnt;
+    word = cnt < max_points ? list[cnt] : 0;              // next slot's word, in flight behind this slot's point
+    float val[kVoxMaxF];
+#pragma unroll
+    for (int k = 0; k < kVoxMaxF; ++k)
+      if (k < F) val[k] = __ldg(src + k);
+#pragma unroll
+    for (int k = 0; k < kVoxMaxF; ++k) {
+      if (k < F) dst[k] = val[k];
+      if (k < mean_features) sum[k] += val[k];
+    }
+  }
+  num_points[row] = cnt;
+  if (voxel_mean || canvas) {
+#pragma unroll
+    for (int k = 0; k < kVoxMaxF; ++k) {
+      if (k >= mean_features) break;
+      const float m = sum[k] / (float)cnt;
+      if (voxel_mean) voxel_mean[row * mean_features + k] = m;
+      if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
+    }
+  }
+}
+
+// pillar scatter for UNIQUE coordinates (what hard voxelization produces): canvas pre-zeroed, one thread per element
+template <typename T>
+__global__ void scatter_unique_kernel(const T *__restrict__ feats, const int32_t *__restrict__ coors, int64_t M, int C,
+                                      int batch, int nz, int ny, int nx, T *__restrict__ canvas) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M * C) return;
+  const int64_t m = e / C;
+  const int c = (int)(e - m * C);
+  const int4 co = reinterpret_cast<const int4 *>(coors)[m];
+  if (co.x < 0 || co.x >= batch || co.y < 0 || co.y >= nz || co.z < 0 || co.z >= ny || co.w < 0 || co.w >= nx) return;
+  canvas[((((int64_t)co.x * C + c) * nz + co.y) * ny + co.z) * nx + co.w] = feats[e];
+}
+
 struct VoxTemp {
   size_t off_scan, off_counts, zero_bytes;   // [0, zero_bytes) memset 0
   size_t off_keys;                           // memset 0xff
@@ -260,8 +564,40 @@ static VoxTemp vox_temp_layout(int batch, int64_t total_points, int max_voxels, 
   return L;
 }
 
+// dense mode: first-point table + voxel-number table over all cells of the batch (int32 each), point -> global cell ids
+struct VoxDenseTemp {
+  size_t off_status, off_tickets, off_lists, zero_bytes;   // [0, zero_bytes) memset 0 (scan status words, tickets, slot lists)
+  size_t off_first, first_bytes;                // memset 0x7f
+  size_t off_vid, off_gcell, off_cell_of_vid, off_totals, bytes;
+  int tiles_per_sample;
+};
+constexpr int64_t kVoxDenseMaxCells = 1ll << 26;          // cells of the whole batch (2 x 256 MB of tables); larger grids hash
+static bool vox_dense_ok(int batch, const int *grid) {
+  const int64_t cells = (int64_t)grid[0] * grid[1] * grid[2];
+  const char *e = std::getenv("BEVVOX_FORCE_HASH");          // tests: exercise the hash path on small grids
+  const bool forced_hash = e && e[0] == '1';
+  return !forced_hash && cells > 0 && (int64_t)batch * cells <= kVoxDenseMaxCells;
+}
+static VoxDenseTemp vox_dense_layout(int batch, int64_t total_points, int max_voxels, int max_points, const int *grid) {
+  VoxDenseTemp L{};
+  const size_t cells = (size_t)grid[0] * grid[1] * grid[2];
+  L.tiles_per_sample = (int)scan_num_tiles(total_points > 0 ? total_points : 1);    // (the largest sample is bounded by the total)
+  size_t o = 0;
+  L.off_status = o;  o = align_up(o + (size_t)batch * L.tiles_per_sample * 8, 256);
+  L.off_tickets = o; o = align_up(o + (size_t)batch * 4, 256);
+  L.off_lists = o;   o = align_up(o + (size_t)batch * max_voxels * max_points * 4, 256);
+  L.zero_bytes = o;
+  L.off_first = o;  L.first_bytes = align_up((size_t)batch * cells * 4, 256); o += L.first_bytes;
+  L.off_vid = o;    o += align_up((size_t)batch * cells * 4, 256);
+  L.off_gcell = o;  o = align_up(o + (size_t)total_points * 4, 256);
+  L.off_cell_of_vid = o; o = align_up(o + (size_t)batch * max_voxels * 4, 256);
+  L.off_totals = o; o = align_up(o + (size_t)batch * 4, 256);
+  L.bytes = o > 256 ? o : 256;
+  return L;
+}
+
 static int check_vox_args(int batch, int64_t total_points, int F, int max_voxels, int max_points) {
-  if (batch <= 0 || batch > 65535 || total_points < 0 || F < 3 || max_voxels <= 0 || max_points <= 0) return BEVPOOL_E_ARG;
+  if (batch <= 0 || batch > 65535 || total_points < 0 || F < 3 || F > kVoxMaxF || max_voxels <= 0 || max_points <= 0) return BEVPOOL_E_ARG;
   if (total_points >= 0x7f7f7f7f || (int64_t)batch * max_voxels * max_points >= INT32_MAX) return BEVPOOL_E_RANGE;
   return BEVPOOL_OK;
 }
@@ -278,32 +614,83 @@ static VoxGeom make_geom(const float *vs, const float *range, const int *grid) {
 
 using namespace bevpool;
 
-extern "C" int bevvox_temp_bytes(int batch, int64_t total_points, int max_voxels, int max_points,
+extern "C" int bevvox_temp_bytes(int batch, int64_t total_points, const int *grid_host, int max_voxels, int max_points,
                                  size_t *temp_bytes) {
   int rc = check_vox_args(batch, total_points, 3, max_voxels, max_points);
   if (rc) return rc;
-  if (!temp_bytes) return BEVPOOL_E_ARG;
-  *temp_bytes = vox_temp_layout(batch, total_points, max_voxels, max_points).bytes;
+  if (!temp_bytes || !grid_host) return BEVPOOL_E_ARG;
+  *temp_bytes = vox_dense_ok(batch, grid_host) ? vox_dense_layout(batch, total_points, max_voxels, max_points, grid_host).bytes
+                                               : vox_temp_layout(batch, total_points, max_voxels, max_points).bytes;
   return BEVPOOL_OK;
 }
 
-extern "C" int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int batch,
-                                    int64_t total_points, int64_t max_sample_points, int num_features,
-                                    const float *voxel_size_host, const float *range_host,
-                                    const int *grid_host, int max_points, int max_voxels, float *voxels,
-                                    int32_t *coors, int32_t *num_points, int32_t *voxel_base,
-                                    float *voxel_mean, int mean_features, void *temp, void *stream_) {
+static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int batch, int64_t total_points,
+                               int64_t max_sample_points, int F, const VoxGeom &g, const int *grid, int max_points,
+                               int max_voxels, float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_base,
+                               float *voxel_mean, int mean_features, float *canvas, void *temp, cudaStream_t stream) {
+  const VoxDenseTemp L = vox_dense_layout(batch, total_points, max_voxels, max_points, grid);
+  int32_t *lists = reinterpret_cast<int32_t *>(static_cast<char *>(temp) + L.off_lists);
+  const int tps = (int)scan_num_tiles(max_sample_points > 0 ? max_sample_points : 1);   // <= L.tiles_per_sample
+  char *tb = static_cast<char *>(temp);
+  int32_t *first = reinterpret_cast<int32_t *>(tb + L.off_first);
+  int32_t *vid_of_cell = reinterpret_cast<int32_t *>(tb + L.off_vid);
+  int32_t *gcell = reinterpret_cast<int32_t *>(tb + L.off_gcell);
+  int32_t *cell_of_vid = reinterpret_cast<int32_t *>(tb + L.off_cell_of_vid);
+  uint32_t *totals = reinterpret_cast<uint32_t *>(tb + L.off_totals);
+  const int64_t cells = (int64_t)grid[0] * grid[1] * grid[2];
+  const size_t rows = (size_t)batch * max_voxels;
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, L.zero_bytes, stream));
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(voxels, 0, rows * max_points * F * sizeof(float), stream));
+  const dim3 pgrid((unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer), (unsigned)batch);
+  if (total_points > 0) {
+    vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(pts, sample_offsets, F, g,
+                                                                                                 cells, first, gcell);
+    BEVPOOL_LAUNCH_CHECK();
+  }
+  vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(
+      sample_offsets, gcell, first, vid_of_cell, cell_of_vid, max_voxels, totals,
+      reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
+      L.tiles_per_sample);
+  BEVPOOL_LAUNCH_CHECK();
+  vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, batch, max_voxels, voxel_base);
+  BEVPOOL_LAUNCH_CHECK();
+  if (total_points > 0) {
+    vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists);
+    BEVPOOL_LAUNCH_CHECK();
+  }
+  vox_finalize_kernel<<<(unsigned)ceil_div64((int64_t)rows, 256), 256, (size_t)(batch + 1) * sizeof(int), stream>>>(
+      pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
+      voxel_mean, mean_features, canvas);
+  BEVPOOL_LAUNCH_CHECK();
+  return BEVPOOL_OK;
+}
+
+static int hard_voxelize_impl(const float *points, const float *const *sample_ptrs, const int32_t *sample_offsets, int batch, int64_t total_points,
+                              int64_t max_sample_points, int num_features, const float *voxel_size_host,
+                              const float *range_host, const int *grid_host, int max_points, int max_voxels,
+                              float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_base,
+                              float *voxel_mean, int mean_features, float *canvas, void *temp, void *stream_) {
   int rc = check_vox_args(batch, total_points, num_features, max_voxels, max_points);
   if (rc) return rc;
   if (!sample_offsets || !voxel_size_host || !range_host || !grid_host || !voxels || !coors || !num_points ||
       !voxel_base || !temp)
     return BEVPOOL_E_ARG;
-  if (total_points > 0 && !points) return BEVPOOL_E_ARG;
-  if (voxel_mean && (mean_features <= 0 || mean_features > num_features || mean_features > 32)) return BEVPOOL_E_ARG;
+  if (total_points > 0 && !points && !sample_ptrs) return BEVPOOL_E_ARG;
+  if ((voxel_mean || canvas) && (mean_features <= 0 || mean_features > num_features || mean_features > 16)) return BEVPOOL_E_ARG;
   if (!aligned16(temp) || !aligned16(coors)) return BEVPOOL_E_ALIGN;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const VoxGeom g = make_geom(voxel_size_host, range_host, grid_host);
   if (g.gx <= 0 || g.gy <= 0 || g.gz <= 0) return BEVPOOL_E_ARG;
+  if (vox_dense_ok(batch, grid_host)) {
+    if (canvas) {          // dense BEV canvas of the fused HardSimpleVFE mean: (batch, mean_features, gz, gy, gx), zeroed here
+      BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(canvas, 0, (size_t)batch * mean_features * g.gx * g.gy * g.gz * sizeof(float), stream));
+    }
+    return hard_voxelize_dense(VoxPoints{points, sample_ptrs}, sample_offsets, batch, total_points, max_sample_points, num_features, g, grid_host,
+                               max_points, max_voxels, voxels, coors, num_points, voxel_base, voxel_mean, mean_features,
+                               canvas, temp, stream);
+  }
+  if (canvas || !points) return BEVPOOL_E_RANGE;   // the fused canvas and per-sample pointers exist on the dense-grid path only
   const VoxTemp L = vox_temp_layout(batch, total_points, max_voxels, max_points);
   char *tb = static_cast<char *>(temp);
   int32_t *counts = reinterpret_cast<int32_t *>(tb + L.off_counts);
@@ -342,6 +729,34 @@ extern "C" int bevvox_hard_voxelize(const float *points, const int32_t *sample_o
   return BEVPOOL_OK;
 }
 
+extern "C" int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int batch,
+                                    int64_t total_points, int64_t max_sample_points, int num_features,
+                                    const float *voxel_size_host, const float *range_host,
+                                    const int *grid_host, int max_points, int max_voxels, float *voxels,
+                                    int32_t *coors, int32_t *num_points, int32_t *voxel_base,
+                                    float *voxel_mean, int mean_features, void *temp, void *stream_) {
+  return hard_voxelize_impl(points, nullptr, sample_offsets, batch, total_points, max_sample_points, num_features, voxel_size_host,
+                            range_host, grid_host, max_points, max_voxels, voxels, coors, num_points, voxel_base, voxel_mean,
+                            mean_features, nullptr, temp, stream_);
+}
+
+// voxelize + HardSimpleVFE + pillar scatter in one call (models/bev_depth.py:181-183 with a dense-scatter middle
+// encoder).  The clouds are given either concatenated (`points`) or as a DEVICE array of `batch` per-sample base
+// pointers (`sample_ptrs`, points == NULL): the list of tensors the reference passes, without a torch.cat.  canvas
+// (batch, mean_features, gz, gy, gx) may be NULL (no scatter).  Dense-grid path only.
+extern "C" int bevvox_hard_voxelize_scatter(const float *points, const float *const *sample_ptrs,
+                                            const int32_t *sample_offsets, int batch, int64_t total_points,
+                                            int64_t max_sample_points, int num_features, const float *voxel_size_host,
+                                            const float *range_host, const int *grid_host, int max_points,
+                                            int max_voxels, float *voxels, int32_t *coors, int32_t *num_points,
+                                            int32_t *voxel_base, float *voxel_mean, int mean_features, float *canvas,
+                                            void *temp, void *stream_) {
+  if (grid_host && !vox_dense_ok(batch, grid_host)) return BEVPOOL_E_RANGE;
+  return hard_voxelize_impl(points, sample_ptrs, sample_offsets, batch, total_points, max_sample_points, num_features,
+                            voxel_size_host, range_host, grid_host, max_points, max_voxels, voxels, coors, num_points,
+                            voxel_base, voxel_mean, mean_features, canvas, temp, stream_);
+}
+
 extern "C" int bevvox_dynamic_voxelize(const float *points, int64_t num_points, int num_features,
                                        const float *voxel_size_host, const float *range_host,
                                        const int *grid_host, int32_t *coors, void *stream_) {
@@ -359,10 +774,25 @@ extern "C" int pillar_scatter_forward(const void *voxel_features, const int32_t 
                                       int channels, int dtype, int batch, int nz, int ny, int nx,
                                       void *canvas, int32_t *index_map, void *stream_) {
   if (num_voxels < 0 || channels <= 0 || batch <= 0 || batch > 65535 || nz <= 0 || ny <= 0 || nx <= 0) return BEVPOOL_E_ARG;
-  if (!canvas || !index_map || (num_voxels > 0 && (!voxel_features || !coors))) return BEVPOOL_E_ARG;
+  if (!canvas || (num_voxels > 0 && (!voxel_features || !coors))) return BEVPOOL_E_ARG;
   if (num_voxels > 0 && !aligned16(coors)) return BEVPOOL_E_ALIGN;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int64_t cells = (int64_t)nz * ny * nx;
+  if (!index_map) {
+    // UNIQUE coordinates promised by the caller (the output of hard voxelization): DRAM-speed zero fill of the canvas +
+    // one store per (voxel, channel); with duplicate coordinates the winner would be arbitrary -- pass index_map then.
+    const size_t esz = dtype == BEVPOOL_F32 ? 4 : 2;
+    if (dtype != BEVPOOL_F32 && dtype != BEVPOOL_F16 && dtype != BEVPOOL_BF16) return BEVPOOL_E_DTYPE;
+    BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(canvas, 0, (size_t)batch * channels * cells * esz, stream));
+    if (num_voxels == 0) return BEVPOOL_OK;
+    const unsigned grid = (unsigned)ceil_div64(num_voxels * channels, 256);
+    if (dtype == BEVPOOL_F32)
+      scatter_unique_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float *>(voxel_features), coors, num_voxels, channels, batch, nz, ny, nx, static_cast<float *>(canvas));
+    else
+      scatter_unique_kernel<uint16_t><<<grid, 256, 0, stream>>>(static_cast<const uint16_t *>(voxel_features), coors, num_voxels, channels, batch, nz, ny, nx, static_cast<uint16_t *>(canvas));
+    BEVPOOL_LAUNCH_CHECK();
+    return BEVPOOL_OK;
+  }
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(index_map, 0xff, (size_t)batch * cells * 4, stream));
   if (num_voxels > 0) {
     scatter_index_kernel<<<(unsigned)ceil_div64(num_voxels, 256), 256, 0, stream>>>(coors, num_voxels, batch, nz, ny, nx, index_map);

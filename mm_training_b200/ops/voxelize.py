@@ -19,6 +19,7 @@ repo pins nothing here.  No CPU fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -43,13 +44,49 @@ def _grid_size(voxel_size, point_cloud_range) -> List[int]:
     return torch.round((r[3:] - r[:3]) / v).long().tolist()
 
 
+_OFFSETS_CACHE = {}
+
+
+def _offsets_tensor(offs: tuple, dev) -> torch.Tensor:
+    """Device copy of the samples' row offsets, cached per (device, point counts): repeated calls with the same cloud
+    sizes (and calls under CUDA-graph capture, where a pageable H2D copy is not allowed) reuse it."""
+    key = (str(dev), offs)
+    t = _OFFSETS_CACHE.get(key)
+    if t is None:
+        if len(_OFFSETS_CACHE) > 256:
+            _OFFSETS_CACHE.clear()
+        t = torch.tensor(offs, dtype=torch.int32).to(dev)
+        _OFFSETS_CACHE[key] = t
+    return t
+
+
+_PTR_CACHE = {}
+
+
+def _pointer_table(ptrs: tuple, dev) -> torch.Tensor:
+    """Device array of the samples' base pointers (int64), cached per pointer tuple (see ``_offsets_tensor``)."""
+    key = (str(dev), ptrs)
+    t = _PTR_CACHE.get(key)
+    if t is None:
+        if len(_PTR_CACHE) > 256:
+            _PTR_CACHE.clear()
+        t = torch.tensor(ptrs, dtype=torch.int64).to(dev)
+        _PTR_CACHE[key] = t
+    return t
+
+
 def hard_voxelize_batch(points_list: Sequence[torch.Tensor], voxel_size, point_cloud_range,
-                        max_num_points: int, max_voxels: int, mean_features: int = 0):
+                        max_num_points: int, max_voxels: int, mean_features: int = 0, padded: bool = False,
+                        scatter: bool = False):
     """Voxelizes a list of (Np_i, F) float32 CUDA clouds in one native call.
 
-    Returns ``(voxels (M, T, F), num_points (M,), coors (M, 4) [b,z,y,x], voxel_base (B+1,) cpu,
-    voxel_mean (M, mean_features) or None)`` with the samples' voxels concatenated in order.
-    One D2H sync (the voxel counts) -- mmcv pays one per sample.
+    Returns ``(voxels (M, T, F), num_points (M,), coors (M, 4) [b,z,y,x], voxel_base (B+1,), voxel_mean
+    (M, mean_features) or None)`` with the samples' voxels concatenated in order (mmdet3d's packing).  M is
+    data dependent, so the exact-size result costs ONE D2H sync (mmcv pays one per sample) and ``voxel_base`` comes
+    back on the CPU.  ``padded=True`` skips the sync (CUDA-graph capturable): the tensors keep their ``B *
+    max_voxels`` rows -- rows >= voxel_base[B] are zero -- and ``voxel_base`` stays on the device.
+    ``scatter=True`` (needs ``mean_features``) appends the dense BEV canvas ``(B, mean_features * gz, gy, gx)`` of the
+    fused HardSimpleVFE mean: voxelize -> VFE -> scatter of ``models/bev_depth.py:181-183`` in one call.
     """
     assert len(points_list) > 0
     _lib.require_cuda(*points_list)
@@ -61,16 +98,24 @@ def hard_voxelize_batch(points_list: Sequence[torch.Tensor], voxel_size, point_c
             raise TypeError('points must be float32 (Np, F) tensors with the same F')
     B = len(points_list)
     total = sum(counts)
-    points = points_list[0].contiguous() if B == 1 else torch.cat([p.contiguous() for p in points_list], 0)
     offs = [0]
     for c in counts:
         offs.append(offs[-1] + c)
     grid = _grid_size(voxel_size, point_cloud_range)
+    grid_c = _i32_array(grid)
     L = _lib.lib()
     tb = ctypes.c_size_t()
-    _lib.check(L.bevvox_temp_bytes(B, total, max_voxels, max_num_points, ctypes.byref(tb)), 'bevvox_temp_bytes')
+    _lib.check(L.bevvox_temp_bytes(B, total, grid_c, max_voxels, max_num_points, ctypes.byref(tb)), 'bevvox_temp_bytes')
+    assert not scatter or mean_features > 0, 'scatter=True needs mean_features'
+    gx, gy, gz = grid
+    dense = B * gx * gy * gz <= (1 << 26) and os.environ.get('BEVVOX_FORCE_HASH', '0') != '1'
     with torch.cuda.device(dev):
-        offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+        offsets = _offsets_tensor(tuple(offs), dev)
+        points_list = [p.contiguous() for p in points_list]
+        if dense and B > 1:          # the kernels read the list through a device array of base pointers: no torch.cat
+            points, sample_ptrs = None, _pointer_table(tuple(p.data_ptr() for p in points_list), dev)
+        else:
+            points, sample_ptrs = (points_list[0] if B == 1 else torch.cat(points_list, 0)), None
         rows = B * max_voxels
         voxels = torch.empty(rows, max_num_points, F, dtype=torch.float32, device=dev)
         coors = torch.empty(rows, 4, dtype=torch.int32, device=dev)
@@ -78,15 +123,31 @@ def hard_voxelize_batch(points_list: Sequence[torch.Tensor], voxel_size, point_c
         voxel_base = torch.empty(B + 1, dtype=torch.int32, device=dev)
         mean = torch.empty(rows, mean_features, dtype=torch.float32, device=dev) if mean_features > 0 else None
         temp = torch.empty(tb.value, dtype=torch.uint8, device=dev)
-        _lib.check(L.bevvox_hard_voxelize(
-            points.data_ptr() if total > 0 else None, offsets.data_ptr(), B, total, max(counts), F,
-            _f32_array(voxel_size), _f32_array(point_cloud_range), _i32_array(grid), max_num_points, max_voxels,
-            voxels.data_ptr(), coors.data_ptr(), num_points.data_ptr(), voxel_base.data_ptr(),
-            mean.data_ptr() if mean is not None else None, mean_features, temp.data_ptr(),
-            _lib.stream_ptr(dev)), 'bevvox_hard_voxelize')
+        tail = [offsets.data_ptr(), B, total, max(counts), F,
+                _f32_array(voxel_size), _f32_array(point_cloud_range), grid_c, max_num_points, max_voxels,
+                voxels.data_ptr(), coors.data_ptr(), num_points.data_ptr(), voxel_base.data_ptr(),
+                mean.data_ptr() if mean is not None else None, mean_features]
+        canvas = None
+        if dense:
+            if scatter:
+                canvas = torch.empty(B, mean_features * gz, gy, gx, dtype=torch.float32, device=dev)
+            _lib.check(L.bevvox_hard_voxelize_scatter(
+                points.data_ptr() if (points is not None and total > 0) else None,
+                sample_ptrs.data_ptr() if sample_ptrs is not None else None, *tail,
+                canvas.data_ptr() if canvas is not None else None, temp.data_ptr(), _lib.stream_ptr(dev)),
+                'bevvox_hard_voxelize_scatter')
+        else:
+            _lib.check(L.bevvox_hard_voxelize(points.data_ptr() if total > 0 else None, *tail, temp.data_ptr(),
+                                              _lib.stream_ptr(dev)), 'bevvox_hard_voxelize')
+            if scatter:              # hash path (huge grids): the separate scatter kernel
+                canvas = pillar_scatter(mean, coors, B, (gz, gy, gx), unique_coors=True)
+        if padded:
+            out = (voxels, num_points, coors, voxel_base, mean)
+            return out + (canvas,) if scatter else out
         base = voxel_base.cpu()
     M = int(base[-1])
-    return voxels[:M], num_points[:M], coors[:M], base, (mean[:M] if mean is not None else None)
+    out = (voxels[:M], num_points[:M], coors[:M], base, (mean[:M] if mean is not None else None))
+    return out + (canvas,) if scatter else out
 
 
 def dynamic_voxelize(points: torch.Tensor, voxel_size, point_cloud_range) -> torch.Tensor:
@@ -137,16 +198,23 @@ class Voxelization(nn.Module):
 
 
 @torch.no_grad()
-def voxelize(points: Sequence[torch.Tensor], layer: Voxelization, mean_features: int = 0):
+def voxelize(points: Sequence[torch.Tensor], layer: Voxelization, mean_features: int = 0, padded: bool = False,
+             scatter: bool = False):
     """``MVXTwoStageDetector.voxelize``: ``(voxels, num_points, coors_batch [b,z,y,x])`` -- the order
     unpacked at ``models/bev_depth.py:181``.  With ``mean_features`` > 0 a fourth element, the fused
-    HardSimpleVFE output, is appended."""
-    voxels, num_points, coors, _, mean = hard_voxelize_batch(points, layer.voxel_size, layer.point_cloud_range,
-                                                             layer.max_num_points, layer._max_voxels(),
-                                                             mean_features)
+    HardSimpleVFE output, is appended; with ``scatter`` a fifth, the dense canvas of that mean.  ``padded`` skips the
+    voxel-count read-back (see ``hard_voxelize_batch``) and appends the device ``voxel_base`` as the last element."""
+    res = hard_voxelize_batch(points, layer.voxel_size, layer.point_cloud_range, layer.max_num_points,
+                              layer._max_voxels(), mean_features, padded, scatter)
+    voxels, num_points, coors, base, mean = res[:5]
+    out = [voxels, num_points, coors]
     if mean_features > 0:
-        return voxels, num_points, coors, mean
-    return voxels, num_points, coors
+        out.append(mean)
+    if scatter:
+        out.append(res[5])
+    if padded:
+        out.append(base)
+    return tuple(out)
 
 
 class HardSimpleVFE(nn.Module):
@@ -166,7 +234,7 @@ class HardSimpleVFE(nn.Module):
 
 class _PillarScatter(Function):
     @staticmethod
-    def forward(ctx, voxel_features, coors, batch_size, grid_zyx):
+    def forward(ctx, voxel_features, coors, batch_size, grid_zyx, unique_coors=False):
         _lib.require_cuda(voxel_features, coors)
         nz, ny, nx = (int(v) for v in grid_zyx)
         feats = voxel_features.contiguous()
@@ -178,11 +246,11 @@ class _PillarScatter(Function):
         dev = feats.device
         with torch.cuda.device(dev):
             canvas = torch.empty(batch_size, C, nz, ny, nx, dtype=feats.dtype, device=dev)
-            index_map = torch.empty(batch_size * nz * ny * nx, dtype=torch.int32, device=dev)
+            index_map = None if unique_coors else torch.empty(batch_size * nz * ny * nx, dtype=torch.int32, device=dev)
             _lib.check(_lib.lib().pillar_scatter_forward(
                 feats.data_ptr() if M else None, co.data_ptr() if M else None, M, C, _lib.dtype_code(feats),
-                batch_size, nz, ny, nx, canvas.data_ptr(), index_map.data_ptr(), _lib.stream_ptr(dev)),
-                'pillar_scatter_forward')
+                batch_size, nz, ny, nx, canvas.data_ptr(), index_map.data_ptr() if index_map is not None else None,
+                _lib.stream_ptr(dev)), 'pillar_scatter_forward')
         ctx.save_for_backward(co)
         ctx.dims = (M, C, batch_size, nz, ny, nx)
         return canvas.view(batch_size, C * nz, ny, nx)
@@ -197,19 +265,23 @@ class _PillarScatter(Function):
             _lib.check(_lib.lib().pillar_scatter_backward(
                 g.data_ptr(), co.data_ptr() if M else None, M, C, _lib.dtype_code(g), B, nz, ny, nx,
                 grad_feats.data_ptr() if M else None, _lib.stream_ptr(g.device)), 'pillar_scatter_backward')
-        return grad_feats, None, None, None
+        return grad_feats, None, None, None, None
 
 
-def pillar_scatter(voxel_features: torch.Tensor, coors: torch.Tensor, batch_size: int, grid_zyx) -> torch.Tensor:
+def pillar_scatter(voxel_features: torch.Tensor, coors: torch.Tensor, batch_size: int, grid_zyx,
+                   unique_coors: bool = False) -> torch.Tensor:
     """(M, C) voxel features at ``coors`` [b, z, y, x] -> dense (B, C*nz, ny, nx); differentiable
-    w.r.t. the features."""
-    return _PillarScatter.apply(voxel_features, coors, batch_size, tuple(grid_zyx))
+    w.r.t. the features.  ``unique_coors=True`` (true for the output of hard voxelization) takes the fast path:
+    zero fill + one store per element; with duplicate coordinates the default path lets the highest row win."""
+    return _PillarScatter.apply(voxel_features, coors, batch_size, tuple(grid_zyx), unique_coors)
 
 
 class PointPillarsScatter(nn.Module):
-    """mmdet3d ``PointPillarsScatter(in_channels, output_shape=(ny, nx))``; same call signature as
-    ``SparseEncoder.forward(voxel_features, coors, batch_size)`` -- the seam at
-    ``models/bev_depth.py:183``."""
+    """mmdet3d ``PointPillarsScatter(in_channels, output_shape=(ny, nx))``: the scatter-to-dense step only.
+    The reference's ``pts_middle_encoder`` (``models/bev_depth.py:183``, ``exps/conf_aim.py:202-212``) is a
+    ``SparseEncoder``: spconv sparse 3-D convolutions (5 -> 128 channels) FOLLOWED by ``.dense()``.  The sparse
+    convolution stack is out of scope here; this module replaces the ``.dense()`` / pillar-scatter step after it
+    (same ``(voxel_features, coors, batch_size)`` call signature), it is not a functional replacement of the encoder."""
 
     def __init__(self, in_channels: int, output_shape, nz: int = 1):
         super().__init__()

@@ -1,4 +1,5 @@
-"""Times the LiDAR branch alone (for ncu launch lists): python scripts/lidar_probe.py [sweeps]"""
+"""The LiDAR-branch side measurement alone (launch lists / ncu): python scripts/lidar_probe.py [sweeps]"""
+import json
 import os
 import sys
 
@@ -7,7 +8,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 
-if __name__ == '__main__':
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    torch.cuda.set_device(0)
-    print(bench.run_lidar_side(torch.device('cuda', 0), 6458.4, sweeps=n))
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))
+r = bench.run_lidar_side(torch.device('cuda'), float(peaks.get('hbm_gbs', 6650.0)), int(sys.argv[1]) if len(sys.argv) > 1 else 32)
+print(json.dumps(r))

@@ -32,6 +32,12 @@ def test_every_declared_symbol_is_exported(L):
         assert n in names, f'{n} bound in _lib.py but not declared in the header'
 
 
+def test_reference_launcher_symbol_is_exported(L):
+    """ops/voxel_pooling/src/voxel_pooling_forward.cpp:21-22 links against this C++ symbol (Itanium mangling of
+    voxel_pooling_forward_kernel_launcher(int x6, const int*, const float*, float*, int*, cudaStream_t))."""
+    assert hasattr(L, '_Z37voxel_pooling_forward_kernel_launcheriiiiiiPKiPKfPfPiP11CUstream_st')
+
+
 def test_abi_version_and_error_strings(L):
     assert L.bevpool_abi_version() == 2
     assert L.bevpool_error_string(0) == b'ok'

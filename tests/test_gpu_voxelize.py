@@ -109,6 +109,51 @@ def test_adversarial_sets():
     assert c.tolist() == [[0, 0, 0, 0]] and n.tolist() == [1]                      # NaN / inf dropped (documented)
 
 
+@pytest.mark.parametrize('hash_path', [False, True])
+def test_dense_and_hash_tables_agree(hash_path, monkeypatch):
+    # grids up to 2^26 cells use a dense first-point table, larger ones a hash table: same outputs
+    monkeypatch.setenv('BEVVOX_FORCE_HASH', '1' if hash_path else '0')
+    clouds = [synthetic.lidar_sweep(n, 5, seed=20 + i) for i, n in enumerate([50000, 20000])]
+    _check_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, 15, 25000, mean_features=5)
+    _check_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, 2, 300, mean_features=3)
+
+
+def test_padded_no_sync_and_fused_scatter():
+    # padded=True: no voxel-count read-back (CUDA-graph capturable); scatter=True: voxelize -> VFE mean -> dense canvas
+    clouds_np = [synthetic.lidar_sweep(n, 5, seed=30 + i) for i, n in enumerate([60000, 1, 45000])]
+    clouds = [torch.from_numpy(p).to(DEV) for p in clouds_np]
+    T, M = 15, 25000
+    exact = hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, T, M, mean_features=5)
+    voxels, num, coors, base, mean, canvas = hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, T, M,
+                                                                 mean_features=5, padded=True, scatter=True)
+    assert base.is_cuda and voxels.shape[0] == 3 * M
+    n = int(base[-1])
+    assert n == exact[0].shape[0]
+    assert torch.equal(voxels[:n], exact[0]) and torch.equal(num[:n], exact[1]) and torch.equal(coors[:n], exact[2])
+    assert torch.equal(mean[:n], exact[4])
+    assert float(voxels[n:].abs().sum()) == 0.0 and int(num[n:].abs().sum()) == 0      # padding rows are zero
+    gx, gy, gz = 2048, 256, 1
+    ref = vz.pillar_scatter_ref(exact[4].cpu().numpy(), exact[2].cpu().numpy(), 3, (gz, gy, gx))
+    assert canvas.shape == (3, 5 * gz, gy, gx) and np.array_equal(canvas.cpu().numpy(), ref)
+    # the separate scatter call, both implementations
+    a = pillar_scatter(exact[4], exact[2], 3, (gz, gy, gx), unique_coors=True)
+    b = pillar_scatter(exact[4], exact[2], 3, (gz, gy, gx))
+    assert torch.equal(a, canvas) and torch.equal(b, canvas)
+    # capturable: the whole padded call inside a CUDA graph gives the same bits
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, T, M, mean_features=5, padded=True, scatter=True)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        cap = hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, T, M, mean_features=5, padded=True,
+                                  scatter=True)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cap[0], voxels) and torch.equal(cap[5], canvas) and torch.equal(cap[3], base)
+
+
 def test_dynamic_voxelize():
     pts = synthetic.lidar_sweep(50000, 5, seed=3)
     coors = dynamic_voxelize(torch.from_numpy(pts).to(DEV), CFG_3.voxel_size, CFG_3.point_cloud_range)
