@@ -191,12 +191,33 @@ def run_cpu_baseline(cfg, frames: int, iters: int):
                       f'materialise + index_add_ forward + autograd backward', 'ms_per_frame': best / frames * 1e3}
 
 
-def run_sweep(dev, peak_gbs, seed=7):
-    """BASELINE.json configs[4] in miniature: batch 1..64 on the aiMotive grid and the three square grids
-    at batch 8, same step (cold plan + fused forward + backward, NCHW layouts), one CUDA graph each."""
+def _graph_step_ms(step, iters=20, warmup=3):
+    """Capture ``step`` as one CUDA graph and time its replay (median ms, CUDA events)."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        keep = step()                                           # noqa: F841
+    med, mn = time_cuda(g.replay, iters, warmup)
+    del g, keep
+    return med, mn
+
+
+def run_sweep(dev, peak_gbs, seed=7, full=False, ref_arms=False):
+    """BASELINE.json configs[4]: batch x grid sweep of the same step (cold plan from geom_xyz + fused forward +
+    backward, NCHW layouts), one CUDA graph per point, this rank's GPU.  Default: a miniature (batch 1/8/64 on the
+    aiMotive grid, the three square grids at batch 8, the shipped CFG-AIM shape at batch 4); ``full``: batch
+    1..64 x {128,256,512}^2.  ``ref_arms``: the reference's CUDA pipeline (oracle/_ref) on the same inputs beside
+    every point, and the CPU port on a bounded sample (batch <= 2)."""
     from mm_training_b200.configs import sweep_grid_config
-    from mm_training_b200.ops.voxel_pooling import build_plan, context_rows_nhwc, fused_backward, fused_forward
-    points = [(CFG_2, 1), (CFG_2, 8), (CFG_2, 64)] + [(sweep_grid_config(g), 8) for g in (128, 256, 512)]
+    from mm_training_b200.ops.voxel_pooling import build_plan, fused_backward, fused_forward
+    if full:
+        points = [(sweep_grid_config(g), b) for g in (128, 256, 512) for b in (1, 2, 4, 8, 16, 32, 64)]
+    else:
+        points = [(CFG_2, 1), (CFG_2, 8), (CFG_2, 64)] + [(sweep_grid_config(g), 8) for g in (128, 256, 512)] + [(CFG_AIM, 4)]
     rows_out = []
     for cfg, B in points:
         geom, vn_t = synthetic.camera_rig(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=seed)
@@ -209,22 +230,71 @@ def run_sweep(dev, peak_gbs, seed=7):
             plan = build_plan(geom, vn, frustum=fr, max_runs=n)
             out = fused_forward(plan, depth, ctx)
             return out, fused_backward(plan, go, depth, ctx)
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            step()
-        torch.cuda.current_stream().wait_stream(s)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            keep = step()                                       # noqa: F841
-        med, _ = time_cuda(g.replay, 20, 3)
+        med, _ = _graph_step_ms(step)
         kept = int((build_plan(geom, vn).cell_of_point >= 0).sum().item()) / B
         gbs = algorithmic_bytes(cfg, kept)['step'] * B / (med * 1e-3) / 1e9
-        rows_out.append({'workload': cfg.name, 'frames_per_step': B, 'ms_per_step': med,
-                         'frames_per_s': B / (med * 1e-3), 'frac_of_hbm_peak': gbs / peak_gbs})
-        del g, keep, geom, depth, ctx, go
+        row = {'workload': cfg.name, 'frames_per_step': B, 'ms_per_step': med,
+               'frames_per_s': B / (med * 1e-3), 'frac_of_hbm_peak': gbs / peak_gbs}
+        if ref_arms:
+            from oracle import ref_cuda_op
+            if ref_cuda_op.available():
+                d_r, c_r = depth.detach().requires_grad_(True), ctx.detach().requires_grad_(True)
+
+                def ref_step():
+                    d_r.grad = None
+                    c_r.grad = None
+                    ref_cuda_op.ref_pipeline(geom, d_r, c_r, vn).backward(go)
+                rmed, _ = time_cuda(ref_step, 3, 1)
+                row['ref_cuda_frames_per_s'] = B / (rmed * 1e-3)
+                del d_r, c_r
+            if B <= 2:
+                row['cpu_port_frames_per_s'] = run_cpu_baseline(cfg, B, 1)['value']
+        rows_out.append(row)
+        del geom, depth, ctx, go
         torch.cuda.empty_cache()
     return rows_out
+
+
+def run_dropin_op(dev, peak_gbs, cfg=CFG_2, B=8, seed=5):
+    """Row (A) of SURVEY.md 8(d): the drop-in op ``voxel_pooling(geom_xyz, input_features, voxel_num)`` on
+    PRE-MATERIALISED features (B, N, D, H, W, C), forward + autograd backward w.r.t. the features, NCHW-contiguous
+    incoming gradient (what lss_fpn.py:466 hands back) -- beside the reference's own CUDA op on the same tensors."""
+    from mm_training_b200.ops.voxel_pooling import voxel_pooling
+    from oracle import ref_cuda_op
+    geom, vn_t = synthetic.camera_rig(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=seed)
+    vn = tuple(int(v) for v in vn_t.tolist())
+    depth, ctx, go = synthetic.camera_features(cfg, B, device=dev, seed=seed)
+    N = cfg.num_cams
+    f = depth.unsqueeze(1) * ctx.unsqueeze(2)                                        # lss_fpn.py:441-460
+    feats = f.reshape(B, N, *f.shape[1:]).permute(0, 1, 3, 4, 5, 2).contiguous().requires_grad_(True)
+    del f
+
+    def ours():
+        feats.grad = None
+        voxel_pooling(geom, feats, vn).backward(go)
+    ours()
+    torch.cuda.synchronize()
+    from mm_training_b200.ops.voxel_pooling import build_plan
+    kept = int((build_plan(geom, vn).cell_of_point >= 0).sum().item()) / B
+    P, C = cfg.points_per_frame, cfg.output_channels
+    G = vn[0] * vn[1]
+    bytes_frame = 12 * P + 4 * C * kept + 4 * C * G + 4 * C * G + 4 * P + 4 * C * P
+    med, mn = time_cuda(ours, 10, 3)
+    res = {'what': 'drop-in op voxel_pooling(geom_xyz, input_features, voxel_num).backward(grad): cold point plan + '
+                   'forward + backward per call, through the autograd Function (eager), pre-materialised features',
+           'workload': cfg.name, 'frames_per_step': B, 'ms_per_step': med, 'frames_per_s': B / (med * 1e-3),
+           'algorithmic_bytes_per_frame': bytes_frame,
+           'roofline': {'bound': 'hbm', 'achieved': bytes_frame * B / (med * 1e-3) / 1e9, 'peak': peak_gbs, 'unit': 'GB/s',
+                        'frac': bytes_frame * B / (med * 1e-3) / 1e9 / peak_gbs}}
+    if ref_cuda_op.available():
+        def ref():
+            feats.grad = None
+            ref_cuda_op.ref_voxel_pooling(geom, feats, vn).backward(go)
+        rmed, _ = time_cuda(ref, 5, 2)
+        res['ref_cuda_op'] = {'what': 'the reference op (its CUDA kernel + voxel_pooling.py autograd wrapper) on the same tensors',
+                              'ms_per_step': rmed, 'frames_per_s': B / (rmed * 1e-3)}
+        res['speedup_vs_ref_cuda_op'] = rmed / med
+    return res
 
 
 def run_lidar_side(dev, peak_gbs, sweeps: int = 32):
@@ -294,7 +364,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU per step')
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'aim'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'aim', 'train'],
+                    help="'train': BASELINE.json configs[3], the fusion training step (bench_train.py), bf16 autocast + DDP")
+    ap.add_argument('--train-cfg', default='aim', choices=['aim', 'cfg2'], help='camera shape of --workload train')
     ap.add_argument('--e2e-chunk', type=int, default=4, help='frames per chunk of the host-buffer pipeline')
     ap.add_argument('--plan', default='runs', choices=['runs', 'points'],
                     help="what the plan sorts: 'runs' (vertical point runs, two-stage forward) or 'points'")
@@ -304,9 +376,12 @@ def main():
                          "reference's int32 geom_xyz tensor, 'auto' = rig when proven")
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip e2e / cpu / reference-CUDA side measurements')
+    ap.add_argument('--sweep', default='mini', choices=['mini', 'full'],
+                    help="'full': BASELINE.json configs[4] batch 1..64 x {128,256,512}^2 with both reference arms per point")
     args = ap.parse_args()
-    cfg = CFG_2 if args.workload == 'cfg2' else CFG_AIM
-    if args.workload == 'aim' and args.batch == 32:
+    args.batch_given = any(a == '--batch' or a.startswith('--batch=') for a in sys.argv[1:])
+    cfg = CFG_AIM if args.workload == 'aim' else CFG_2
+    if args.workload == 'aim' and not args.batch_given:
         args.batch = 4
 
     rank = int(os.environ.get('RANK', 0))
@@ -359,6 +434,13 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     _lib.lib()
+    if args.workload == 'train':
+        import bench_train
+        bench_train.run_train(args, rank, world, local_rank, json_fd)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     B = args.batch
     geom, vn_t = synthetic.camera_rig(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=1 + rank)
@@ -453,34 +535,48 @@ def main():
     e2e = None
     if not args.no_extras:
         from mm_training_b200.ops.voxel_pooling.host_pipeline import HostPoolingPipeline
-        h_geom, h_depth, h_ctx, h_go = (t.cpu().pin_memory() for t in (geom, depth, ctx, go))
+        # geometry as the data loader holds it: the rig matrices (4 KB/frame) when the on-device index path is
+        # proven on this GPU, else the reference's int32 geom_xyz tensor (3.8 MB/frame)
+        e2e_rig = variant is not None
+        pin = lambda t: t.cpu().contiguous().pin_memory()
+        h_depth, h_ctx, h_go = pin(depth), pin(ctx), pin(go)
+        if e2e_rig:
+            h_s2e, h_k, h_geom = pin(s2e), pin(intrin), None
+        else:
+            h_s2e, h_k, h_geom = None, None, pin(geom)
         X, Y, _ = vn
         h_out = torch.empty(B, cfg.output_channels, Y, X).pin_memory()
         h_gd, h_gc = torch.empty_like(h_depth).pin_memory(), torch.empty_like(h_ctx).pin_memory()
         pipe = HostPoolingPipeline(cfg.num_cams, geom.shape, depth.shape, ctx.shape, vn,
-                                   chunk_frames=max(1, min(args.e2e_chunk, B)), device=dev)
+                                   chunk_frames=max(1, min(args.e2e_chunk, B)), device=dev, rig=lsg if e2e_rig else None)
         e2e_iters = max(5, min(args.steps, 20))
+        run_e2e = lambda: pipe.run(h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc, h_sensor2ego=h_s2e, h_intrin=h_k)
         for _ in range(3):
-            pipe.run(h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc)
-        torch.cuda.synchronize()
+            run_e2e()                                   # returns with the results in host memory, plans validated
         assert torch.allclose(h_out.to(dev), out.permute(0, 3, 1, 2), rtol=1e-5, atol=1e-6)   # same results as the device path
         if world > 1:
             dist.barrier()
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record()
         for _ in range(e2e_iters):
-            pipe.run(h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc)
+            run_e2e()
         eb.record()
         torch.cuda.synchronize()
         e2e_value, e2e_total_ms, _ = aggregate_throughput(B * e2e_iters, ea.elapsed_time(eb), device=dev)
-        h2d = sum(t.numel() * t.element_size() for t in (h_geom, h_depth, h_ctx, h_go))
-        d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gd, h_gc))
+        h_in = [t for t in (h_geom, h_s2e, h_k, h_depth, h_ctx, h_go) if t is not None]
+        h2d = sum(t.numel() * t.element_size() for t in h_in)
+        d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gd, h_gc)) + 4 * ((B + pipe.chunk - 1) // pipe.chunk)
         e2e = {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                'ms_per_step': e2e_total_ms / e2e_iters, 'steps': e2e_iters,
                'api': 'HostPoolingPipeline.run: voxel_pooling_fused(...).backward(...) on pinned host tensors, '
-                      f'{pipe.chunk}-frame chunks on 3 streams (H2D | plan+fwd+bwd | D2H); bytes are per GPU',
-               'pcie_gbs_per_gpu': (h2d + d2h) / (e2e_total_ms / e2e_iters * 1e-3) / 1e9}
-        del pipe, h_geom, h_depth, h_ctx, h_go, h_out, h_gd, h_gc
+                      f'{pipe.chunk}-frame chunks on 3 streams (H2D | run plan + fwd + bwd | D2H), results in host memory and '
+                      'plan status checked before every call returns; bytes are per GPU',
+               'geometry_input': 'sensor2ego + intrin matrices (plan built on the device)' if e2e_rig else 'int32 geom_xyz tensor',
+               'scratch_reruns': pipe.reruns,
+               'pcie_gbs_per_gpu': (h2d + d2h) / (e2e_total_ms / e2e_iters * 1e-3) / 1e9,
+               'h2d_gbs_per_gpu': h2d / (e2e_total_ms / e2e_iters * 1e-3) / 1e9,
+               'd2h_gbs_per_gpu': d2h / (e2e_total_ms / e2e_iters * 1e-3) / 1e9}
+        del pipe, h_geom, h_s2e, h_k, h_depth, h_ctx, h_go, h_out, h_gd, h_gc
 
     if rank != 0:
         if world > 1:
@@ -527,6 +623,32 @@ def main():
         cl_ms = time_cuda(g2.replay, 20, 3)
     except Exception as e:                                      # pragma: no cover
         print(f'[bench] channels_last side measurement failed ({e})', file=sys.stderr)
+    # ---- the public autograd op, eager, no hints (what INTEGRATION.md section 1 shows a user calling)
+    def op_step_geom():
+        d_, c_ = depth.detach().requires_grad_(True), ctx.detach().requires_grad_(True)
+        voxel_pooling_fused(geom, d_, c_, vn).backward(go)
+    stages['autograd_op_eager: voxel_pooling_fused(geom_xyz, depth, context, voxel_num).backward(g)'] = time_cuda(op_step_geom, 20, 3)
+    if variant is not None:
+        from mm_training_b200.ops.voxel_pooling import voxel_pooling_rig
+
+        def op_step_rig():
+            d_, c_ = depth.detach().requires_grad_(True), ctx.detach().requires_grad_(True)
+            voxel_pooling_rig(lsg, s2e, intrin, d_, c_).backward(go)
+        stages['autograd_op_eager: voxel_pooling_rig(lsg, sensor2ego, intrin, depth, context).backward(g)'] = time_cuda(op_step_rig, 20, 3)
+    # ---- sustained: the headline graph replayed for >= 1 s (clocks / power settle), this rank
+    sustained = None
+    if graph is not None and not args.no_extras:
+        n_sus = int(1200.0 / max(ms_per_step, 1e-3)) + 1
+        with ClockSampler(local_rank) as clk_s:
+            sa, sb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sa.record()
+            for _ in range(n_sus):
+                run()
+            sb.record()
+            torch.cuda.synchronize()
+        sus_ms = sa.elapsed_time(sb)
+        sustained = {'steps': n_sus, 'seconds': sus_ms * 1e-3, 'ms_per_step': sus_ms / n_sus,
+                     'frames_per_s': B * n_sus / (sus_ms * 1e-3), 'clocks': clk_s.summary()}
     dom_name, dom = ('fused_backward', k_bwd) if k_bwd[0] >= k_fwd[0] else ('fused_forward', k_fwd)
     achieved = bytes_[dom_name] * B / (dom[0] * 1e-3) / 1e9
     traffic = None                      # dram__bytes_read+write per launch of that kernel, from the committed ncu capture
@@ -559,6 +681,9 @@ def main():
                                    {'what': 'same step with channels_last context and incoming gradient (zero-copy '
                                             'layouts: no transposes, no gradient-row pass), CUDA graph replay, this rank',
                                     'ms_per_step': cl_ms[0], 'frames_per_s': B / (cl_ms[0] * 1e-3)}),
+            'sustained': sustained,
+            'tolerance': 'integer work bit-exact; fp32 features/gradients rtol 1e-5 vs the fp64 oracle + 1e-6 x sum|terms| of the '
+                         'cell (a few ulps of the partial sums; the reference itself is not run-to-run stable: fp32 atomicAdd order)',
             'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks.summary()}
 
@@ -590,9 +715,15 @@ def main():
 
         # ---- batch / grid sweep (BASELINE.json configs[4], single GPU)
         try:
-            line['sweep'] = run_sweep(dev, peak_gbs)
+            line['sweep'] = run_sweep(dev, peak_gbs, full=args.sweep == 'full', ref_arms=args.sweep == 'full')
         except Exception as e:                                  # pragma: no cover
             line['sweep'] = {'error': repr(e)}
+
+        # ---- drop-in op (A) on pre-materialised features beside the reference's CUDA op
+        try:
+            line['dropin_op'] = run_dropin_op(dev, peak_gbs)
+        except Exception as e:                                  # pragma: no cover
+            line['dropin_op'] = {'error': repr(e)}
 
         # ---- LiDAR branch (BASELINE.json configs[2]): hard voxelization + HardSimpleVFE mean + pillar scatter
         try:
