@@ -297,6 +297,42 @@ def run_dropin_op(dev, peak_gbs, cfg=CFG_2, B=8, seed=5):
     return res
 
 
+def run_depth_labels_side(dev, peak_gbs, B=4):
+    """Side measurement: depth labels for the depth loss at the shipped shape (704 x 1280 images, 2
+    cameras, 200 k LiDAR points per frame, 16 x 16 min-pool, 409 bins): the native two-launch path beside the
+    reference's python loop of torch ops (exps/mm_training_aim.py:115-215, restated in oracle/) on the same GPU and on
+    the host cores (one frame)."""
+    from mm_training_b200.ops.depth_labels import DepthLabelGenerator
+    from oracle import depth_labels_ref as dl
+    cfg = CFG_AIM
+    hw, D = cfg.final_dim, cfg.depth_bins
+    case = dl.synthetic_case(batch=B, sweeps=1, cams=cfg.num_cams, num_points=200_000, image_hw=hw, seed=21)
+    clouds, ext, intr, bda = case
+    g_clouds, g_ext, g_intr, g_bda = [c.to(dev) for c in clouds], ext.to(dev), intr.to(dev), bda.to(dev)
+    gen = DepthLabelGenerator(hw, cfg.downsample_factor, cfg.d_bound, D)
+    labels, bins = gen(g_clouds, g_ext, g_intr, g_bda, return_bins=True)
+    _, ref_bins = dl.depth_labels_exact([clouds[0]], ext[:1], intr[:1], bda[:1], hw, cfg.downsample_factor, cfg.d_bound, D)
+    n0 = ref_bins.numel()
+    assert torch.equal(bins[:n0].cpu().long(), ref_bins), 'depth labels differ from the oracle'
+    med, mn = time_cuda(lambda: gen(g_clouds, g_ext, g_intr, g_bda), 20, 3)
+    ref_gpu, _ = time_cuda(lambda: dl.depth_labels_torch(g_clouds, g_ext, g_intr, g_bda, hw, cfg.downsample_factor, cfg.d_bound, D), 3, 1)
+    t0 = time.perf_counter()
+    dl.depth_labels_torch([clouds[0]], ext[:1], intr[:1], bda[:1], hw, cfg.downsample_factor, cfg.d_bound, D)
+    cpu_s = time.perf_counter() - t0
+    cells = bins.numel()
+    # compulsory bytes: every point read once per image it is projected into (12 B) + the one-hot rows written once
+    alg = sum(int(c.shape[0]) for c in clouds) * 12 * cfg.num_cams + cells * D * 4
+    return {'workload': f'depth_labels_{hw[0]}x{hw[1]}_2cam_200kpts_D{D}', 'frames_per_step': B, 'ms_per_step': med,
+            'frames_per_s': B / (med * 1e-3), 'algorithmic_bytes_per_step': alg,
+            'roofline': {'bound': 'hbm', 'achieved': alg / (med * 1e-3) / 1e9, 'peak': peak_gbs, 'unit': 'GB/s',
+                         'frac': alg / (med * 1e-3) / 1e9 / peak_gbs,
+                         'note': 'the full-resolution winner map (8 B/pixel, read + cleared) is scratch traffic, not counted'},
+            'reference_torch_loop_same_gpu': {'ms_per_step': ref_gpu, 'frames_per_s': B / (ref_gpu * 1e-3)},
+            'speedup_vs_reference_torch_loop': ref_gpu / med,
+            'cpu_port': {'frames_per_s': 1.0 / cpu_s, 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': '1 frame'},
+            'parity': 'bin indices bit-exact vs oracle/depth_labels_ref.py::depth_labels_exact (checked in this run)'}
+
+
 def run_lidar_side(dev, peak_gbs, sweeps: int = 32):
     """Side measurement (not the headline metric; BASELINE.json configs[2]): ``sweeps`` synthetic 200k-point long-range
     sweeps through hard voxelization + fused HardSimpleVFE mean + pillar scatter.  Three ways:
@@ -724,6 +760,12 @@ def main():
             line['dropin_op'] = run_dropin_op(dev, peak_gbs)
         except Exception as e:                                  # pragma: no cover
             line['dropin_op'] = {'error': repr(e)}
+
+        # ---- depth labels for the depth loss
+        try:
+            line['depth_labels'] = run_depth_labels_side(dev, peak_gbs)
+        except Exception as e:                                  # pragma: no cover
+            line['depth_labels'] = {'error': repr(e)}
 
         # ---- LiDAR branch (BASELINE.json configs[2]): hard voxelization + HardSimpleVFE mean + pillar scatter
         try:

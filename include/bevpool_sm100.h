@@ -261,6 +261,28 @@ int pillar_scatter_backward(const void *grad_canvas, const int32_t *coors, int64
                             int channels, int dtype, int batch, int nz, int ny, int nx,
                             void *grad_voxel_features, void *stream);
 
+/* ==== depth labels for the depth loss ================================================
+ * Replaces exps/mm_training_aim.py:115-162 (get_depth_labels / get_depth_image: python loop over batch x sweep x
+ * camera, projection of the LiDAR cloud into every image, `depth_map[v, u] = depth`) and :180-215
+ * (get_downsampled_gt_depth: min over each downsample x downsample block, bin index, one_hot).
+ *   sample_ptrs     DEVICE array of `batch` pointers to the samples' clouds, (Np_b, num_features) float32, xyz first
+ *   sample_counts   device int32[batch]: Np_b;  max_points = largest Np_b (host value, sizes the launch)
+ *   bda_inv         (batch, 3, 3) float32 = inverse(bda_mat[:3,:3]) (:126-127; the cloud is un-augmented with it)
+ *   extrinsics / intrinsics  (batch * images_per_sample, 4, 4) float32, images ordered (sweep, camera) like :120-125
+ *   bin_offset = d_bound[0] - d_bound[2], bin_step = d_bound[2] (as float32, :207-208)
+ *   labels          (batch * images_per_sample * (img_h/ds) * (img_w/ds), depth_channels) float32 one-hot, written once
+ *   bins            optional int32 per cell: the bin index (0 = no return / out of range); may be NULL
+ *   scratch         bevlabel_scratch_bytes(): one 64-bit word per full-resolution pixel.  The call leaves it zeroed;
+ *                   pass scratch_is_clean != 0 on later calls with the same buffer to skip the memset.
+ * Several points in one pixel: the LAST point in cloud order wins (the reference's CPU behaviour; its CUDA
+ * index_put_ picks an arbitrary one).  Arithmetic order: see csrc/depth_labels.cu.                                   */
+int bevlabel_scratch_bytes(int num_images, int img_h, int img_w, size_t *bytes);
+int bevlabel_depth_labels(const float *const *sample_ptrs, const int32_t *sample_counts, int num_features,
+                          int batch, int images_per_sample, int64_t max_points, const float *bda_inv,
+                          const float *extrinsics, const float *intrinsics, int img_h, int img_w,
+                          int downsample, float bin_offset, float bin_step, int depth_channels,
+                          float *labels, int32_t *bins, void *scratch, int scratch_is_clean, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
