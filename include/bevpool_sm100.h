@@ -283,6 +283,24 @@ int bevlabel_depth_labels(const float *const *sample_ptrs, const int32_t *sample
                           int downsample, float bin_offset, float bin_step, int depth_channels,
                           float *labels, int32_t *bins, void *scratch, int scratch_is_clean, void *stream);
 
+/* ==== depth distribution: softmax over D + depth-oracle overwrite in one pass ==========
+ * Replaces layers/backbones/lss_fpn.py:423 (`depth_feature[:, :D].softmax(1)`) and the oracle branch :427-434
+ * (max over D, two permute + contiguous copies, masked index_put, permuted view).
+ *   logits   (num_images, >= depth_bins, H, W): the first depth_bins channels of DepthNet's output, element type
+ *            `dtype`; consecutive images are logits_image_stride ELEMENTS apart (so the channel slice needs no copy)
+ *   oracle   optional float32 (num_images, depth_bins, H, W): pixels whose max over D is > 0 take the oracle's
+ *            distribution (:428-432); NULL = plain softmax
+ *   prob     float32 (num_images, depth_bins, H, W): the softmax (what the depth loss consumes, :466)
+ *   used     float32, same shape: the distribution the pooling consumes (required iff oracle != NULL)
+ * backward: grad_logits = prob * (g - sum_d prob * g), g = grad_prob + (pixel not overwritten ? grad_used : 0);
+ *           either gradient may be NULL; grad_logits (num_images, depth_bins, H, W) contiguous, element type `dtype`. */
+int bevdepth_softmax_forward(const void *logits, int dtype, int64_t logits_image_stride, const float *oracle,
+                             int num_images, int depth_bins, int feat_h, int feat_w, float *prob, float *used,
+                             void *stream);
+int bevdepth_softmax_backward(const float *prob, const float *grad_prob, const float *grad_used,
+                              const float *oracle, int num_images, int depth_bins, int feat_h, int feat_w,
+                              void *grad_logits, int dtype, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ def L():
 def _declared_symbols():
     text = open(os.path.join(ROOT, 'include', 'bevpool_sm100.h')).read()
     text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    return sorted(set(re.findall(r'\b((?:bevpool|bevvox|bevlabel|pillar)_[a-z0-9_]+)\s*\(', text)))
+    return sorted(set(re.findall(r'\b((?:bevpool|bevvox|bevlabel|bevdepth|pillar)_[a-z0-9_]+)\s*\(', text)))
 
 
 def test_every_declared_symbol_is_exported(L):
