@@ -310,7 +310,7 @@ def run_depth_labels_side(dev, peak_gbs, B=4):
     clouds, ext, intr, bda = case
     g_clouds, g_ext, g_intr, g_bda = [c.to(dev) for c in clouds], ext.to(dev), intr.to(dev), bda.to(dev)
     gen = DepthLabelGenerator(hw, cfg.downsample_factor, cfg.d_bound, D)
-    labels, bins = gen(g_clouds, g_ext, g_intr, g_bda, return_bins=True)
+    labels, bins = gen(g_clouds, g_ext, g_intr, g_bda, return_bins=True, bda_inv=torch.linalg.inv(bda[:, :3, :3].float()))
     _, ref_bins = dl.depth_labels_exact([clouds[0]], ext[:1], intr[:1], bda[:1], hw, cfg.downsample_factor, cfg.d_bound, D)
     n0 = ref_bins.numel()
     assert torch.equal(bins[:n0].cpu().long(), ref_bins), 'depth labels differ from the oracle'

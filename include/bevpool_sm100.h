@@ -163,12 +163,29 @@ int bevpool_fused_forward_runs_nchw(const void *plan, const void *depth, const v
                                     void *out_nhwc, int dtype, int batch, int num_cams, int depth_bins,
                                     int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
                                     void *run_rows, int64_t run_rows_capacity, void *workspace, void *stream);
+/* Concat epilogue (models/bev_depth.py:187-189, `torch.cat([img_bev, lidar_bev], dim=1)`; also replaces the
+ * `.contiguous()` of lss_fpn.py:466 for channels-last consumers): the same forward, writing its rows into a wider
+ * channels-last buffer (B, Y, X, C_total).  out_rows = address of the first camera channel of cell 0; consecutive
+ * cells are out_row_stride floats apart (>= channels, multiple of 4); the other channels of a row are not touched.  */
+int bevpool_fused_forward_runs_into(const void *plan, const void *depth, const void *context, int context_is_nchw,
+                                    void *out_rows, int64_t out_row_stride, int dtype, int batch, int num_cams,
+                                    int depth_bins, int feat_h, int feat_w, int channels, int num_voxel_x,
+                                    int num_voxel_y, void *run_rows, int64_t run_rows_capacity, void *workspace,
+                                    void *stream);
 /* backward on a RUN plan (pair records): context / grad_context as pixel rows (B*N, H, W, C) or, with
  * context_is_nchw != 0, as (B*N, C, H, W).  bevpool_fused_backward above accepts any plan (point plans included). */
 int bevpool_fused_backward_runs(const void *plan, const void *grad_out_nhwc, const void *depth,
                                 const void *context, void *grad_depth, void *grad_context, int context_is_nchw,
                                 int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
                                 int channels, int num_voxel_x, int num_voxel_y, void *stream);
+
+/* ... and its counterpart for the gradient of a concatenated buffer: the gradient row of cell c starts at
+ * grad_rows + c * grad_row_stride floats (>= channels, multiple of 4).  Needs feat_w % 4 == 0.                     */
+int bevpool_fused_backward_runs_from(const void *plan, const void *grad_rows, int64_t grad_row_stride,
+                                     const void *depth, const void *context, void *grad_depth, void *grad_context,
+                                     int context_is_nchw, int dtype, int batch, int num_cams, int depth_bins,
+                                     int feat_h, int feat_w, int channels, int num_voxel_x, int num_voxel_y,
+                                     void *stream);
 
 /* ---- run plan straight from the camera rig: no geom_xyz tensor -------------------------------------
  * Replaces layers/backbones/lss_fpn.py:328-361 (get_geometry) + :461-462 (index quantisation) as the

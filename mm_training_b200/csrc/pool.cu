@@ -545,15 +545,15 @@ static int launch_forward(const PlanView &pv, const T *rows, const T *depth, T *
       if (u == 2) {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 2><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, (int64_t)INT32_MAX)));
+                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, (int64_t)INT32_MAX, (int64_t)C)));
       } else {
         BEVPOOL_G8_DISPATCH(C, (pool_forward_share_kernel<NV2, kFused, 4><<<ctas, kFwWarpsPerCta * 32, 0, s>>>(
                                    pv.cell_start, pv.sorted_ids, pv.sorted_cells, rows, depth, out, ws_head, ws_tail,
-                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, (int64_t)INT32_MAX)));
+                                   (int64_t)0, total_cells, fd_dhw, fd_hw, cps, (int64_t)INT32_MAX, (int64_t)C)));
       }
       BEVPOOL_LAUNCH_CHECK();
       BEVPOOL_G8_DISPATCH(C, (pool_forward_fixup_kernel<NV2><<<(unsigned)ceil_div64((int64_t)slices * 8, 128), 128, 0, s>>>(
-                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, (int64_t)0, total_cells, slices, (int64_t)INT32_MAX)));
+                                 pv.cell_start, pv.sorted_cells, ws_head, ws_tail, out, (int64_t)0, total_cells, slices, (int64_t)INT32_MAX, (int64_t)C)));
       BEVPOOL_LAUNCH_CHECK();
       return BEVPOOL_OK;
     }
@@ -615,7 +615,7 @@ static int fused_forward_t(const void *plan, const void *depth, const void *ctx,
 template <typename T>
 static int fused_backward_t(const void *plan, const void *grad, const void *depth, const void *ctx,
                             void *gdepth, void *gctx, int B, int N, int D, int H, int W, int C, int X,
-                            int Y, cudaStream_t s, bool nchw = false, bool runs = false) {
+                            int Y, cudaStream_t s, bool nchw = false, bool runs = false, int64_t g_stride = 0) {
   const int64_t Np = (int64_t)N * D * H * W;
   const PlanView pv = plan_view(plan, B, Np, X, Y);
   const int C4 = C >> 2;
@@ -629,7 +629,8 @@ static int fused_backward_t(const void *plan, const void *grad, const void *dept
       // run plans (pair records): column kernel (pool_bwd2.cu; needs W % 4 == 0); else tile kernel (pool_bwd.cu; C <= 96)
       static const int which = env_int("BEVPOOL_BW_KERNEL", 2);
       if (runs && which == 2 && fused_backward_col_supported(C, W, dp, gd, pv.cell_of_point))
-        return launch_fused_backward_col(pv.cell_of_point, pv.pair_rec, g, dp, cx, gd, gc, nchw, B, N, D, H, W, C, cells, s);
+        return launch_fused_backward_col(pv.cell_of_point, pv.pair_rec, g, dp, cx, gd, gc, nchw, B, N, D, H, W, C, cells, s, g_stride);
+      if (g_stride != 0 && g_stride != C) return BEVPOOL_E_ALIGN;     // strided gradient rows exist only on the column kernel
       if (!nchw && fused_backward_tile_supported(C))
         return launch_fused_backward_tile(pv.cell_of_point, g, dp, cx, gd, gc, B, N, D, H, W, C, cells, s);
     }
@@ -728,6 +729,28 @@ extern "C" int bevpool_fused_backward_runs(const void *plan, const void *grad_ou
   return fused_backward_t<float>(plan, grad_out_nhwc, depth, context, grad_depth, grad_context, batch, num_cams,
                                  depth_bins, feat_h, feat_w, channels, X, Y, static_cast<cudaStream_t>(stream),
                                  context_is_nchw != 0, true);
+}
+
+// gradient rows inside a wider channels-last buffer (the gradient of a concatenated BEV feature map): row of cell c
+// starts at grad_rows + c * grad_row_stride floats
+extern "C" int bevpool_fused_backward_runs_from(const void *plan, const void *grad_rows, int64_t grad_row_stride,
+                                                const void *depth, const void *context, void *grad_depth,
+                                                void *grad_context, int context_is_nchw, int dtype, int batch,
+                                                int num_cams, int depth_bins, int feat_h, int feat_w, int channels,
+                                                int X, int Y, void *stream) {
+  if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
+  int rc = check_plan_dims(batch, np, X, Y);
+  if (rc) return rc;
+  if (dtype != BEVPOOL_F32) return BEVPOOL_E_DTYPE;
+  if (!g8_supported(channels)) return BEVPOOL_E_CHANNELS;
+  if (!plan || !grad_rows || !depth || !context || !grad_depth || !grad_context) return BEVPOOL_E_ARG;
+  if (grad_row_stride < channels || (grad_row_stride % 4) != 0) return BEVPOOL_E_ARG;
+  if (!aligned16(grad_rows) || !aligned16(context) || !aligned16(grad_context)) return BEVPOOL_E_ALIGN;
+  if ((feat_w % 4) != 0 || !aligned16(depth) || !aligned16(grad_depth)) return BEVPOOL_E_ALIGN;
+  return fused_backward_t<float>(plan, grad_rows, depth, context, grad_depth, grad_context, batch, num_cams,
+                                 depth_bins, feat_h, feat_w, channels, X, Y, static_cast<cudaStream_t>(stream),
+                                 context_is_nchw != 0, true, grad_row_stride);
 }
 
 extern "C" int bevpool_grad_rows(const void *plan, const void *grad_out_nchw, void *rows_nhwc, int dtype,

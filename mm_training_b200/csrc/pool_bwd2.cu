@@ -86,7 +86,7 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
                           const float *__restrict__ grad_rows, const float *__restrict__ depth,
                           const float *__restrict__ ctx_nhwc, float *__restrict__ grad_depth,
                           float *__restrict__ grad_ctx_nhwc, int num_cams, int D, int H, int W,
-                          int64_t cells_per_sample, int tiles_h, int tiles_w) {
+                          int64_t cells_per_sample, int tiles_h, int tiles_w, int64_t g_stride) {
   pdl_wait();
   pdl_trigger();
   using S = BcSmem<NV2>;
@@ -112,7 +112,7 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
   const int h0 = th * kBcTH, w0 = tw * kBcTW;
   const int HW = H * W;
   const int64_t img_base = (int64_t)bn * D * HW;
-  const float *gbase = grad_rows + (int64_t)(bn / num_cams) * cells_per_sample * C;
+  const float *gbase = grad_rows + (int64_t)(bn / num_cams) * cells_per_sample * g_stride;   // rows may sit in a wider buffer
   const int nchunks = (D + kBcDC - 1) / kBcDC;
   // pair records of this tile: index (((bn * D + d) * tiles_h + th) * W + w0 + column)
   const int4 *rec_base = pair_rec + ((int64_t)bn * D * tiles_h + th) * W + w0;
@@ -189,7 +189,7 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
         const int row = rs + 16 * k;
         const int cell = recs[row].x;
         if (cell >= 0) {
-          const float4 *src = reinterpret_cast<const float4 *>(gbase + (int64_t)cell * C) + e8;
+          const float4 *src = reinterpret_cast<const float4 *>(gbase + (int64_t)cell * g_stride) + e8;
           float4 *dst = reinterpret_cast<float4 *>(dst0 + row * C) + e8;
 #pragma unroll
           for (int v = 0; v < (C4 + 7) / 8; ++v)
@@ -360,7 +360,7 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
               const int cell = __ldg(cell_of_point + gp);
               const float dv = __ldg(depth + gp);
               float gs[NREG];
-              g8_load_row<NV2, false>(reinterpret_cast<const char *>(gbase + (int64_t)cell * C), l8, gs);
+              g8_load_row<NV2, false>(reinterpret_cast<const char *>(gbase + (int64_t)cell * g_stride), l8, gs);
               float2 da = make_float2(0.f, 0.f);
 #pragma unroll
               for (int r = 0; r < NREG; r += 2)
@@ -418,13 +418,13 @@ template <int NV2, bool kNchw>
 static int launch_bc(const CUtensorMap &ctx_map, const CUtensorMap &gctx_map, const int32_t *cell_of_point,
                      const int4 *pair_rec, const float *grad_rows, const float *depth, const float *ctx_nhwc, float *grad_depth,
                      float *grad_ctx_nhwc, int num_cams, int D, int H, int W, int64_t cells_per_sample, int64_t ctas,
-                     int tiles_h, int tiles_w, cudaStream_t s) {
+                     int tiles_h, int tiles_w, int64_t g_stride, cudaStream_t s) {
   constexpr size_t smem = BcSmem<NV2>::bytes;
   BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_col_kernel<NV2, kNchw>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BEVPOOL_RETURN_IF_CUDA(launch_pdl(fused_backward_col_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kBcThreads), smem, s,
                                     ctx_map, gctx_map, cell_of_point, pair_rec, grad_rows, depth, ctx_nhwc, grad_depth, grad_ctx_nhwc,
-                                    num_cams, D, H, W, cells_per_sample, tiles_h, tiles_w));
+                                    num_cams, D, H, W, cells_per_sample, tiles_h, tiles_w, g_stride));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -436,7 +436,8 @@ bool fused_backward_col_supported(int C, int W, const void *depth, const void *g
 // context / grad_context: NCHW (B*N, C, H, W) when `nchw`, else pixel rows (B*N, H, W, C)
 int launch_fused_backward_col(const int32_t *cell_of_point, const int4 *pair_rec, const float *grad_rows, const float *depth,
                               const float *ctx, float *grad_depth, float *grad_ctx, bool nchw, int batch, int num_cams,
-                              int D, int H, int W, int C, int64_t cells_per_sample, cudaStream_t s) {
+                              int D, int H, int W, int C, int64_t cells_per_sample, cudaStream_t s, int64_t grad_row_stride) {
+  if (grad_row_stride <= 0) grad_row_stride = C;
   const int64_t tiles_h = ceil_div64(H, kBcTH), tiles_w = ceil_div64(W, kBcTW);
   const int64_t ctas = (int64_t)batch * num_cams * tiles_h * tiles_w;
   if (ctas >= (int64_t)INT32_MAX) return BEVPOOL_E_RANGE;
@@ -451,7 +452,7 @@ int launch_fused_backward_col(const int32_t *cell_of_point, const int4 *pair_rec
   }
   int rc = BEVPOOL_OK;
 #define BEVPOOL_BC_ARGS ctx_map, gctx_map, cell_of_point, pair_rec, grad_rows, depth, ctx, grad_depth, grad_ctx, num_cams, D, H, W, \
-                        cells_per_sample, ctas, (int)tiles_h, (int)tiles_w, s
+                        cells_per_sample, ctas, (int)tiles_h, (int)tiles_w, grad_row_stride, s
   if (nchw) { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, true>(BEVPOOL_BC_ARGS))); }
   else { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, false>(BEVPOOL_BC_ARGS))); }
 #undef BEVPOOL_BC_ARGS

@@ -155,7 +155,7 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
                           const float *__restrict__ depth, float *__restrict__ out,
                           float *__restrict__ ws_head, float *__restrict__ ws_tail, int64_t cell_base,
                           int64_t total_cells, FastDiv div_dhw, FastDiv div_hw, int fill_period,
-                          int64_t row_capacity) {
+                          int64_t row_capacity, int64_t out_stride) {
   pdl_wait();
   pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2, C4 = C / 4;
@@ -185,10 +185,16 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
       const int ncell = (int)min((int64_t)32, c_end - c0);
       const unsigned occ = __ballot_sync(kFull, ce > cs);
       if (occ != kFull) {
-        float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
+        if (out_stride == C) {
+          float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
 #pragma unroll 4
-        for (int i = lane; i < ncell * C4; i += 32)
-          if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(o4 + i, z);
+          for (int i = lane; i < ncell * C4; i += 32)
+            if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(o4 + i, z);
+        } else {                               // rows inside a wider buffer (concatenated BEV features)
+#pragma unroll 4
+          for (int i = lane; i < ncell * C4; i += 32)
+            if (!((occ >> (i / C4)) & 1u)) stg_stream_f4(reinterpret_cast<float4 *>(out + (c0 + i / C4) * out_stride) + i % C4, z);
+        }
       }
       cs = cs_n;
       ce = ce_n;
@@ -282,7 +288,7 @@ pool_forward_share_kernel(const int32_t *__restrict__ cell_start, const int32_t 
             g8_store_row<NV2>(reinterpret_cast<char *>(head_row), l8, acc);
             in_head = false;
           } else {
-            g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)kk[u] * C), l8, acc);
+            g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)kk[u] * out_stride), l8, acc);
           }
 #pragma unroll
           for (int r = 0; r < NREG; ++r) acc[r] = 0.f;
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(128)
 pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t *__restrict__ sorted_cells,
                           const float *__restrict__ ws_head, const float *__restrict__ ws_tail,
                           float *__restrict__ out, int64_t cell_base, int64_t total_cells, int num_slices,
-                          int64_t row_capacity) {
+                          int64_t row_capacity, int64_t out_stride) {
   pdl_wait();
   pdl_trigger();
   constexpr int C = 16 * NV2, NREG = 2 * NV2;
@@ -327,7 +333,7 @@ pool_forward_fixup_kernel(const int32_t *__restrict__ cell_start, const int32_t 
     for (int r = 0; r < NREG; ++r) acc[r] += v[r];
     if (!(thi < K && __ldg(sorted_cells + thi - 1) == key && __ldg(sorted_cells + thi) == key)) break;
   }
-  g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)key * C), l8, acc);
+  g8_store_row<NV2>(reinterpret_cast<char *>(out + (size_t)key * out_stride), l8, acc);
 }
 
 inline bool g8_supported(int C) {

@@ -98,7 +98,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
                       const float *__restrict__ ctx_nhwc, float *__restrict__ run_rows,
                       const int32_t *__restrict__ cell_start, float *__restrict__ out, int32_t *__restrict__ status,
                       int img0, int64_t cell_base, int64_t num_cells, int D, int H, int W, int d_split, int d_per_cta,
-                      int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints) {
+                      int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints, int64_t out_stride) {
   pdl_wait();
   pdl_trigger();
   using S = RaSmem<NV2>;
@@ -240,7 +240,7 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
         const int ncell = (int)min((int64_t)kRaZeroCells, num_cells - off);
         const int64_t c0 = cell_base + off;
         const unsigned em = __ballot_sync(kFull, lane < ncell && ce[a] == cs[a]);
-        if (ncell == kRaZeroCells && em == kFull) {
+        if (ncell == kRaZeroCells && em == kFull && out_stride == C) {
           if (lane == 0) {
             if (hints) tma_store_1d_hint(out + c0 * C, s_zero, kRaZeroCells * C * 4, l2_policy_evict_first());
             else tma_store_1d(out + c0 * C, s_zero, kRaZeroCells * C * 4);
@@ -248,10 +248,16 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
           }
         } else if (em) {
           const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
+          if (out_stride == C) {
+            float4 *o4 = reinterpret_cast<float4 *>(out + c0 * C);
 #pragma unroll 4
-          for (int i = lane; i < ncell * C4; i += 32)
-            if ((em >> (i / C4)) & 1u) stg_stream_f4(o4 + i, z);
+            for (int i = lane; i < ncell * C4; i += 32)
+              if ((em >> (i / C4)) & 1u) stg_stream_f4(o4 + i, z);
+          } else {                                           // rows inside a wider (concatenated) buffer: C floats every out_stride
+#pragma unroll 4
+            for (int i = lane; i < ncell * C4; i += 32)
+              if ((em >> (i / C4)) & 1u) stg_stream_f4(reinterpret_cast<float4 *>(out + (c0 + i / C4) * out_stride) + i % C4, z);
+          }
         }
       }
     }
@@ -375,7 +381,8 @@ using namespace bevpool;
 template <int NV2, bool kNchw>
 static int launch_stage_a(const CUtensorMap &ctx_map, const PlanView &pv, const float *dp, const float *cx, float *rr,
                           float *out, int32_t *status, int img0, int64_t cell_base, int64_t num_cells, int nb, int num_cams,
-                          int D, int H, int W, int64_t capacity, int vec, int fill, int hints, int d_split, cudaStream_t s) {
+                          int D, int H, int W, int64_t capacity, int vec, int fill, int hints, int d_split, int64_t out_stride,
+                          cudaStream_t s) {
   constexpr int C = 16 * NV2;
   const int tiles_h = (int)ceil_div64(H, kRunHB), tiles_w = (int)ceil_div64(W, kRaTW);
   const int d_per_cta = (int)(ceil_div64(ceil_div64(D, d_split), kRaDC) * kRaDC);      // whole chunks per CTA
@@ -388,7 +395,7 @@ static int launch_stage_a(const CUtensorMap &ctx_map, const PlanView &pv, const 
     BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2, kNchw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
       ctx_map, pv.run_code, pv.pair_rec, dp, cx, rr, pv.cell_start, out, status, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
-      tiles_w, capacity, vec, fill, hints));
+      tiles_w, capacity, vec, fill, hints, out_stride));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -423,7 +430,9 @@ static const RunKnobs &run_knobs() {
 static int fused_forward_runs_impl(const void *plan, const void *depth, const void *context, bool nchw, void *out_nhwc,
                                    int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
                                    int channels, int X, int Y, void *run_rows, int64_t run_rows_capacity,
-                                   void *workspace, void *stream) {
+                                   void *workspace, void *stream, int64_t out_stride = 0) {
+  if (out_stride == 0) out_stride = channels;
+  if (out_stride < channels || (out_stride % 4) != 0) return BEVPOOL_E_ARG;
   if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
   const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
   int rc = check_plan_dims(batch, np, X, Y);
@@ -465,10 +474,10 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
     }
     if (nchw) {
       BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2, true>(ctx_map, pv, dp, cx, rr, out, status, b0 * num_cams, cell_base, ncells, nb, num_cams,
-                                                                    depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, s)));
+                                                                    depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, out_stride, s)));
     } else {
       BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2, false>(ctx_map, pv, dp, cx, rr, out, status, b0 * num_cams, cell_base, ncells, nb, num_cams,
-                                                                     depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, s)));
+                                                                     depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, out_stride, s)));
     }
     if (rc) return rc;
     // stage B: even-share segmented sum of the run rows (identity ids), fill CTAs only if stage A did not fill
@@ -481,13 +490,13 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
     BEVPOOL_G8_DISPATCH(channels, (le = launch_pdl_if(pdl_forward_enabled(), pool_forward_share_kernel<NV2, false, 4, true>, dim3(ctas_b),
                                                    dim3(kFwWarpsPerCta * 32), 0, s, pv.cell_start, (const int32_t *)nullptr,
                                                    pv.sorted_cells, (const float *)rr, (const float *)nullptr, out, ws_head,
-                                                   ws_tail, cell_base, ncells, one, one, period_b, run_rows_capacity)));
+                                                   ws_tail, cell_base, ncells, one, one, period_b, run_rows_capacity, out_stride)));
     BEVPOOL_RETURN_IF_CUDA(le);
     BEVPOOL_LAUNCH_CHECK();
     BEVPOOL_G8_DISPATCH(channels, (le = launch_pdl_if(pdl_forward_enabled(), pool_forward_fixup_kernel<NV2>,
                                                    dim3((unsigned)ceil_div64((int64_t)slices * 8, 128)), dim3(128), 0, s,
                                                    pv.cell_start, pv.sorted_cells, (const float *)ws_head,
-                                                   (const float *)ws_tail, out, cell_base, ncells, slices, run_rows_capacity)));
+                                                   (const float *)ws_tail, out, cell_base, ncells, slices, run_rows_capacity, out_stride)));
     BEVPOOL_RETURN_IF_CUDA(le);
     BEVPOOL_LAUNCH_CHECK();
   }
@@ -508,4 +517,17 @@ extern "C" int bevpool_fused_forward_runs_nchw(const void *plan, const void *dep
                                                int64_t run_rows_capacity, void *workspace, void *stream) {
   return fused_forward_runs_impl(plan, depth, context_nchw, true, out_nhwc, dtype, batch, num_cams, depth_bins, feat_h,
                                  feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream);
+}
+
+// Concat epilogue (models/bev_depth.py:187-189: `torch.cat([img_bev, lidar_bev], dim=1)`): the pooled rows are written
+// straight into a wider channels-last buffer -- out points at the first camera channel of cell 0, consecutive cells are
+// out_row_stride floats apart -- so neither lss_fpn.py:466's `.contiguous()` nor the cat copies the camera half.
+extern "C" int bevpool_fused_forward_runs_into(const void *plan, const void *depth, const void *context,
+                                               int context_is_nchw, void *out_rows, int64_t out_row_stride, int dtype,
+                                               int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                                               int channels, int X, int Y, void *run_rows, int64_t run_rows_capacity,
+                                               void *workspace, void *stream) {
+  if (out_row_stride <= 0) return BEVPOOL_E_ARG;
+  return fused_forward_runs_impl(plan, depth, context, context_is_nchw != 0, out_rows, dtype, batch, num_cams, depth_bins,
+                                 feat_h, feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream, out_row_stride);
 }

@@ -38,9 +38,10 @@ class DepthLabelGenerator:
         self._clean = False
 
     def __call__(self, pointclouds: Sequence[torch.Tensor], extrinsics: torch.Tensor, intrinsics: torch.Tensor,
-                 bda_mats: torch.Tensor, return_bins: bool = False):
+                 bda_mats: torch.Tensor, return_bins: bool = False, bda_inv: torch.Tensor = None):
         """pointclouds: list of B float32 (Np_b, F >= 3) CUDA tensors; extrinsics / intrinsics (B, S, C, 4, 4);
-        bda_mats (B, 4, 4).  Returns the one-hot labels (B*S*C*h*w, D) (and the int32 bin per cell)."""
+        bda_mats (B, 4, 4).  Returns the one-hot labels (B*S*C*h*w, D) (and the int32 bin per cell).  ``bda_inv``
+        (B, 3, 3): a precomputed ``inverse(bda_mats[:, :3, :3])`` to use instead of inverting here."""
         _lib.require_cuda(extrinsics, intrinsics, bda_mats, *pointclouds)
         B = len(pointclouds)
         assert extrinsics.shape[0] == B and extrinsics.shape[-2:] == (4, 4) and intrinsics.shape == extrinsics.shape
@@ -63,7 +64,9 @@ class DepthLabelGenerator:
             ptrs = _pointer_table(tuple(p.data_ptr() for p in clouds), dev)
             cnt = torch.tensor(counts, dtype=torch.int32).to(dev, non_blocking=True)
             # :126-127 -- inverse(bda_mat[:3,:3]); B tiny matrices, left in torch (same LU kernels as the reference)
-            bda_inv = torch.linalg.inv(bda_mats[:, :3, :3].float()).contiguous()
+            if bda_inv is None:
+                bda_inv = torch.linalg.inv(bda_mats[:, :3, :3].float())
+            bda_inv = bda_inv.to(dev).float().contiguous()
             ext = extrinsics.float().contiguous()
             intr = intrinsics.float().contiguous()
             cells = images * (self.H // self.ds) * (self.W // self.ds)
@@ -80,7 +83,7 @@ class DepthLabelGenerator:
 
 @torch.no_grad()
 def depth_labels(pointclouds, extrinsics, intrinsics, bda_mats, image_hw, downsample_factor, d_bound, depth_channels,
-                 return_bins: bool = False):
+                 return_bins: bool = False, bda_inv: torch.Tensor = None):
     """One-shot form of ``DepthLabelGenerator`` (allocates the scratch per call)."""
     return DepthLabelGenerator(image_hw, downsample_factor, d_bound, depth_channels)(
-        pointclouds, extrinsics, intrinsics, bda_mats, return_bins)
+        pointclouds, extrinsics, intrinsics, bda_mats, return_bins, bda_inv)

@@ -470,3 +470,85 @@ def voxel_pooling_fused(geom_xyz: Optional[torch.Tensor], depth: torch.Tensor, c
     softmax probabilities; context (B*N, C, H, W), NCHW or channels_last.  Returns (B, C, Y, X)
     as a permuted view of a (B, Y, X, C) buffer, like the reference op."""
     return VoxelPoolingFused.apply(geom_xyz, depth, context, voxel_num, plan)
+
+
+class VoxelPoolingFusedConcat(Function):
+    """``torch.cat([voxel_pooling_fused(...), other_bev], dim=1)`` without the copies of the camera half."""
+
+    @staticmethod
+    def forward(ctx, depth, context, other_bev, voxel_num, plan):
+        _lib.require_cuda(depth, context, other_bev)
+        X, Y, _ = _voxel_num_ints(voxel_num)
+        BN, D, H, W = depth.shape
+        C = context.shape[1]
+        B = plan.batch
+        N = BN // B
+        assert other_bev.shape[0] == B and tuple(other_bev.shape[2:]) == (Y, X)
+        C2 = other_bev.shape[1]
+        Ct = C + C2
+        nchw = _nchw_direct(context, depth)
+        rows = None if nchw else context_rows_nhwc(context)
+        with torch.cuda.device(depth.device):
+            buf = torch.empty(B, Y, X, Ct, dtype=torch.float32, device=depth.device)
+            cap = max(1, plan.num_sorted)
+            run_rows = torch.empty(cap, C, dtype=torch.float32, device=depth.device)
+            ws = _forward_workspace(C, depth.device)
+            _lib.check(_lib.lib().bevpool_fused_forward_runs_into(
+                plan.ptr, depth.data_ptr(), (context if nchw else rows).data_ptr(), 1 if nchw else 0, buf.data_ptr(), Ct,
+                _lib.dtype_code(depth), B, N, D, H, W, C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(),
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_forward_runs_into')
+            buf[..., C:].copy_(other_bev.permute(0, 2, 3, 1))          # the other half: the one copy a cat cannot avoid
+        ctx.plan, ctx.nchw, ctx.C, ctx.other_dtype = plan, nchw, C, other_bev.dtype
+        if nchw:
+            ctx.save_for_backward(depth, context)
+        else:
+            ctx.save_for_backward(depth, context, rows)
+        return buf.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_cat):
+        plan, C = ctx.plan, ctx.C
+        if ctx.nchw:
+            (depth, context), rows = ctx.saved_tensors, None
+        else:
+            depth, context, rows = ctx.saved_tensors
+        BN, D, H, W = depth.shape
+        B = plan.batch
+        N = BN // B
+        X, Y, _ = plan.voxel_num
+        g = grad_cat.permute(0, 2, 3, 1)
+        if not g.is_contiguous() or g.dtype != torch.float32:           # channels_last gradients (the usual case) pass as they are
+            g = g.float().contiguous()
+        Ct = g.shape[-1]
+        with torch.cuda.device(depth.device):
+            grad_depth = torch.empty_like(depth)
+            if ctx.nchw:
+                grad_context = torch.empty_like(context)
+                gc_arg = grad_context
+            else:
+                gc_arg = torch.empty(BN, H, W, C, dtype=context.dtype, device=context.device)
+            _lib.check(_lib.lib().bevpool_fused_backward_runs_from(
+                plan.ptr, g.data_ptr(), Ct, depth.data_ptr(), (context if ctx.nchw else rows).data_ptr(),
+                grad_depth.data_ptr(), gc_arg.data_ptr(), 1 if ctx.nchw else 0, _lib.dtype_code(depth), B, N, D, H, W, C, X, Y,
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_backward_runs_from')
+            if not ctx.nchw:
+                if context.permute(0, 2, 3, 1).is_contiguous():
+                    grad_context = gc_arg.permute(0, 3, 1, 2)
+                else:
+                    grad_context = _transpose(gc_arg, BN, H * W, C).view(BN, C, H, W)
+        grad_other = g[..., C:].permute(0, 3, 1, 2).to(ctx.other_dtype)
+        return grad_depth, grad_context, grad_other, None, None
+
+
+def voxel_pooling_fused_concat(depth: torch.Tensor, context: torch.Tensor, other_bev: torch.Tensor, voxel_num: VoxelNum,
+                               plan: PoolingPlan) -> torch.Tensor:
+    """Concat epilogue of the camera branch (``models/bev_depth.py:187-189``): returns
+    ``torch.cat([voxel_pooling_fused(None, depth, context, voxel_num, plan), other_bev], dim=1)`` as a float32
+    channels-last tensor.  On a run plan (fp32, W % 4 == 0) the pooled rows are written straight into the concatenated
+    buffer and the backward reads its gradient rows straight out of the concatenated gradient -- neither
+    ``lss_fpn.py:466``'s ``.contiguous()`` nor the cat copies the camera half; other cases compose the two stock ops."""
+    C = context.shape[1]
+    if (plan.mode == 'runs' and runs_supported(C, depth.dtype) and depth.shape[3] % 4 == 0 and other_bev.shape[1] % 4 == 0
+            and depth.is_contiguous()):
+        return VoxelPoolingFusedConcat.apply(depth, context, other_bev, voxel_num, plan)
+    return torch.cat([voxel_pooling_fused(None, depth, context, voxel_num, plan), other_bev.to(depth.dtype)], dim=1)

@@ -212,3 +212,34 @@ def test_stale_max_runs_hint_is_flagged_not_fatal():
     assert stale.status() == 1
     with pytest.raises(RuntimeError):
         stale.raise_if_overflowed()
+
+
+# ---------------------------------------------------------------- concat epilogue (bev_depth.py:187-189)
+@pytest.mark.parametrize('channels_last_ctx', [False, True])
+@pytest.mark.parametrize('c2', [256, 4])
+def test_concat_epilogue_equals_cat_of_the_stock_op(channels_last_ctx, c2):
+    from mm_training_b200.ops.voxel_pooling import voxel_pooling_fused_concat
+    cfg, B = CFG_2, 3
+    geom, vn_t = synthetic.camera_rig(cfg, B, device=DEV, yaw_jitter_deg=5.0, seed=8)
+    vn = tuple(int(v) for v in vn_t.tolist())
+    depth, ctx, _ = synthetic.camera_features(cfg, B, device=DEV, seed=8)
+    if channels_last_ctx:
+        ctx = ctx.contiguous(memory_format=torch.channels_last)
+    X, Y, _ = vn
+    g = torch.Generator().manual_seed(2)
+    other = torch.randn(B, c2, Y, X, generator=g).to(DEV)
+    go = torch.rand(B, cfg.output_channels + c2, Y, X, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    plan = build_plan(geom, vn, frustum=tuple(geom.shape[1:5]))
+    d1, c1, o1 = depth.clone().requires_grad_(True), ctx.clone().requires_grad_(True), other.clone().requires_grad_(True)
+    d2, c2_, o2 = depth.clone().requires_grad_(True), ctx.clone().requires_grad_(True), other.clone().requires_grad_(True)
+    cat = voxel_pooling_fused_concat(d1, c1, o1, vn, plan)
+    ref = torch.cat([voxel_pooling_fused(None, d2, c2_, vn, plan), o2], dim=1)
+    assert cat.shape == ref.shape and cat.permute(0, 2, 3, 1).is_contiguous()
+    assert torch.equal(cat, ref)                                       # same kernels, same order: bit-equal
+    cat.backward(go)
+    ref.backward(go)
+    assert torch.equal(d1.grad, d2.grad) and torch.equal(c1.grad, c2_.grad) and torch.equal(o1.grad, o2.grad)
+    go_nchw = go.contiguous()                                           # an NCHW gradient takes the copying path: same values
+    d1.grad = c1.grad = o1.grad = None
+    voxel_pooling_fused_concat(d1, c1, o1, vn, plan).backward(go_nchw)
+    assert torch.equal(d1.grad, d2.grad) and torch.equal(c1.grad, c2_.grad) and torch.equal(o1.grad, o2.grad)
