@@ -172,6 +172,15 @@ int bevpool_fused_forward_runs_into(const void *plan, const void *depth, const v
                                     int depth_bins, int feat_h, int feat_w, int channels, int num_voxel_x,
                                     int num_voxel_y, void *run_rows, int64_t run_rows_capacity, void *workspace,
                                     void *stream);
+/* Softmax folded into the forward (lss_fpn.py:423 + :441-443): the kernel reads DepthNet's output tensor itself --
+ * depth_feature (B*N, feature_channels, H, W) fp32 NCHW, logits in channels [0, depth_bins), context in channels
+ * [context_channel_offset, +channels) -- so neither the probability tensor nor the channel slices are ever made.
+ * stats: scratch of 8 * B*N * feat_h * feat_w bytes.  out_rows / out_row_stride as in ..._runs_into (0 = channels).  */
+int bevpool_fused_forward_runs_logits(const void *plan, const void *depth_feature, int feature_channels,
+                                      int context_channel_offset, void *stats, void *out_rows, int64_t out_row_stride,
+                                      int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
+                                      int channels, int num_voxel_x, int num_voxel_y, void *run_rows,
+                                      int64_t run_rows_capacity, void *workspace, void *stream);
 /* backward on a RUN plan (pair records): context / grad_context as pixel rows (B*N, H, W, C) or, with
  * context_is_nchw != 0, as (B*N, C, H, W).  bevpool_fused_backward above accepts any plan (point plans included). */
 int bevpool_fused_backward_runs(const void *plan, const void *grad_out_nhwc, const void *depth,

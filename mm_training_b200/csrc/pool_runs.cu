@@ -91,14 +91,18 @@ __device__ __forceinline__ void nchw_box_to_rows(float *s_ctx, int tid) {
 // does no voting.  The staging threads transpose the depths to [bin][column][row] and zero the rows that are not
 // kept, so the reduction loop is branch-free over the rows (4 depths = one LDS.128).  Pairs holding several runs
 // (tilted cameras, random geometry) take a per-row path that reads run_code from global memory.
-template <int NV2, bool kNchw>
+// kLogits: `depth` holds the DepthNet LOGITS (lss_fpn.py:423 folded in): consecutive images are dep_img_stride floats
+// apart (a channel slice of depth_feature needs no copy) and `stats` holds {max, 1 / sum exp(l - max)} per pixel
+// (depth_stats_kernel below); the staging threads turn a logit into its probability while they transpose it.
+template <int NV2, bool kNchw, bool kLogits = false>
 __global__ void __launch_bounds__(kRaThreads, 4)
 frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t *__restrict__ run_code,
                       const int4 *__restrict__ pair_rec, const float *__restrict__ depth,
                       const float *__restrict__ ctx_nhwc, float *__restrict__ run_rows,
                       const int32_t *__restrict__ cell_start, float *__restrict__ out, int32_t *__restrict__ status,
                       int img0, int64_t cell_base, int64_t num_cells, int D, int H, int W, int d_split, int d_per_cta,
-                      int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints, int64_t out_stride) {
+                      int tiles_h, int tiles_w, int64_t capacity, int vec, int fill, int hints, int64_t out_stride,
+                      int64_t dep_img_stride, const float2 *__restrict__ stats) {
   pdl_wait();
   pdl_trigger();
   using S = RaSmem<NV2>;
@@ -154,7 +158,17 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
   // fetch the chunk's 16 x 4 pair records.
   const int sh = tid & 15, sd = tid >> 4;
   const bool srow = h0 + sh < H;
-  const int64_t sbase = (int64_t)bn * D * HW + (int64_t)(h0 + sh) * W + w0;
+  const int64_t sbase = (int64_t)bn * dep_img_stride + (int64_t)(h0 + sh) * W + w0;
+  float smax[4] = {0.f, 0.f, 0.f, 0.f}, srcp[4] = {0.f, 0.f, 0.f, 0.f};     // kLogits: softmax statistics of this thread's 4 pixels
+  if (kLogits && srow) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (w0 + c < W) {
+        const float2 st = __ldg(stats + (int64_t)bn * HW + (int64_t)(h0 + sh) * W + w0 + c);
+        smax[c] = st.x;
+        srcp[c] = st.y;
+      }
+  }
   const int nchunks = (d_end - d_begin + kRaDC - 1) / kRaDC;
   const int4 *rec_base = pair_rec + ((int64_t)bn * D * tiles_h + th) * W + w0;
   const int64_t rec_bin_stride = (int64_t)tiles_h * W;
@@ -274,7 +288,13 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
       const int bin = sd + 8 * pass;
-      const float4 pd = s_dep[st][bin][sh];
+      float4 pd = s_dep[st][bin][sh];
+      if (kLogits) {                                         // softmax(l) = exp(l - max) * (1 / sum); rows / bins beyond the tensor are masked below
+        pd.x = expf(pd.x - smax[0]) * srcp[0];
+        pd.y = expf(pd.y - smax[1]) * srcp[1];
+        pd.z = expf(pd.z - smax[2]) * srcp[2];
+        pd.w = expf(pd.w - smax[3]) * srcp[3];
+      }
       const unsigned m0 = (unsigned)s_rec[st][bin][0].y, m1 = (unsigned)s_rec[st][bin][1].y;
       const unsigned m2 = (unsigned)s_rec[st][bin][2].y, m3 = (unsigned)s_rec[st][bin][3].y;
       float *dT = s_depT + bin * kRaDepStride + sh;
@@ -374,15 +394,34 @@ frustum_reduce_kernel(const __grid_constant__ CUtensorMap ctx_map, const int32_t
   if (issued_bulk) tma_store_wait_read();                // the zero buffer must outlive the bulk stores reading it
 }
 
+// softmax statistics per pixel: {max_d l, 1 / sum_d exp(l - max)}; thread = pixel, one streaming read of the logits
+__global__ void __launch_bounds__(256)
+depth_stats_kernel(const float *__restrict__ logits, int64_t img_stride, int D, int HW, float2 *__restrict__ stats) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const float *lp = logits + (int64_t)blockIdx.y * img_stride + pix;
+  float m = -INFINITY, s = 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float l = __ldg(lp + (int64_t)d * HW);
+    if (l > m) {
+      s = s * expf(m - l);
+      m = l;
+    }
+    s += expf(l - m);
+  }
+  stats[(int64_t)blockIdx.y * HW + pix] = make_float2(m, 1.0f / s);
+}
+
 }  // namespace bevpool
 
 using namespace bevpool;
 
-template <int NV2, bool kNchw>
+template <int NV2, bool kNchw, bool kLogits = false>
 static int launch_stage_a(const CUtensorMap &ctx_map, const PlanView &pv, const float *dp, const float *cx, float *rr,
                           float *out, int32_t *status, int img0, int64_t cell_base, int64_t num_cells, int nb, int num_cams,
                           int D, int H, int W, int64_t capacity, int vec, int fill, int hints, int d_split, int64_t out_stride,
-                          cudaStream_t s) {
+                          cudaStream_t s, int64_t dep_img_stride = 0, const float2 *stats = nullptr) {
+  if (dep_img_stride <= 0) dep_img_stride = (int64_t)D * H * W;
   constexpr int C = 16 * NV2;
   const int tiles_h = (int)ceil_div64(H, kRunHB), tiles_w = (int)ceil_div64(W, kRaTW);
   const int d_per_cta = (int)(ceil_div64(ceil_div64(D, d_split), kRaDC) * kRaDC);      // whole chunks per CTA
@@ -392,10 +431,10 @@ static int launch_stage_a(const CUtensorMap &ctx_map, const PlanView &pv, const 
   (void)C;
   const size_t smem = RaSmem<NV2>::bytes;
   if (smem > 48 * 1024)
-    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2, kNchw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
+    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(frustum_reduce_kernel<NV2, kNchw, kLogits>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl_if(pdl_forward_enabled(), frustum_reduce_kernel<NV2, kNchw, kLogits>, dim3((unsigned)ctas), dim3(kRaThreads), smem, s,
       ctx_map, pv.run_code, pv.pair_rec, dp, cx, rr, pv.cell_start, out, status, img0, cell_base, num_cells, D, H, W, splits, d_per_cta, tiles_h,
-      tiles_w, capacity, vec, fill, hints, out_stride));
+      tiles_w, capacity, vec, fill, hints, out_stride, dep_img_stride, stats));
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -430,8 +469,12 @@ static const RunKnobs &run_knobs() {
 static int fused_forward_runs_impl(const void *plan, const void *depth, const void *context, bool nchw, void *out_nhwc,
                                    int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
                                    int channels, int X, int Y, void *run_rows, int64_t run_rows_capacity,
-                                   void *workspace, void *stream, int64_t out_stride = 0) {
+                                   void *workspace, void *stream, int64_t out_stride = 0, int64_t dep_img_stride = 0,
+                                   const float2 *stats = nullptr, int64_t ctx_img_stride = 0) {
+  if (ctx_img_stride <= 0) ctx_img_stride = (int64_t)channels * feat_h * feat_w;
   if (out_stride == 0) out_stride = channels;
+  if (stats && !nchw) return BEVPOOL_E_ARG;                   // the logits entry point exists for the NCHW layout only
+  if (dep_img_stride != 0 && ((dep_img_stride % 4) != 0 || dep_img_stride < (int64_t)depth_bins * feat_h * feat_w)) return BEVPOOL_E_ARG;
   if (out_stride < channels || (out_stride % 4) != 0) return BEVPOOL_E_ARG;
   if (num_cams <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
   const int64_t np = (int64_t)num_cams * depth_bins * feat_h * feat_w;
@@ -456,7 +499,7 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
   CUtensorMap ctx_map{};
   if (nchw) {
     const uint64_t dims[4] = {(uint64_t)feat_w, (uint64_t)feat_h, (uint64_t)channels, (uint64_t)batch * num_cams};
-    const uint64_t strides[3] = {(uint64_t)feat_w * 4, (uint64_t)feat_h * feat_w * 4, (uint64_t)channels * feat_h * feat_w * 4};
+    const uint64_t strides[3] = {(uint64_t)feat_w * 4, (uint64_t)feat_h * feat_w * 4, (uint64_t)ctx_img_stride * 4};
     const uint32_t box[4] = {kRaTW, kRunHB, (uint32_t)channels, 1};
     if ((rc = make_tensor_map_f32(&ctx_map, cx, 4, dims, strides, box))) return rc;
   }
@@ -472,7 +515,11 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
       const int max_split = (int)ceil_div64(depth_bins, kRaDC);
       d_split = d_split < 1 ? 1 : (d_split > max_split ? max_split : d_split);
     }
-    if (nchw) {
+    if (nchw && stats) {
+      BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2, true, true>(ctx_map, pv, dp, cx, rr, out, status, b0 * num_cams, cell_base, ncells, nb,
+                                                                          num_cams, depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints,
+                                                                          d_split, out_stride, s, dep_img_stride, stats)));
+    } else if (nchw) {
       BEVPOOL_G8_DISPATCH(channels, (rc = launch_stage_a<NV2, true>(ctx_map, pv, dp, cx, rr, out, status, b0 * num_cams, cell_base, ncells, nb, num_cams,
                                                                     depth_bins, feat_h, feat_w, run_rows_capacity, vec, fill, hints, d_split, out_stride, s)));
     } else {
@@ -530,4 +577,30 @@ extern "C" int bevpool_fused_forward_runs_into(const void *plan, const void *dep
   if (out_row_stride <= 0) return BEVPOOL_E_ARG;
   return fused_forward_runs_impl(plan, depth, context, context_is_nchw != 0, out_rows, dtype, batch, num_cams, depth_bins,
                                  feat_h, feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream, out_row_stride);
+}
+
+// lss_fpn.py:423 + :441-443 folded into the forward: the kernel reads DepthNet's output tensor itself -- depth_feature
+// (B*N, feature_channels, H, W) fp32 NCHW, logits in channels [0, depth_bins), context in channels
+// [context_channel_offset, context_channel_offset + channels) -- no softmax output, no channel-slice copies.
+// stats: scratch of 8 * B*N * H * W bytes (softmax max / normaliser per pixel, written by a small pre-pass).
+extern "C" int bevpool_fused_forward_runs_logits(const void *plan, const void *depth_feature, int feature_channels,
+                                                 int context_channel_offset, void *stats, void *out_rows,
+                                                 int64_t out_row_stride, int dtype, int batch, int num_cams,
+                                                 int depth_bins, int feat_h, int feat_w, int channels, int X, int Y,
+                                                 void *run_rows, int64_t run_rows_capacity, void *workspace,
+                                                 void *stream) {
+  if (!depth_feature || !stats || num_cams <= 0 || batch <= 0 || depth_bins <= 0 || feat_h <= 0 || feat_w <= 0) return BEVPOOL_E_ARG;
+  if (context_channel_offset < 0 || context_channel_offset + channels > feature_channels || depth_bins > feature_channels) return BEVPOOL_E_ARG;
+  if (dtype != BEVPOOL_F32) return BEVPOOL_E_DTYPE;
+  if (!aligned16(depth_feature) || (feat_w % 4) != 0) return BEVPOOL_E_ALIGN;
+  const int HW = feat_h * feat_w;
+  const int64_t img_stride = (int64_t)feature_channels * HW;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float *base = static_cast<const float *>(depth_feature);
+  depth_stats_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)(batch * num_cams)), 256, 0, s>>>(
+      base, img_stride, depth_bins, HW, static_cast<float2 *>(stats));
+  BEVPOOL_LAUNCH_CHECK();
+  return fused_forward_runs_impl(plan, base, base + (int64_t)context_channel_offset * HW, true, out_rows, dtype, batch, num_cams,
+                                 depth_bins, feat_h, feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream,
+                                 out_row_stride, img_stride, static_cast<const float2 *>(stats), img_stride);
 }

@@ -552,3 +552,63 @@ def voxel_pooling_fused_concat(depth: torch.Tensor, context: torch.Tensor, other
             and depth.is_contiguous()):
         return VoxelPoolingFusedConcat.apply(depth, context, other_bev, voxel_num, plan)
     return torch.cat([voxel_pooling_fused(None, depth, context, voxel_num, plan), other_bev.to(depth.dtype)], dim=1)
+
+
+class VoxelPoolingFusedLogits(Function):
+    """Pooling straight from DepthNet's output tensor: softmax over the depth logits (``lss_fpn.py:423``) and the
+    channel slices of ``:441-443`` happen inside the forward kernel."""
+
+    @staticmethod
+    def forward(ctx, depth_feature, depth_channels, channels, voxel_num, plan):
+        _lib.require_cuda(depth_feature)
+        X, Y, _ = _voxel_num_ints(voxel_num)
+        BN, Ct, H, W = depth_feature.shape
+        D, C = int(depth_channels), int(channels)
+        B = plan.batch
+        N = BN // B
+        assert plan.mode == 'runs' and plan.frustum == (N, D, H, W) and depth_feature.is_contiguous()
+        dev = depth_feature.device
+        with torch.cuda.device(dev):
+            out = torch.empty(B, Y, X, C, dtype=torch.float32, device=dev)
+            stats = torch.empty(BN, H, W, 2, dtype=torch.float32, device=dev)
+            cap = max(1, plan.num_sorted)
+            run_rows = torch.empty(cap, C, dtype=torch.float32, device=dev)
+            ws = _forward_workspace(C, dev)
+            _lib.check(_lib.lib().bevpool_fused_forward_runs_logits(
+                plan.ptr, depth_feature.data_ptr(), Ct, D, stats.data_ptr(), out.data_ptr(), 0, _lib.dtype_code(depth_feature),
+                B, N, D, H, W, C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(), _lib.stream_ptr(dev)),
+                'bevpool_fused_forward_runs_logits')
+        ctx.plan, ctx.D, ctx.C = plan, D, C
+        ctx.save_for_backward(depth_feature)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from ..depth_distribution import _backward as softmax_backward, _forward as softmax_forward
+        (depth_feature,) = ctx.saved_tensors
+        D, C = ctx.D, ctx.C
+        with torch.cuda.device(grad_out.device):
+            prob, _, _ = softmax_forward(depth_feature[:, :D], None)          # recomputed: the forward never stored it
+            context = depth_feature[:, D:D + C].contiguous()
+            grad_depth, grad_context = fused_backward(ctx.plan, grad_out, prob, context)
+            grad_logits = softmax_backward(prob, None, grad_depth, None, depth_feature.dtype)
+            grad_feature = torch.zeros_like(depth_feature) if depth_feature.shape[1] > D + C else torch.empty_like(depth_feature)
+            grad_feature[:, :D] = grad_logits
+            grad_feature[:, D:D + C] = grad_context
+        return grad_feature, None, None, None, None
+
+
+def voxel_pooling_fused_logits(depth_feature: torch.Tensor, depth_channels: int, channels: int, voxel_num: VoxelNum,
+                               plan: PoolingPlan) -> torch.Tensor:
+    """``depth_feature`` (B*N, >= D + C, H, W): DepthNet's output (``lss_fpn.py:415-423``) -- depth logits in channels
+    [0, D), context in [D, D + C).  Equals ``voxel_pooling_fused(None, depth_feature[:, :D].softmax(1),
+    depth_feature[:, D:D+C], voxel_num, plan)`` without the probability tensor or the slice copies (run plan, fp32,
+    W % 4 == 0, C in RUN_CHANNELS; other cases compose the stock ops).  For training runs that also need the
+    probabilities (depth loss) use ``depth_distribution`` + ``voxel_pooling_fused``."""
+    D, C = int(depth_channels), int(channels)
+    if (plan.mode == 'runs' and runs_supported(C, depth_feature.dtype) and depth_feature.shape[3] % 4 == 0
+            and depth_feature.is_contiguous() and depth_feature.data_ptr() % 16 == 0
+            and os.environ.get('BEVPOOL_NCHW_DIRECT', '1') != '0'):
+        return VoxelPoolingFusedLogits.apply(depth_feature, D, C, voxel_num, plan)
+    return voxel_pooling_fused(None, depth_feature[:, :D].softmax(1).contiguous(), depth_feature[:, D:D + C].contiguous(),
+                               voxel_num, plan)

@@ -96,3 +96,32 @@ def test_feeds_the_fused_pooling_without_a_copy():
 def test_cpu_tensors_raise():
     with pytest.raises(RuntimeError):
         depth_distribution(torch.zeros(1, 4, 2, 2), 3)
+
+
+# ---------------------------------------------------------------- softmax folded into the forward
+@pytest.mark.parametrize('cfg_name,B,extra', [('cfg2', 3, 0), ('cfg2', 1, 8), ('aim', 1, 0)])
+def test_forward_from_logits_equals_softmax_then_pooling(cfg_name, B, extra):
+    from mm_training_b200 import synthetic
+    from mm_training_b200.configs import CFG_2, CFG_AIM
+    from mm_training_b200.ops.voxel_pooling import build_plan, voxel_pooling_fused, voxel_pooling_fused_logits
+    cfg = CFG_2 if cfg_name == 'cfg2' else CFG_AIM
+    D, C = cfg.depth_bins, cfg.output_channels
+    geom, vn_t = synthetic.camera_rig(cfg, B, device=DEV, yaw_jitter_deg=5.0, seed=6)
+    vn = tuple(int(v) for v in vn_t.tolist())
+    g = torch.Generator().manual_seed(B + extra)
+    feat = (torch.randn(B * cfg.num_cams, D + C + extra, *cfg.feat_hw, generator=g) * 2).to(DEV)
+    plan = build_plan(geom, vn, frustum=tuple(geom.shape[1:5]))
+    a = feat.clone().requires_grad_(True)
+    b = feat.clone().requires_grad_(True)
+    out = voxel_pooling_fused_logits(a, D, C, vn, plan)
+    ref = voxel_pooling_fused(None, b[:, :D].softmax(1).contiguous(), b[:, D:D + C].contiguous(), vn, plan)
+    # same sums in the same order over probabilities that differ by float32 rounding of exp / normaliser
+    scale = voxel_pooling_fused(None, b[:, :D].softmax(1).contiguous().detach(), b[:, D:D + C].abs().contiguous().detach(), vn, plan)
+    assert bool(((out - ref).abs() <= 1e-5 * ref.abs() + 2e-6 * scale).all())
+    assert bool((out[scale == 0] == 0).all())
+    go = torch.rand(out.shape, generator=g).to(DEV)
+    out.backward(go)
+    ref.backward(go)
+    assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-5)
+    if extra:
+        assert float(a.grad[:, D + C:].abs().sum()) == 0.0
