@@ -453,6 +453,87 @@ plan_key_rig_kernel(RigParams rp, const int32_t *__restrict__ geom, int num_cams
   uint32_t filled = 0;                 // heads this warp has written so far (warp-uniform)
   int prev = -2, primary = -1, nheads = 0;
   uint32_t fastm = 0u, keptm = 0u;
+
+  // ---- level-camera fast path (rig plans).  Every coordinate of a point is a weakly MONOTONE function of its image
+  // row h: py = fy[h] * d enters each dot product once, and fl(.) of a monotone function is monotone through every
+  // rounding step (multiply, fused multiply-add, add, subtract, divide by a constant, truncate).  So when the x and y
+  // cell indices agree at the first and the last row of a pair they agree on every row in between (a level camera:
+  // m[.][1] == 0 for x and y), and the rows whose z index lies in [0, Z) form ONE interval, found by two binary
+  // searches on z alone: ~10 coordinate evaluations per pair instead of 48, one head, no per-row voting.  Bit-identical
+  // to the per-row walk below by construction; it needs fy sorted (checked per CTA) and finite end points.  A warp
+  // takes it only when all its pairs qualify; tilted cameras and geom_xyz plans walk the rows.
+  bool warp_fast = false;
+  if (kVariant >= 0) {
+    __shared__ int s_unsorted;
+    if (threadIdx.x == 0) s_unsorted = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i + 1 < H; i += kRigThreads)
+      if (!(__ldg(rp.fy + i) <= __ldg(rp.fy + i + 1))) s_unsorted = 1;
+    __syncthreads();
+    const int rows_here = valid ? min(kRunHB, H - hb * kRunHB) : 0;
+    constexpr int V = kVariant < 0 ? 0 : kVariant;
+    int ix0 = 0, iy0 = 0, iz0 = 0, ix1 = 0, iy1 = 0, iz1 = 0;
+    bool fast = s_unsorted == 0;
+    if (valid && fast) {
+      const float pya = __fmul_rn(__ldg(rp.fy + hb * kRunHB), dd), pyb = __fmul_rn(__ldg(rp.fy + hb * kRunHB + rows_here - 1), dd);
+      const float ea0 = rig_dot4<V>(m0, px, pya, dd), ea1 = rig_dot4<V>(m1, px, pya, dd), ea2 = rig_dot4<V>(m2, px, pya, dd);
+      const float eb0 = rig_dot4<V>(m0, px, pyb, dd), eb1 = rig_dot4<V>(m1, px, pyb, dd), eb2 = rig_dot4<V>(m2, px, pyb, dd);
+      const float big = fmaxf(fmaxf(fmaxf(fabsf(ea0), fabsf(ea1)), fmaxf(fabsf(ea2), fabsf(eb0))), fmaxf(fabsf(eb1), fabsf(eb2)));
+      rig_quantise3(ea0, ea1, ea2, rp, ix0, iy0, iz0);
+      rig_quantise3(eb0, eb1, eb2, rp, ix1, iy1, iz1);
+      fast = big < 1e30f && ix0 == ix1 && iy0 == iy1;          // (NaN compares false -> per-row walk)
+    }
+    warp_fast = __all_sync(0xffffffffu, fast);
+    if (warp_fast) {
+      int lo = 0, hi = 0;                                       // kept rows of the pair: [lo, hi)
+      const bool xy_ok = valid && ((unsigned)ix0 < (unsigned)X) && ((unsigned)iy0 < (unsigned)Y);
+      if (xy_ok) {
+        if (iz0 == iz1) {
+          if ((unsigned)iz0 < (unsigned)Z) hi = rows_here;
+        } else {
+          const bool asc = iz0 < iz1;                           // z index as a function of the row: ascending or descending
+          auto zi = [&](int k) {                                // ascending view: k-th row from the low-z end
+            const int r = asc ? k : rows_here - 1 - k;
+            const float py = __fmul_rn(__ldg(rp.fy + hb * kRunHB + r), dd);
+            return rig_quantise(rig_dot4<V>(m2, px, py, dd), rp.lo[2], rp.vs[2], rp.inv_vs[2]);
+          };
+          auto lower_bound = [&](int thr) {                     // first k with zi(k) >= thr (zi(0) = min end, zi(rows-1) = max end)
+            int a = 0, e = rows_here;
+            while (a < e) {
+              const int mid = (a + e) >> 1;
+              if (zi(mid) >= thr) e = mid; else a = mid + 1;
+            }
+            return a;
+          };
+          const int ka = lower_bound(0), kb = lower_bound(Z);   // kept (ascending view) = [ka, kb)
+          if (asc) { lo = ka; hi = kb; } else { lo = rows_here - kb; hi = rows_here - ka; }
+        }
+      }
+      const bool has = hi > lo;
+      const int cell = has ? iy0 * X + ix0 : -1;
+      if (valid) {
+#pragma unroll 4
+        for (int r = 0; r < rows_here; ++r) {
+          const int gp = col_base + (hb * kRunHB + r) * W;
+          const bool kept = r >= lo && r < hi;
+          cell_of_point[gp] = kept ? cell : -1;
+          run_code[gp] = kept ? (r == lo ? cell : kRunCont) : kRunDropped;     // the head: overwritten with its slot by K4
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, has);
+      if (has) {
+        const int64_t pos = region + __popc(bal & lt);
+        head_cells[pos] = cell;
+        head_ids[pos] = (col_base + (hb * kRunHB + lo) * W) | (int32_t)0x80000000;   // first kept row of its pair
+        atomicAdd(counts + (int64_t)b * cells + cell, 1u);
+        primary = cell;
+        keptm = fastm = ((hi - lo >= 32 ? 0u : (1u << (hi - lo))) - 1u) << lo;
+        nheads = 1;
+      }
+      filled = __popc(bal);
+    }
+  }
+  if (!warp_fast) {
 #pragma unroll 4
   for (int r = 0; r < kRunHB; ++r) {
     const int h = hb * kRunHB + r;
@@ -493,6 +574,7 @@ plan_key_rig_kernel(RigParams rp, const int32_t *__restrict__ geom, int num_cams
       atomicAdd(counts + (int64_t)b * cells + code, 1u);
     }
     filled += __popc(bal);
+  }
   }
   if (valid) pair_rec[(int64_t)b * pairs + q] = make_int4(primary, (int)(fastm | ((keptm & ~fastm) << 16)), -1, nheads);
   __shared__ uint32_t s_cta_total;

@@ -248,11 +248,12 @@ __global__ void scatter_backward_kernel(const T *__restrict__ grad_canvas, const
 //                          max_points smallest indices in ascending order whatever the interleaving).  The lists are
 //                          a compact array that stays in L2 -- atomics on the padded voxel tensor itself (15 x F
 //                          floats per row, far larger than L2) ran at DRAM random-access speed, 4x slower
-//   D vox_finalize_kernel  one thread per voxel row: slot list -> point rows, count, coordinates, HardSimpleVFE mean
-//                          in slot order and, optionally, its pillar scatter into the dense canvas
-// `voxels` and the canvas are zeroed by cudaMemsetAsync (DRAM-speed fills: 93 % of a voxel tensor is padding), so
-// only real points are ever written by a kernel.  The clouds may be given as one concatenated tensor or as a device
-// array of per-sample pointers (no torch.cat of the batch).
+//   D vox_finalize_kernel  one lane per voxel row, one warp per 32 rows: slot list -> point rows gathered into a
+//                          shared-memory tile that leaves as one contiguous, coalesced span of the padded voxel
+//                          tensor (93 % of it is zeros: written once, by this kernel, at streaming-store speed);
+//                          count, coordinates, HardSimpleVFE mean in slot order and, optionally, its pillar scatter
+// The canvas is zeroed by cudaMemsetAsync (a DRAM-speed fill; the pillars then overwrite their cells).  The clouds may
+// be given as one concatenated tensor or as a device array of per-sample pointers (no torch.cat of the batch).
 constexpr int kVcThreads = 256;
 constexpr int kVoxMaxF = 16;
 constexpr int32_t kVoxIdxBias = 0x7fffffff;          // slot word = kVoxIdxBias - point index  (> 0; 0 = empty)
@@ -446,6 +447,10 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
     if (vid[k] >= max_voxels) continue;                  // out of range, or voxel cap: the whole cell is dropped
     int *slot0 = lists + (int64_t)(base + vid[k]) * max_points;
     int v = kVoxIdxBias - (i0 + 256 * k);
+    // words only grow: once the LAST slot holds an earlier point (a larger word) every slot does and this point can
+    // never enter.  Checked before the first atomic: the thousands of points of a near-range cell would otherwise all
+    // queue on the same 15 words (CTAs start in point order, so the list is full of early points almost at once).
+    if (*reinterpret_cast<volatile int *>(slot0 + (max_points - 1)) > v) continue;
     int old = atomicMax(slot0, v);
     if (old == 0) continue;                              // first point of the voxel so far: done (the common case)
     v = old < v ? old : v;                               // carry the later point to the next slot
@@ -459,68 +464,86 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
   }
 }
 
-// One thread per row of the padded output (batch * max_voxels rows): rows beyond the voxel count get num_points = 0
-// (their point slots were zeroed by the memset); a live row finds its sample (binary search in voxel_base), its
-// coordinates (cell_of_vid) and walks its slots: index word -> point row copied over the word, running sums for the
-// HardSimpleVFE mean in slot order, count = number of filled slots.
-__global__ void __launch_bounds__(256)
+// One LANE per row of the padded output (batch * max_voxels rows), one warp per 32 consecutive rows.  A live row finds its
+// sample (binary search in voxel_base) and its coordinates (cell_of_vid) and walks its slot list: index word -> point
+// row, gathered into the warp's shared-memory tile [32 rows][max_points * F] (zero-initialised: the padding);
+// running sums for the HardSimpleVFE mean in slot order, count = number of filled slots.  The tile then leaves as ONE
+// contiguous span of 32 * max_points * F floats written with 16-byte stores -- every element of `voxels` is written
+// exactly once, coalesced (no memset of the 93 %-padding tensor, no 20-byte scattered stores).  Rows beyond the voxel
+// count are written as zeros with num_points = 0.
+constexpr int kFinWarps = 4;
+__global__ void __launch_bounds__(kFinWarps * 32)
 vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
                     const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists, int batch, int max_voxels,
                     int max_points, float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
                     const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
                     float *__restrict__ canvas) {
-  extern __shared__ int s_vb[];                           // voxel_base, batch + 1 entries
+  extern __shared__ __align__(16) float s_fin[];          // [kFinWarps][32][TF] floats, then voxel_base (batch + 1 ints)
+  const int TF = max_points * F;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *tile = s_fin + (size_t)warp * 32 * TF;
+  int *s_vb = reinterpret_cast<int *>(s_fin + (size_t)kFinWarps * 32 * TF);
   for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
+  for (int e = lane; e < 32 * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= (int64_t)batch * max_voxels) return;
-  if (row >= s_vb[batch]) {
-    num_points[row] = 0;
-    return;
-  }
-  int lo = 0, hi = batch;                                 // sample b: s_vb[b] <= row < s_vb[b + 1]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (s_vb[mid] <= row) lo = mid; else hi = mid;
-  }
-  const int b = lo;
-  const int begin = offsets[b];
-  const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
-  const int64_t c = (int64_t)gc - (int64_t)b * cells;
-  const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
-  reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
-  float *vrow = voxels + row * max_points * F;
-  const int32_t *list = lists + row * max_points;
-  float sum[kVoxMaxF];
+  const int64_t total_rows = (int64_t)batch * max_voxels;
+  const int64_t row0 = ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
+  if (row0 >= total_rows) return;
+  const int64_t row = row0 + lane;
+  if (row < total_rows) {
+    int cnt = 0;
+    if (row < s_vb[batch]) {
+      int lo = 0, hi = batch;                             // sample b: s_vb[b] <= row < s_vb[b + 1]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_vb[mid] <= row) lo = mid; else hi = mid;
+      }
+      const int b = lo;
+      const int begin = offsets[b];
+      const int32_t *list = lists + row * max_points;
+      int word = list[0];
+      const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
+      const int64_t c = (int64_t)gc - (int64_t)b * cells;
+      const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
+      reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
+      float *trow = tile + (size_t)lane * TF;
+      float sum[kVoxMaxF];
 #pragma unroll
-  for (int k = 0; k < kVoxMaxF; ++k) sum[k] = 0.f;
-  int cnt = 0;
-  int word = list[0];
-  while (word != 0) {
-    float *dst = vrow + (int64_t)cnt * F;
-    const float *src = pts.row(b, begin, kVoxIdxBias - word, F);
-    ++cnt;
-    word = cnt < max_points ? list[cnt] : 0;              // next slot's word, in flight behind this slot's point
-    float val[kVoxMaxF];
+      for (int k = 0; k < kVoxMaxF; ++k) sum[k] = 0.f;
+      while (word != 0) {
+        float *dst = trow + cnt * F;
+        const float *src = pts.row(b, begin, kVoxIdxBias - word, F);
+        ++cnt;
+        word = cnt < max_points ? list[cnt] : 0;          // next slot's word, in flight behind this slot's point
+        float val[kVoxMaxF];
 #pragma unroll
-    for (int k = 0; k < kVoxMaxF; ++k)
-      if (k < F) val[k] = __ldg(src + k);
+        for (int k = 0; k < kVoxMaxF; ++k)
+          if (k < F) val[k] = __ldg(src + k);
 #pragma unroll
-    for (int k = 0; k < kVoxMaxF; ++k) {
-      if (k < F) dst[k] = val[k];
-      if (k < mean_features) sum[k] += val[k];
+        for (int k = 0; k < kVoxMaxF; ++k) {
+          if (k < F) dst[k] = val[k];
+          if (k < mean_features) sum[k] += val[k];
+        }
+      }
+      if (voxel_mean || canvas) {
+#pragma unroll
+        for (int k = 0; k < kVoxMaxF; ++k) {
+          if (k >= mean_features) break;
+          const float m = sum[k] / (float)cnt;
+          if (voxel_mean) voxel_mean[row * mean_features + k] = m;
+          if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
+        }
+      }
     }
+    num_points[row] = cnt;
   }
-  num_points[row] = cnt;
-  if (voxel_mean || canvas) {
-#pragma unroll
-    for (int k = 0; k < kVoxMaxF; ++k) {
-      if (k >= mean_features) break;
-      const float m = sum[k] / (float)cnt;
-      if (voxel_mean) voxel_mean[row * mean_features + k] = m;
-      if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
-    }
-  }
+  __syncwarp();
+  // the warp's 32 rows are one contiguous span of the output
+  const int64_t nrows = min((int64_t)32, total_rows - row0);
+  float *out = voxels + row0 * TF;
+  const int n4 = (int)(nrows * TF / 4);                    // row0 * TF * 4 bytes is a multiple of 16 (row0 % 32 == 0)
+  for (int e = lane; e < n4; e += 32) stg_stream_f4(reinterpret_cast<float4 *>(out) + e, reinterpret_cast<const float4 *>(tile)[e]);
+  for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
 }
 
 // pillar scatter for UNIQUE coordinates (what hard voxelization produces): canvas pre-zeroed, one thread per element
@@ -641,7 +664,6 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   const size_t rows = (size_t)batch * max_voxels;
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, L.zero_bytes, stream));
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
-  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(voxels, 0, rows * max_points * F * sizeof(float), stream));
   const dim3 pgrid((unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer), (unsigned)batch);
   if (total_points > 0) {
     vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(pts, sample_offsets, F, g,
@@ -659,7 +681,11 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists);
     BEVPOOL_LAUNCH_CHECK();
   }
-  vox_finalize_kernel<<<(unsigned)ceil_div64((int64_t)rows, 256), 256, (size_t)(batch + 1) * sizeof(int), stream>>>(
+  const size_t fin_smem = (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
+  if (fin_smem > 200 * 1024) return BEVPOOL_E_RANGE;       // max_points * F beyond ~390 floats: not a pillar configuration
+  if (fin_smem > 48 * 1024)
+    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+  vox_finalize_kernel<<<(unsigned)ceil_div64((int64_t)rows, kFinWarps * 32), kFinWarps * 32, fin_smem, stream>>>(
       pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
       voxel_mean, mean_features, canvas);
   BEVPOOL_LAUNCH_CHECK();
@@ -678,7 +704,7 @@ static int hard_voxelize_impl(const float *points, const float *const *sample_pt
     return BEVPOOL_E_ARG;
   if (total_points > 0 && !points && !sample_ptrs) return BEVPOOL_E_ARG;
   if ((voxel_mean || canvas) && (mean_features <= 0 || mean_features > num_features || mean_features > 16)) return BEVPOOL_E_ARG;
-  if (!aligned16(temp) || !aligned16(coors)) return BEVPOOL_E_ALIGN;
+  if (!aligned16(temp) || !aligned16(coors) || !aligned16(voxels)) return BEVPOOL_E_ALIGN;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const VoxGeom g = make_geom(voxel_size_host, range_host, grid_host);
   if (g.gx <= 0 || g.gy <= 0 || g.gz <= 0) return BEVPOOL_E_ARG;
