@@ -213,7 +213,7 @@ def run_sweep(dev, peak_gbs, seed=7, full=False, ref_arms=False):
     1..64 x {128,256,512}^2.  ``ref_arms``: the reference's CUDA pipeline (oracle/_ref) on the same inputs beside
     every point, and the CPU port on a bounded sample (batch <= 2)."""
     from mm_training_b200.configs import sweep_grid_config
-    from mm_training_b200.ops.voxel_pooling import build_plan, fused_backward, fused_forward
+    from mm_training_b200.ops.voxel_pooling import build_plan, fused_backward, fused_forward_cold
     if full:
         points = [(sweep_grid_config(g), b) for g in (128, 256, 512) for b in (1, 2, 4, 8, 16, 32, 64)]
     else:
@@ -227,8 +227,7 @@ def run_sweep(dev, peak_gbs, seed=7, full=False, ref_arms=False):
         n = build_plan(geom, vn, frustum=fr).num_sorted
 
         def step():
-            plan = build_plan(geom, vn, frustum=fr, max_runs=n)
-            out = fused_forward(plan, depth, ctx)
+            plan, out = fused_forward_cold(lambda: build_plan(geom, vn, frustum=fr, max_runs=n), B, vn, depth, ctx)
             return out, fused_backward(plan, go, depth, ctx)
         med, _ = _graph_step_ms(step)
         kept = int((build_plan(geom, vn).cell_of_point >= 0).sum().item()) / B
@@ -514,9 +513,11 @@ def main():
             return PoolingPlan.from_rig(lsg, combine, variant, max_runs)
         return build_plan(geom, vn, frustum=frustum, max_runs=max_runs)
 
+    from mm_training_b200.ops.voxel_pooling import fused_forward_cold
+
     def step():
-        plan = make_plan()
-        out = fused_forward(plan, depth, ctx)          # NCHW context read through a TMA tensor map
+        # cold call: the output's zero fill runs on a side stream while the plan is built (fork / join inside the step)
+        plan, out = fused_forward_cold(make_plan, B, vn, depth, ctx)      # NCHW context read through a TMA tensor map
         gd, gc = fused_backward(plan, go, depth, ctx)  # NCHW incoming gradient; grad_context written NCHW like ctx
         return plan, out, gd, gc
 
@@ -643,8 +644,7 @@ def main():
     # ---- the same step when the caller keeps context and gradient channels_last (zero-copy layouts: no
     # context / context-gradient transposes, no gradient-row pass); reported beside the headline, not as it
     def step_cl():
-        p = make_plan()
-        o = fused_forward(p, depth, ctx_nhwc)
+        p, o = fused_forward_cold(make_plan, B, vn, depth, ctx_nhwc)
         return o, fused_backward(p, go_nhwc, depth, ctx_nhwc)
     cl_ms = None
     try:

@@ -167,7 +167,10 @@ int bevpool_fused_forward_runs_nchw(const void *plan, const void *depth, const v
  * `.contiguous()` of lss_fpn.py:466 for channels-last consumers): the same forward, writing its rows into a wider
  * channels-last buffer (B, Y, X, C_total).  out_rows = address of the first camera channel of cell 0; consecutive
  * cells are out_row_stride floats apart (>= channels, multiple of 4); the other channels of a row are not touched.  */
-int bevpool_fused_forward_runs_into(const void *plan, const void *depth, const void *context, int context_is_nchw,
+#define BEVPOOL_FWD_NCHW_CONTEXT   1   /* context is (B*N, C, H, W); else pixel rows (B*N, H, W, C)                    */
+#define BEVPOOL_FWD_OUT_PREZEROED  2   /* the caller zero-filled the output rows (e.g. on a side stream while the plan  */
+                                       /* was being built): the kernels write occupied cells only                     */
+int bevpool_fused_forward_runs_into(const void *plan, const void *depth, const void *context, int flags,
                                     void *out_rows, int64_t out_row_stride, int dtype, int batch, int num_cams,
                                     int depth_bins, int feat_h, int feat_w, int channels, int num_voxel_x,
                                     int num_voxel_y, void *run_rows, int64_t run_rows_capacity, void *workspace,

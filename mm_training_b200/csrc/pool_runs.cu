@@ -470,7 +470,7 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
                                    int dtype, int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
                                    int channels, int X, int Y, void *run_rows, int64_t run_rows_capacity,
                                    void *workspace, void *stream, int64_t out_stride = 0, int64_t dep_img_stride = 0,
-                                   const float2 *stats = nullptr, int64_t ctx_img_stride = 0) {
+                                   const float2 *stats = nullptr, int64_t ctx_img_stride = 0, bool prezeroed = false) {
   if (ctx_img_stride <= 0) ctx_img_stride = (int64_t)channels * feat_h * feat_w;
   if (out_stride == 0) out_stride = channels;
   if (stats && !nchw) return BEVPOOL_E_ARG;                   // the logits entry point exists for the NCHW layout only
@@ -493,7 +493,8 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
   const RunKnobs &kn = run_knobs();
   int fpc = kn.chunk;
   if (fpc <= 0 || fpc > batch) fpc = batch;
-  const int fill = kn.fill, hints = kn.hints, cps_b = kn.cps_b;
+  // prezeroed: the caller zero-filled the output itself (e.g. on a side stream, behind the plan build): nobody fills
+  const int fill = prezeroed ? 0 : kn.fill, hints = kn.hints, cps_b = kn.cps_b;
   const float *dp = static_cast<const float *>(depth), *cx = static_cast<const float *>(context);
   float *rr = static_cast<float *>(run_rows), *out = static_cast<float *>(out_nhwc);
   CUtensorMap ctx_map{};
@@ -528,7 +529,7 @@ static int fused_forward_runs_impl(const void *plan, const void *depth, const vo
     }
     if (rc) return rc;
     // stage B: even-share segmented sum of the run rows (identity ids), fill CTAs only if stage A did not fill
-    const int period_b = fill ? 0 : cps_b + 1;
+    const int period_b = (fill || prezeroed) ? 0 : cps_b + 1;
     const unsigned ctas_b = (unsigned)(sm_count_runs() * (period_b ? period_b : cps_b));
     const int slices = (int)(period_b ? ctas_b - ctas_b / period_b : ctas_b) * kFwWarpsPerCta * 4;
     float *ws_head = static_cast<float *>(workspace);
@@ -570,13 +571,14 @@ extern "C" int bevpool_fused_forward_runs_nchw(const void *plan, const void *dep
 // straight into a wider channels-last buffer -- out points at the first camera channel of cell 0, consecutive cells are
 // out_row_stride floats apart -- so neither lss_fpn.py:466's `.contiguous()` nor the cat copies the camera half.
 extern "C" int bevpool_fused_forward_runs_into(const void *plan, const void *depth, const void *context,
-                                               int context_is_nchw, void *out_rows, int64_t out_row_stride, int dtype,
+                                               int context_is_nchw /* flags: bit 0 NCHW context, bit 1 output pre-zeroed */, void *out_rows, int64_t out_row_stride, int dtype,
                                                int batch, int num_cams, int depth_bins, int feat_h, int feat_w,
                                                int channels, int X, int Y, void *run_rows, int64_t run_rows_capacity,
                                                void *workspace, void *stream) {
   if (out_row_stride <= 0) return BEVPOOL_E_ARG;
-  return fused_forward_runs_impl(plan, depth, context, context_is_nchw != 0, out_rows, dtype, batch, num_cams, depth_bins,
-                                 feat_h, feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream, out_row_stride);
+  return fused_forward_runs_impl(plan, depth, context, (context_is_nchw & 1) != 0, out_rows, dtype, batch, num_cams, depth_bins,
+                                 feat_h, feat_w, channels, X, Y, run_rows, run_rows_capacity, workspace, stream, out_row_stride,
+                                 0, nullptr, 0, (context_is_nchw & 2) != 0);
 }
 
 // lss_fpn.py:423 + :441-443 folded into the forward: the kernel reads DepthNet's output tensor itself -- depth_feature

@@ -162,6 +162,6 @@ def voxel_pooling_rig(lsg: LiftSplatGeometry, sensor2ego_mat: torch.Tensor, intr
                       depth: torch.Tensor, context: torch.Tensor, max_runs: Optional[int] = None) -> torch.Tensor:
     """``lss_fpn.py:455-464`` in one call: geometry, quantisation, outer product and pooling.  depth (B*N, D, H, W),
     context (B*N, C, H, W); returns (B, C, Y, X) like the reference op."""
-    from .voxel_pooling import voxel_pooling_fused
-    plan = lsg.plan(sensor2ego_mat, intrin_mat, max_runs=max_runs)
-    return voxel_pooling_fused(None, depth, context, lsg.voxel_num, plan)
+    from .voxel_pooling import VoxelPoolingFused
+    return VoxelPoolingFused.apply(None, depth, context, lsg.voxel_num, None,
+                                   lambda: lsg.plan(sensor2ego_mat, intrin_mat, max_runs=max_runs), int(sensor2ego_mat.shape[0]))

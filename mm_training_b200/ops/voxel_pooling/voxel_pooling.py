@@ -309,8 +309,11 @@ def _nchw_direct(context: torch.Tensor, depth: torch.Tensor) -> bool:
 
 
 def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
-                  context_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """depth (B*N, D, H, W), context (B*N, C, H, W) NCHW or channels_last -> (B, Y, X, C)."""
+                  context_rows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                  prezeroed: bool = False) -> torch.Tensor:
+    """depth (B*N, D, H, W), context (B*N, C, H, W) NCHW or channels_last -> (B, Y, X, C).  ``out``: a caller-provided
+    (B, Y, X, C) buffer; ``prezeroed``: it already holds zeros (run plans only: the kernels then write occupied cells
+    only -- see ``fused_forward_cold``)."""
     BN, D, H, W = depth.shape
     C = context.shape[1]
     X, Y, _ = plan.voxel_num
@@ -319,7 +322,10 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
     assert context.shape == (BN, C, H, W) and depth.dtype == context.dtype
     assert B * N == BN and plan.num_points == N * D * H * W
     with torch.cuda.device(depth.device):
-        out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
+        if out is None:
+            out = torch.empty(B, Y, X, C, dtype=depth.dtype, device=depth.device)
+            prezeroed = False
+        assert out.shape == (B, Y, X, C) and out.is_contiguous() and out.dtype == depth.dtype
         if plan.mode == 'runs':
             if not runs_supported(C, depth.dtype):
                 raise ValueError(f'run plans need float32 and C in {RUN_CHANNELS}; build a point plan for C={C}, {depth.dtype}')
@@ -327,18 +333,12 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
             cap = max(1, plan.num_sorted)
             run_rows = torch.empty(cap, C, dtype=torch.float32, device=depth.device)
             ws = _forward_workspace(C, out.device)
-            if context_rows is None and _nchw_direct(context, depth):
-                _lib.check(_lib.lib().bevpool_fused_forward_runs_nchw(
-                    plan.ptr, depth.data_ptr(), context.data_ptr(), out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
-                    C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(), _lib.stream_ptr(depth.device)),
-                    'bevpool_fused_forward_runs_nchw')
-                return out
-            ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
-            _lib.check(_lib.lib().bevpool_fused_forward_runs(plan.ptr, depth.data_ptr(), ctx_nhwc.data_ptr(),
-                                                             out.data_ptr(), _lib.dtype_code(depth), B, N, D, H, W,
-                                                             C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(),
-                                                             _lib.stream_ptr(depth.device)),
-                       'bevpool_fused_forward_runs')
+            nchw = context_rows is None and _nchw_direct(context, depth)
+            ctx_arg = context if nchw else (context_rows_nhwc(context) if context_rows is None else context_rows)
+            _lib.check(_lib.lib().bevpool_fused_forward_runs_into(
+                plan.ptr, depth.data_ptr(), ctx_arg.data_ptr(), (1 if nchw else 0) | (2 if prezeroed else 0), out.data_ptr(), C,
+                _lib.dtype_code(depth), B, N, D, H, W, C, X, Y, run_rows.data_ptr(), cap, ws.data_ptr(),
+                _lib.stream_ptr(depth.device)), 'bevpool_fused_forward_runs_into')
             return out
         ctx_nhwc = context_rows_nhwc(context) if context_rows is None else context_rows
         ws = _forward_workspace(C, out.device)
@@ -347,6 +347,41 @@ def fused_forward(plan: PoolingPlan, depth: torch.Tensor, context: torch.Tensor,
                                                     C, X, Y, ws.data_ptr(), _lib.stream_ptr(depth.device)),
                    'bevpool_fused_forward')
     return out
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
+def fused_forward_cold(make_plan, batch: int, voxel_num: VoxelNum, depth: torch.Tensor, context: torch.Tensor):
+    """Plan build + fused forward of a COLD call (geometry changed: the plan is rebuilt).  80 % of a BEV grid is empty
+    and its zero fill is pure DRAM-write work, while the plan kernels are latency / issue bound and leave DRAM idle: the
+    output is zero-filled on a side stream WHILE ``make_plan()`` runs on the caller's stream (fork / join with events:
+    CUDA-graph capturable), and the forward then writes occupied cells only.  Returns ``(plan, out (B, Y, X, C))``.
+    Point plans / unsupported shapes take the plain sequence."""
+    X, Y, _ = _voxel_num_ints(voxel_num)
+    C = context.shape[1]
+    dev = depth.device
+    if not runs_supported(C, depth.dtype) or os.environ.get('BEVPOOL_COLD_OVERLAP', '1') == '0':
+        plan = make_plan()
+        return plan, fused_forward(plan, depth, context)
+    with torch.cuda.device(dev):
+        cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        out = torch.empty(batch, Y, X, C, dtype=depth.dtype, device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out.zero_()
+        plan = make_plan()
+        cur.wait_stream(side)          # (every later use of `out`, its free included, is ordered behind this join)
+        if plan.mode != 'runs':
+            return plan, fused_forward(plan, depth, context, out=out)
+        return plan, fused_forward(plan, depth, context, out=out, prezeroed=True)
 
 
 def fused_backward(plan: PoolingPlan, grad_output: torch.Tensor, depth: torch.Tensor,
@@ -426,11 +461,21 @@ def voxel_pooling(geom_xyz: torch.Tensor, input_features: torch.Tensor, voxel_nu
 
 class VoxelPoolingFused(Function):
     @staticmethod
-    def forward(ctx, geom_xyz, depth, context, voxel_num, plan):
+    def forward(ctx, geom_xyz, depth, context, voxel_num, plan, make_plan=None, batch=None):
         _lib.require_cuda(depth, context)
         assert depth.is_contiguous()
         X, Y, Z = _voxel_num_ints(voxel_num)
         with torch.cuda.device(depth.device):
+            if plan is None and make_plan is not None:
+                # cold call with a caller-supplied plan builder (e.g. from the camera rig): fill overlapped with the build
+                if _nchw_direct(context, depth):
+                    plan, out = fused_forward_cold(make_plan, int(batch), (X, Y, Z), depth, context)
+                    if plan.mode == 'runs':
+                        ctx.plan, ctx.direct = plan, True
+                        ctx.save_for_backward(depth, context)
+                        return out.permute(0, 3, 1, 2)
+                else:
+                    plan = make_plan()
             if plan is None:
                 assert geom_xyz.is_contiguous()
                 frustum = None
@@ -438,6 +483,13 @@ class VoxelPoolingFused(Function):
                 if (geom_xyz.dim() == 6 and runs_supported(context.shape[1], depth.dtype)
                         and not torch.cuda.is_current_stream_capturing()):
                     frustum = tuple(geom_xyz.shape[1:5])      # (N, D, H, W): sort runs, not points
+                if frustum is not None and _nchw_direct(context, depth):
+                    # cold call: zero fill of the output overlapped with the plan build
+                    plan, out = fused_forward_cold(lambda: PoolingPlan(geom_xyz, (X, Y, Z), frustum), int(geom_xyz.shape[0]),
+                                                   (X, Y, Z), depth, context)
+                    ctx.plan, ctx.direct = plan, True
+                    ctx.save_for_backward(depth, context)
+                    return out.permute(0, 3, 1, 2)
                 plan = PoolingPlan(geom_xyz, (X, Y, Z), frustum)
             assert plan.voxel_num == (X, Y, Z)
             direct = plan.mode == 'runs' and _nchw_direct(context, depth)
@@ -459,7 +511,7 @@ class VoxelPoolingFused(Function):
             depth, context, context_rows = ctx.saved_tensors
         with torch.cuda.device(grad_out.device):
             grad_depth, grad_context = fused_backward(ctx.plan, grad_out, depth, context, context_rows)
-        return None, grad_depth, grad_context, None, None
+        return None, grad_depth, grad_context, None, None, None, None
 
 
 def voxel_pooling_fused(geom_xyz: Optional[torch.Tensor], depth: torch.Tensor, context: torch.Tensor,
@@ -469,7 +521,7 @@ def voxel_pooling_fused(geom_xyz: Optional[torch.Tensor], depth: torch.Tensor, c
     geom_xyz: int32 (B, N, D, H, W, 3) (ignored when ``plan`` is given); depth (B*N, D, H, W)
     softmax probabilities; context (B*N, C, H, W), NCHW or channels_last.  Returns (B, C, Y, X)
     as a permuted view of a (B, Y, X, C) buffer, like the reference op."""
-    return VoxelPoolingFused.apply(geom_xyz, depth, context, voxel_num, plan)
+    return VoxelPoolingFused.apply(geom_xyz, depth, context, voxel_num, plan, None, None)
 
 
 class VoxelPoolingFusedConcat(Function):

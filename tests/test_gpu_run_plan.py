@@ -172,3 +172,38 @@ def test_max_runs_hint_makes_the_chain_capturable():
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(captured, eager)
+
+
+def test_cold_forward_with_overlapped_fill_equals_plain_forward_and_is_capturable():
+    """fused_forward_cold: output zero-filled on a side stream while the plan is built, forward writes occupied cells
+    only -- bit-equal to the plain sequence, eagerly and inside a CUDA graph."""
+    from mm_training_b200.ops.voxel_pooling import fused_forward_cold
+    cfg, B = CFG_2, 3
+    geom, vn_t = synthetic.camera_rig(cfg, B, device=DEV, yaw_jitter_deg=5.0, seed=12)
+    vn = tuple(int(v) for v in vn_t.tolist())
+    depth, ctx, _ = synthetic.camera_features(cfg, B, device=DEV, seed=12)
+    fr = tuple(geom.shape[1:5])
+    ref_plan = build_plan(geom, vn, frustum=fr)
+    ref = fused_forward(ref_plan, depth, ctx)
+    n = ref_plan.num_sorted
+    plan, out = fused_forward_cold(lambda: build_plan(geom, vn, frustum=fr, max_runs=n), B, vn, depth, ctx)
+    assert torch.equal(out, ref) and plan.status() == 0
+    cl = ctx.contiguous(memory_format=torch.channels_last)
+    assert torch.equal(fused_forward_cold(lambda: build_plan(geom, vn, frustum=fr, max_runs=n), B, vn, depth, cl)[1], ref)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fused_forward_cold(lambda: build_plan(geom, vn, frustum=fr, max_runs=n), B, vn, depth, ctx)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        _, captured = fused_forward_cold(lambda: build_plan(geom, vn, frustum=fr, max_runs=n), B, vn, depth, ctx)
+    for _ in range(3):
+        captured.fill_(float('nan'))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(captured, ref)
+    # the autograd op takes the same path when it builds the plan itself
+    d, c = depth.clone().requires_grad_(True), ctx.clone().requires_grad_(True)
+    o = voxel_pooling_fused(geom, d, c, vn)
+    assert torch.equal(o.permute(0, 2, 3, 1), ref)
