@@ -258,7 +258,8 @@ int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t r
  * bevvox_hard_voxelize_scatter (dense path only) takes the clouds either concatenated or as a DEVICE array of `batch`
  * per-sample base pointers (points == NULL; the reference passes a list of tensors: no concatenation pass) and, with
  * canvas != NULL, also writes the dense canvas (batch, mean_features, gz, gy, gx) of the fused HardSimpleVFE mean --
- * voxelize -> VFE -> scatter of models/bev_depth.py:181-183 in one call.                                               */
+ * voxelize -> VFE -> scatter of models/bev_depth.py:181-183 in one call.  canvas_is_zeroed != 0: the caller zero-filled
+ * the canvas already (e.g. on a side stream while the voxelizer's first kernels run); else the call fills it.          */
 int bevvox_temp_bytes(int batch, int64_t total_points, const int *grid_host, int max_voxels, int max_points,
                       size_t *temp_bytes);
 int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int batch,
@@ -272,7 +273,8 @@ int bevvox_hard_voxelize_scatter(const float *points, const float *const *sample
                                  int64_t max_sample_points, int num_features, const float *voxel_size_host,
                                  const float *range_host, const int *grid_host, int max_points, int max_voxels,
                                  float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_base,
-                                 float *voxel_mean, int mean_features, float *canvas, void *temp, void *stream);
+                                 float *voxel_mean, int mean_features, float *canvas, int canvas_is_zeroed, void *temp,
+                                 void *stream);
 /* mmcv dynamic voxelization: coors (num_points, 3) int32 [z, y, x], -1 for out-of-range points */
 int bevvox_dynamic_voxelize(const float *points, int64_t num_points, int num_features,
                             const float *voxel_size_host, const float *range_host,

@@ -428,6 +428,19 @@ __global__ void vox_dense_base_kernel(const uint32_t *__restrict__ totals, int b
   if (threadIdx.x == 0) voxel_base[batch] = run;
 }
 
+// A point enters its voxel's slot list (words = kVoxIdxBias - index, 0 = empty, kept sorted descending = ascending
+// index by a chain of atomicMax: the larger word stays, the smaller one is carried to the next slot).  Words only grow,
+// so every slot that already holds a LARGER word (an earlier point) is final for this point and the chain may start
+// behind them: the thread first READS the list (independent loads, one round trip), counts those slots -- all
+// max_points of them: the point can never enter (near-range cells receive thousands of points) -- and issues its first
+// atomic at that position.  Points arriving in index order (the common case: CTAs start in point order) cost one read
+// round trip + one atomic instead of a dependent atomic per occupied slot; a thread's 4 points go through the stages
+// together, not one after the other.  The result is the max_points smallest indices in order whatever the interleaving.
+__device__ __forceinline__ int ld_cg_i32(const int *p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __global__ void __launch_bounds__(256)
 vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                  const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base, int max_voxels,
@@ -437,29 +450,44 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
   const int i0 = begin + blockIdx.x * (256 * kVcPer) + threadIdx.x;
   if (i0 - (int)threadIdx.x >= end) return;
   const int base = voxel_base[b];
-  int gc[kVcPer], vid[kVcPer];
+  int gc[kVcPer], vid[kVcPer], pos[kVcPer], v[kVcPer];
+  int *slot0[kVcPer];
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) gc[k] = i0 + 256 * k < end ? point_gcell[i0 + 256 * k] : -1;
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) vid[k] = gc[k] >= 0 ? vid_of_cell[gc[k]] : max_voxels;
+  // stage 1: position of the first slot that does not hold an earlier point
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
-    if (vid[k] >= max_voxels) continue;                  // out of range, or voxel cap: the whole cell is dropped
-    int *slot0 = lists + (int64_t)(base + vid[k]) * max_points;
-    int v = kVoxIdxBias - (i0 + 256 * k);
-    // words only grow: once the LAST slot holds an earlier point (a larger word) every slot does and this point can
-    // never enter.  Checked before the first atomic: the thousands of points of a near-range cell would otherwise all
-    // queue on the same 15 words (CTAs start in point order, so the list is full of early points almost at once).
-    if (*reinterpret_cast<volatile int *>(slot0 + (max_points - 1)) > v) continue;
-    int old = atomicMax(slot0, v);
-    if (old == 0) continue;                              // first point of the voxel so far: done (the common case)
-    v = old < v ? old : v;                               // carry the later point to the next slot
-    // once the last slot holds an earlier point this one can never enter
-    if (max_points == 1 || *reinterpret_cast<volatile int *>(slot0 + (max_points - 1)) > v) continue;
-    for (int t = 1; t < max_points; ++t) {
-      old = atomicMax(slot0 + t, v);
-      if (old == 0) break;
-      v = old < v ? old : v;
+    pos[k] = max_points;                                  // "cannot enter" (out of range, voxel cap, list full of earlier points)
+    v[k] = kVoxIdxBias - (i0 + 256 * k);
+    slot0[k] = lists;
+    if (vid[k] < max_voxels) {
+      slot0[k] = lists + (int64_t)(base + vid[k]) * max_points;
+      int p = 0;
+      if (max_points <= 16) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t < max_points) p += ld_cg_i32(slot0[k] + t) > v[k];
+      } else {
+        for (int t = 0; t < max_points; ++t) p += ld_cg_i32(slot0[k] + t) > v[k];
+      }
+      pos[k] = p;
+    }
+  }
+  // stage 2: first atomic of every point
+  int old[kVcPer];
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) old[k] = pos[k] < max_points ? atomicMax(slot0[k] + pos[k], v[k]) : 0;
+  // stage 3: carry the displaced (later) point down the list -- rare
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) {
+    if (old[k] == 0) continue;
+    int carry = old[k] < v[k] ? old[k] : v[k];
+    for (int t = pos[k] + 1; t < max_points; ++t) {
+      const int o = atomicMax(slot0[k] + t, carry);
+      if (o == 0) break;
+      carry = o < carry ? o : carry;
     }
   }
 }
@@ -472,6 +500,7 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
 // exactly once, coalesced (no memset of the 93 %-padding tensor, no 20-byte scattered stores).  Rows beyond the voxel
 // count are written as zeros with num_points = 0.
 constexpr int kFinWarps = 4;
+template <int FM>                                       // FM >= F: bound of the per-point register arrays (8 or 16)
 __global__ void __launch_bounds__(kFinWarps * 32)
 vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
                     const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists, int batch, int max_voxels,
@@ -501,33 +530,56 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
       const int b = lo;
       const int begin = offsets[b];
       const int32_t *list = lists + row * max_points;
-      int word = list[0];
+      // the row's slot words first (independent loads: one round trip), then its points four at a time
+      int words[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) words[t] = t < max_points ? __ldg(list + t) : 0;
       const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
       const int64_t c = (int64_t)gc - (int64_t)b * cells;
       const int x = (int)(c % g.gx), y = (int)((c / g.gx) % g.gy), z = (int)(c / ((int64_t)g.gx * g.gy));
       reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
       float *trow = tile + (size_t)lane * TF;
-      float sum[kVoxMaxF];
+      float sum[FM];
 #pragma unroll
-      for (int k = 0; k < kVoxMaxF; ++k) sum[k] = 0.f;
-      while (word != 0) {
-        float *dst = trow + cnt * F;
-        const float *src = pts.row(b, begin, kVoxIdxBias - word, F);
-        ++cnt;
-        word = cnt < max_points ? list[cnt] : 0;          // next slot's word, in flight behind this slot's point
-        float val[kVoxMaxF];
+      for (int k = 0; k < FM; ++k) sum[k] = 0.f;
+      auto word_at = [&](int t) { return t < 16 ? words[t & 15] : (t < max_points ? __ldg(list + t) : 0); };
+      for (int t0 = 0; t0 < max_points; t0 += 4) {
+        int wq[4];
 #pragma unroll
-        for (int k = 0; k < kVoxMaxF; ++k)
-          if (k < F) val[k] = __ldg(src + k);
+        for (int j = 0; j < 4; ++j) {
+          int w = 0;
+          if (t0 + j < 16) {
 #pragma unroll
-        for (int k = 0; k < kVoxMaxF; ++k) {
-          if (k < F) dst[k] = val[k];
-          if (k < mean_features) sum[k] += val[k];
+            for (int q = 0; q < 16; ++q) w = (q == t0 + j) ? words[q] : w;      // (register array: no dynamic indexing)
+          } else {
+            w = word_at(t0 + j);
+          }
+          wq[j] = w;
+        }
+        if (wq[0] == 0) break;                             // filled slots are a prefix
+        float val[4][FM];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float *src = pts.row(b, begin, kVoxIdxBias - (wq[j] ? wq[j] : wq[0]), F);
+#pragma unroll
+          for (int k = 0; k < FM; ++k)
+            if (k < F) val[j][k] = __ldg(src + k);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (wq[j] == 0) break;
+          float *dst = trow + cnt * F;
+          ++cnt;
+#pragma unroll
+          for (int k = 0; k < FM; ++k) {
+            if (k < F) dst[k] = val[j][k];
+            if (k < mean_features) sum[k] += val[j][k];
+          }
         }
       }
       if (voxel_mean || canvas) {
 #pragma unroll
-        for (int k = 0; k < kVoxMaxF; ++k) {
+        for (int k = 0; k < FM; ++k) {
           if (k >= mean_features) break;
           const float m = sum[k] / (float)cnt;
           if (voxel_mean) voxel_mean[row * mean_features + k] = m;
@@ -647,10 +699,35 @@ extern "C" int bevvox_temp_bytes(int batch, int64_t total_points, const int *gri
   return BEVPOOL_OK;
 }
 
+static bool vox_overlap_enabled() {
+  static const bool on = [] {
+    const char *e = std::getenv("BEVVOX_CANVAS_OVERLAP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+// one non-blocking side stream per device, created on first use (host object only: no device memory)
+static cudaStream_t vox_side_stream() {
+  static cudaStream_t streams[64] = {nullptr};
+  static std::atomic<int> lock{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev]) {
+    while (lock.exchange(1)) {}
+    if (!streams[dev]) {
+      cudaStream_t s = nullptr;
+      if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) streams[dev] = s;
+    }
+    lock.store(0);
+  }
+  return streams[dev];
+}
+
 static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int batch, int64_t total_points,
                                int64_t max_sample_points, int F, const VoxGeom &g, const int *grid, int max_points,
                                int max_voxels, float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_base,
-                               float *voxel_mean, int mean_features, float *canvas, void *temp, cudaStream_t stream) {
+                               float *voxel_mean, int mean_features, float *canvas, void *temp, cudaStream_t stream,
+                               bool fill_canvas) {
   const VoxDenseTemp L = vox_dense_layout(batch, total_points, max_voxels, max_points, grid);
   int32_t *lists = reinterpret_cast<int32_t *>(static_cast<char *>(temp) + L.off_lists);
   const int tps = (int)scan_num_tiles(max_sample_points > 0 ? max_sample_points : 1);   // <= L.tiles_per_sample
@@ -662,6 +739,26 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   uint32_t *totals = reinterpret_cast<uint32_t *>(tb + L.off_totals);
   const int64_t cells = (int64_t)grid[0] * grid[1] * grid[2];
   const size_t rows = (size_t)batch * max_voxels;
+  // The canvas fill (335 MB per 32 sweeps of pure DRAM-write work) does not depend on anything the first four kernels do,
+  // and those are latency bound: it runs on a side stream (fork here, join before the kernel that scatters into it).
+  // Event fork / join is legal under stream capture; the side stream is created once per device.
+  cudaEvent_t ev_join = nullptr;
+  if (canvas && fill_canvas) {
+    const size_t cbytes = (size_t)batch * mean_features * g.gx * g.gy * g.gz * sizeof(float);
+    cudaStream_t side = vox_overlap_enabled() ? vox_side_stream() : nullptr;
+    if (side) {
+      cudaEvent_t ev_fork = nullptr;
+      BEVPOOL_RETURN_IF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      BEVPOOL_RETURN_IF_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      BEVPOOL_RETURN_IF_CUDA(cudaEventRecord(ev_fork, stream));
+      BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(canvas, 0, cbytes, side));
+      BEVPOOL_RETURN_IF_CUDA(cudaEventRecord(ev_join, side));
+      cudaEventDestroy(ev_fork);                            // (released once the recorded work has completed)
+    } else {
+      BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(canvas, 0, cbytes, stream));
+    }
+  }
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, L.zero_bytes, stream));
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
   const dim3 pgrid((unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer), (unsigned)batch);
@@ -683,11 +780,24 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   }
   const size_t fin_smem = (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
   if (fin_smem > 200 * 1024) return BEVPOOL_E_RANGE;       // max_points * F beyond ~390 floats: not a pillar configuration
-  if (fin_smem > 48 * 1024)
-    BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-  vox_finalize_kernel<<<(unsigned)ceil_div64((int64_t)rows, kFinWarps * 32), kFinWarps * 32, fin_smem, stream>>>(
-      pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
-      voxel_mean, mean_features, canvas);
+  if (ev_join) {
+    BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    cudaEventDestroy(ev_join);
+  }
+  const unsigned fin_grid = (unsigned)ceil_div64((int64_t)rows, kFinWarps * 32);
+  if (F <= 8) {
+    if (fin_smem > 48 * 1024)
+      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    vox_finalize_kernel<8><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
+        pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
+        voxel_mean, mean_features, canvas);
+  } else {
+    if (fin_smem > 48 * 1024)
+      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
+    vox_finalize_kernel<16><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
+        pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
+        voxel_mean, mean_features, canvas);
+  }
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
@@ -696,7 +806,8 @@ static int hard_voxelize_impl(const float *points, const float *const *sample_pt
                               int64_t max_sample_points, int num_features, const float *voxel_size_host,
                               const float *range_host, const int *grid_host, int max_points, int max_voxels,
                               float *voxels, int32_t *coors, int32_t *num_points, int32_t *voxel_base,
-                              float *voxel_mean, int mean_features, float *canvas, void *temp, void *stream_) {
+                              float *voxel_mean, int mean_features, float *canvas, void *temp, void *stream_,
+                              bool canvas_prezeroed = false) {
   int rc = check_vox_args(batch, total_points, num_features, max_voxels, max_points);
   if (rc) return rc;
   if (!sample_offsets || !voxel_size_host || !range_host || !grid_host || !voxels || !coors || !num_points ||
@@ -709,12 +820,10 @@ static int hard_voxelize_impl(const float *points, const float *const *sample_pt
   const VoxGeom g = make_geom(voxel_size_host, range_host, grid_host);
   if (g.gx <= 0 || g.gy <= 0 || g.gz <= 0) return BEVPOOL_E_ARG;
   if (vox_dense_ok(batch, grid_host)) {
-    if (canvas) {          // dense BEV canvas of the fused HardSimpleVFE mean: (batch, mean_features, gz, gy, gx), zeroed here
-      BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(canvas, 0, (size_t)batch * mean_features * g.gx * g.gy * g.gz * sizeof(float), stream));
-    }
+    // dense BEV canvas of the fused HardSimpleVFE mean: (batch, mean_features, gz, gy, gx), zero-filled by the call unless the caller did
     return hard_voxelize_dense(VoxPoints{points, sample_ptrs}, sample_offsets, batch, total_points, max_sample_points, num_features, g, grid_host,
                                max_points, max_voxels, voxels, coors, num_points, voxel_base, voxel_mean, mean_features,
-                               canvas, temp, stream);
+                               canvas, temp, stream, !canvas_prezeroed);
   }
   if (canvas || !points) return BEVPOOL_E_RANGE;   // the fused canvas and per-sample pointers exist on the dense-grid path only
   const VoxTemp L = vox_temp_layout(batch, total_points, max_voxels, max_points);
@@ -776,11 +885,11 @@ extern "C" int bevvox_hard_voxelize_scatter(const float *points, const float *co
                                             const float *range_host, const int *grid_host, int max_points,
                                             int max_voxels, float *voxels, int32_t *coors, int32_t *num_points,
                                             int32_t *voxel_base, float *voxel_mean, int mean_features, float *canvas,
-                                            void *temp, void *stream_) {
+                                            int canvas_is_zeroed, void *temp, void *stream_) {
   if (grid_host && !vox_dense_ok(batch, grid_host)) return BEVPOOL_E_RANGE;
   return hard_voxelize_impl(points, sample_ptrs, sample_offsets, batch, total_points, max_sample_points, num_features,
                             voxel_size_host, range_host, grid_host, max_points, max_voxels, voxels, coors, num_points,
-                            voxel_base, voxel_mean, mean_features, canvas, temp, stream_);
+                            voxel_base, voxel_mean, mean_features, canvas, temp, stream_, canvas_is_zeroed != 0);
 }
 
 extern "C" int bevvox_dynamic_voxelize(const float *points, int64_t num_points, int num_features,

@@ -81,14 +81,18 @@ class LiftSplatGeometry:
 
     # ---- the reference's tensors (oracle for the integer indices) ------------------------------------
     def geom_xyz(self, sensor2ego_mat: torch.Tensor, intrin_mat: torch.Tensor) -> torch.Tensor:
-        """int32 (B, N, D, H, W, 3) exactly as ``lss_fpn.py:455-462`` makes it."""
-        pts = geometry.get_geometry(self.frustum, sensor2ego_mat, intrin_mat)
-        return geometry.quantise_geometry(pts, self.voxel_coord, self.voxel_size).contiguous()
+        """int32 (B, N, D, H, W, 3) exactly as ``lss_fpn.py:455-462`` makes it (in float32: autocast is switched off here
+        -- under bf16 autocast the matmuls of the reference's geometry would run in bf16 and move points by metres)."""
+        with torch.autocast(device_type=self.device.type, enabled=False):
+            pts = geometry.get_geometry(self.frustum, sensor2ego_mat.float(), intrin_mat.float())
+            return geometry.quantise_geometry(pts, self.voxel_coord, self.voxel_size).contiguous()
 
     @staticmethod
     def combine(sensor2ego_mat: torch.Tensor, intrin_mat: torch.Tensor) -> torch.Tensor:
-        """``sensor2ego @ inverse(intrin)`` (B, N, 4, 4) -- ``lss_fpn.py:354``, left in torch (B*N tiny matrices)."""
-        return sensor2ego_mat.matmul(torch.inverse(intrin_mat)).contiguous()
+        """``sensor2ego @ inverse(intrin)`` (B, N, 4, 4) -- ``lss_fpn.py:354``, left in torch (B*N tiny matrices); always
+        float32 (autocast off)."""
+        with torch.autocast(device_type=sensor2ego_mat.device.type, enabled=False):
+            return sensor2ego_mat.float().matmul(torch.inverse(intrin_mat.float())).contiguous()
 
     # ---- device path ---------------------------------------------------------------------------------
     def rig_geom(self, combine: torch.Tensor, variant: int) -> torch.Tensor:

@@ -134,7 +134,7 @@ def hard_voxelize_batch(points_list: Sequence[torch.Tensor], voxel_size, point_c
             _lib.check(L.bevvox_hard_voxelize_scatter(
                 points.data_ptr() if (points is not None and total > 0) else None,
                 sample_ptrs.data_ptr() if sample_ptrs is not None else None, *tail,
-                canvas.data_ptr() if canvas is not None else None, temp.data_ptr(), _lib.stream_ptr(dev)),
+                canvas.data_ptr() if canvas is not None else None, 0, temp.data_ptr(), _lib.stream_ptr(dev)),
                 'bevvox_hard_voxelize_scatter')
         else:
             _lib.check(L.bevvox_hard_voxelize(points.data_ptr() if total > 0 else None, *tail, temp.data_ptr(),
