@@ -516,7 +516,7 @@ def main():
     from mm_training_b200.ops.voxel_pooling import fused_forward_cold
 
     def step():
-        # cold call: the output's zero fill runs on a side stream while the plan is built (fork / join inside the step)
+        # cold call: plan build, then forward (BEVPOOL_COLD_OVERLAP=1: zero fill on a side stream behind the plan build)
         plan, out = fused_forward_cold(make_plan, B, vn, depth, ctx)      # NCHW context read through a TMA tensor map
         gd, gc = fused_backward(plan, go, depth, ctx)  # NCHW incoming gradient; grad_context written NCHW like ctx
         return plan, out, gd, gc

@@ -360,15 +360,17 @@ def _side_stream(device) -> torch.cuda.Stream:
 
 
 def fused_forward_cold(make_plan, batch: int, voxel_num: VoxelNum, depth: torch.Tensor, context: torch.Tensor):
-    """Plan build + fused forward of a COLD call (geometry changed: the plan is rebuilt).  80 % of a BEV grid is empty
-    and its zero fill is pure DRAM-write work, while the plan kernels are latency / issue bound and leave DRAM idle: the
-    output is zero-filled on a side stream WHILE ``make_plan()`` runs on the caller's stream (fork / join with events:
-    CUDA-graph capturable), and the forward then writes occupied cells only.  Returns ``(plan, out (B, Y, X, C))``.
-    Point plans / unsupported shapes take the plain sequence."""
+    """Plan build + fused forward of a COLD call (geometry changed: the plan is rebuilt); returns ``(plan, out (B, Y, X,
+    C))``.  With ``BEVPOOL_COLD_OVERLAP=1`` the output is zero-filled on a side stream WHILE ``make_plan()`` runs on the
+    caller's stream (fork / join with events: CUDA-graph capturable) and the forward then writes occupied cells only.
+    MEASURED SLOWER than the default (B200, CFG-2, 32 frames: 401 us vs 390 us per step): stage A already hides its fill
+    -- one TMA bulk store per empty 32-cell block, issued by the copy engine behind the issue-bound reduction -- while a
+    separate fill kernel competes with the plan kernels for SM slots and adds a fork / join.  Kept as an option (and
+    tested) because the balance shifts for grids that are mostly empty AND large (512 x 512)."""
     X, Y, _ = _voxel_num_ints(voxel_num)
     C = context.shape[1]
     dev = depth.device
-    if not runs_supported(C, depth.dtype) or os.environ.get('BEVPOOL_COLD_OVERLAP', '1') == '0':
+    if not runs_supported(C, depth.dtype) or os.environ.get('BEVPOOL_COLD_OVERLAP', '0') != '1':
         plan = make_plan()
         return plan, fused_forward(plan, depth, context)
     with torch.cuda.device(dev):

@@ -174,10 +174,11 @@ def test_max_runs_hint_makes_the_chain_capturable():
     assert torch.equal(captured, eager)
 
 
-def test_cold_forward_with_overlapped_fill_equals_plain_forward_and_is_capturable():
-    """fused_forward_cold: output zero-filled on a side stream while the plan is built, forward writes occupied cells
-    only -- bit-equal to the plain sequence, eagerly and inside a CUDA graph."""
+def test_cold_forward_with_overlapped_fill_equals_plain_forward_and_is_capturable(monkeypatch):
+    """fused_forward_cold with BEVPOOL_COLD_OVERLAP=1: output zero-filled on a side stream while the plan is built,
+    forward writes occupied cells only -- bit-equal to the plain sequence, eagerly and inside a CUDA graph."""
     from mm_training_b200.ops.voxel_pooling import fused_forward_cold
+    monkeypatch.setenv('BEVPOOL_COLD_OVERLAP', '1')
     cfg, B = CFG_2, 3
     geom, vn_t = synthetic.camera_rig(cfg, B, device=DEV, yaw_jitter_deg=5.0, seed=12)
     vn = tuple(int(v) for v in vn_t.tolist())
