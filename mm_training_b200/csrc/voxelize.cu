@@ -19,6 +19,7 @@
 // numbering kernel for the same result.
 #include "common.cuh"
 #include "scan.cuh"
+#include "tma.cuh"
 
 #include <cstdlib>
 
@@ -237,18 +238,19 @@ __global__ void scatter_backward_kernel(const T *__restrict__ grad_canvas, const
 // ==== dense-grid path (grids that fit a per-cell table: the aiMotive pillar grid is 2048 x 256 x 1) =================
 // The hash table is replaced by what mmcv's own CPU kernel uses, a dense cell -> first-point table, and the
 // pipeline shrinks to 4 kernels with no per-voxel index lists and no per-point prefix array:
-//   A vox_cell_kernel      points staged through shared memory with fully coalesced 4-byte loads (a point row is
-//                          F*4 = 20 bytes: no wider aligned access exists), global cell id per point,
-//                          warp-aggregated atomicMin -> first point of every cell
+//   A vox_cell_kernel      a tile of 1024 points = one contiguous span of the cloud brought into shared memory by ONE
+//                          TMA bulk copy (a point row is F*4 = 20 bytes: no wider aligned per-thread access exists),
+//                          global cell id per point, warp-aggregated atomicMin -> first point of every cell
 //   B vox_scan_kernel      per sample: "first point of its cell" flags computed on the fly + decoupled look-back scan
-//                          = voxel numbering in point order; the creating point publishes vid_of_cell[cell] and
+//                          = voxel numbering in point order; the creating point overwrites its cell's entry of the
+//                          first-point table with ~vid (one table serves both lookups) and publishes
 //                          cell_of_vid[sample][vid]
-//   C vox_claim_kernel     per kept point: cell -> voxel number -> chain of atomicMax on the voxel's slot list
-//                          (max_points words holding 0x7fffffff - index, zero = empty: the list ends up holding the
-//                          max_points smallest indices in ascending order whatever the interleaving).  The lists are
-//                          a compact array that stays in L2 -- atomics on the padded voxel tensor itself (15 x F
-//                          floats per row, far larger than L2) ran at DRAM random-access speed, 4x slower
-//   D vox_finalize_kernel  one lane per voxel row, one warp per 32 rows: slot list -> point rows gathered into a
+//   C vox_claim_kernel     per kept point: cell -> voxel number -> the voxel's slot list (max_points words holding
+//                          0x7fffffff - index, zero = empty), an unsorted set that converges to the max_points
+//                          smallest indices by compare-and-swap eviction of the latest point (see the kernel).  The
+//                          lists are a compact array that stays in L2 -- atomics on the padded voxel tensor itself
+//                          (15 x F floats per row, far larger than L2) ran at DRAM random-access speed, 4x slower
+//   D vox_finalize_kernel  one lane per voxel row, one warp per 32 rows: slot list sorted in registers -> point rows gathered into a
 //                          shared-memory tile that leaves as one contiguous, coalesced span of the padded voxel
 //                          tensor (93 % of it is zeros: written once, by this kernel, at streaming-store speed);
 //                          count, coordinates, HardSimpleVFE mean in slot order and, optionally, its pillar scatter
@@ -270,15 +272,31 @@ constexpr int kVcPer = 4;                          // points per thread: indepen
 __global__ void __launch_bounds__(kVcThreads)
 vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
                 int32_t *__restrict__ first, int32_t *__restrict__ point_gcell) {
-  extern __shared__ float s_pts[];                 // kVcPer * kVcThreads * F floats
+  extern __shared__ __align__(16) float s_pts[];   // kVcPer * kVcThreads * F floats
+  __shared__ __align__(8) uint64_t s_bar;
   const int b = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
   const int tile0 = begin + blockIdx.x * (kVcThreads * kVcPer);
   if (tile0 >= end) return;
   const int npts = min(kVcThreads * kVcPer, end - tile0);
   const float *src = pts.row(b, begin, tile0, F);
-  for (int e = threadIdx.x; e < npts * F; e += kVcThreads) s_pts[e] = ldg_stream_f32(src + e);
-  __syncthreads();
+  // the tile is one contiguous span of the cloud: ONE bulk copy (TMA, SASS UBLKCP) when its address and size are
+  // multiples of 16 bytes (always for full tiles of a 16-byte aligned cloud), else 4-byte loads (a point row is F*4 = 20
+  // bytes: no wider aligned per-thread access exists)
+  const uint32_t bytes = (uint32_t)npts * (uint32_t)F * 4u;
+  if (((reinterpret_cast<uintptr_t>(src) | bytes) & 15u) == 0) {
+    if (threadIdx.x == 0) {
+      mbar_init(&s_bar, 1);
+      fence_mbar_init();
+      mbar_expect_tx(&s_bar, bytes);
+      tma_load_1d(s_pts, src, bytes, &s_bar);
+    }
+    __syncthreads();                               // (the barrier is initialised before anybody polls it)
+    mbar_wait(&s_bar, 0);
+  } else {
+    for (int e = threadIdx.x; e < npts * F; e += kVcThreads) s_pts[e] = ldg_stream_f32(src + e);
+    __syncthreads();
+  }
   int gcell[kVcPer];
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
@@ -299,12 +317,13 @@ vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGe
 }
 
 // Per SAMPLE (blockIdx.y) exclusive scan, in point order, of flag(i) = "i is the first point of its cell" = the voxel
-// number of every cell-creating point, which publishes it: vid_of_cell[global cell] = vid and cell_of_vid[b][vid] =
-// global cell (vid < max_voxels only).  The sample's number of distinct cells goes to totals[b].  One decoupled
+// number of every cell-creating point, which publishes it: first[global cell] = ~vid (the entry held the point's own
+// index until then; other points of the cell only test it against THEIR index) and cell_of_vid[b][vid] = global cell
+// (vid < max_voxels only).  The sample's number of distinct cells goes to totals[b].  One decoupled
 // look-back chain per sample (a single chain over the whole batch is latency-bound on its tile hand-offs).
 static __global__ void __launch_bounds__(kScanThreads)
 vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
-                const int32_t *__restrict__ first, int32_t *__restrict__ vid_of_cell, int32_t *__restrict__ cell_of_vid,
+                int32_t *first, int32_t *__restrict__ cell_of_vid,
                 int max_voxels, uint32_t *__restrict__ totals, unsigned long long *status, unsigned int *tickets,
                 int tiles_per_sample) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
@@ -402,7 +421,7 @@ vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (fl[k]) {                                        // a creating point: o[k] is its cell's voxel number
-        vid_of_cell[gcs[r][k]] = (int32_t)o[k];
+        first[gcs[r][k]] = ~(int32_t)o[k];                // (readers compare with their own index: either value differs)
         if (o[k] < (uint32_t)max_voxels) cell_of_vid[(int64_t)b * max_voxels + o[k]] = gcs[r][k];
       }
     }
@@ -428,81 +447,131 @@ __global__ void vox_dense_base_kernel(const uint32_t *__restrict__ totals, int b
   if (threadIdx.x == 0) voxel_base[batch] = run;
 }
 
-// A point enters its voxel's slot list (words = kVoxIdxBias - index, 0 = empty, kept sorted descending = ascending
-// index by a chain of atomicMax: the larger word stays, the smaller one is carried to the next slot).  Words only grow
-// and the list is sorted at all times, so every slot that already holds a LARGER word (an earlier point) is final for
-// this point and the chain may start behind them.  A list row is padded to a multiple of 4 words (16-byte aligned): the
-// thread READS slots 0..3 (one 16-byte load) and the last slot (one load) -- if the last slot holds an earlier point the
-// list is full for this point (near-range cells receive thousands of points); else the first atomic goes to the first
-// of slots 0..4 that does not hold an earlier point.  87 % of the voxels hold at most 4 points and CTAs start in point
-// order, so a point typically costs two loads and ONE atomic instead of a dependent atomic per occupied slot, and a
-// thread's 4 points go through the stages together.  (Reading the whole list -- 15 requests per point -- was measured
-// slower than the plain chain: L2 request bound.)  The result is the max_points smallest indices in order, whatever
-// the interleaving.
-__device__ __forceinline__ int ld_cg_i32(const int *p) {
-  int v;
-  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
+// Slot lists.  A voxel's row holds words = kVoxIdxBias - index (> 0), padded to a multiple of 4 words (16-byte
+// aligned); it ends up holding the max_points SMALLEST point indices of the voxel as an UNSORTED set, whatever the
+// interleaving -- vox_finalize_kernel sorts the (at most max_points) words of a row in registers.  Two kernels:
+//   C1 vox_claim_kernel   every kept point takes a ticket from its voxel's arrival counter (one atomicAdd, no chain);
+//                         tickets below max_points are slots: the word is stored there.  Later arrivals append
+//                         (row, word) to an overflow list (one warp-aggregated atomic per warp).  87 % of the voxels
+//                         never overflow: for them this is already the result.
+//   C2 vox_evict_kernel   one thread per overflow entry (3.6 % of the points of a sweep: near-range cells receive
+//                         thousands of points).  The row is full by now; the entry reads it (16-byte L2 loads), finds
+//                         the slot holding the LATEST point and, if it is earlier itself, swaps itself in by
+//                         compare-and-swap.  Slot words only ever grow, so a successful swap proves the victim still
+//                         was the row's minimum at that moment: with max_points earlier points in the row it can never
+//                         be part of the result and is dropped.  A failed swap re-reads the row (somebody else made
+//                         progress); an entry that finds the row full of earlier points is done after the loads.
+// The sorted-insert formulation this replaces carried the displaced word down the row with one dependent atomicMax
+// round trip per slot (71 % of that kernel's stall samples: a sample's 196 CTAs run concurrently, so the points of a
+// near-range cell arrive in random order and most arrivals shifted half a row).
 __device__ __forceinline__ int4 ld_cg_i4(const int *p) {
   int4 v;
-  asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 __host__ __device__ inline int vox_list_stride(int max_points) { return (max_points + 3) & ~3; }
+
 __global__ void __launch_bounds__(256)
 vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                  const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base, int max_voxels,
-                 int max_points, int32_t *__restrict__ lists) {
+                 int max_points, int32_t *__restrict__ lists, uint32_t *__restrict__ arrivals,
+                 int2 *__restrict__ overflow, uint32_t *__restrict__ num_overflow) {
   const int b = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
   const int i0 = begin + blockIdx.x * (256 * kVcPer) + threadIdx.x;
   if (i0 - (int)threadIdx.x >= end) return;
   const int base = voxel_base[b];
   const int LS = vox_list_stride(max_points);
-  int gc[kVcPer], vid[kVcPer], pos[kVcPer], v[kVcPer];
-  int *slot0[kVcPer];
+  const int lane = threadIdx.x & 31;
+  int gc[kVcPer], row[kVcPer];
+  uint32_t pos[kVcPer];
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) gc[k] = i0 + 256 * k < end ? point_gcell[i0 + 256 * k] : -1;
 #pragma unroll
-  for (int k = 0; k < kVcPer; ++k) vid[k] = gc[k] >= 0 ? vid_of_cell[gc[k]] : max_voxels;
-  // stage 1: slots 0..3 and the last slot of every point's list (independent loads)
-  int4 head[kVcPer];
-  int last[kVcPer];
+  for (int k = 0; k < kVcPer; ++k) {
+    const int vid = gc[k] >= 0 ? ~vid_of_cell[gc[k]] : max_voxels;
+    row[k] = vid < max_voxels ? base + vid : -1;                 // (voxel cap: the whole cell is dropped)
+  }
+#pragma unroll
+  for (int k = 0; k < kVcPer; ++k) pos[k] = row[k] >= 0 ? atomicAdd(arrivals + row[k], 1u) : 0u;
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
-    v[k] = kVoxIdxBias - (i0 + 256 * k);
-    slot0[k] = lists;
-    head[k] = make_int4(0, 0, 0, 0);
-    last[k] = 0;
-    if (vid[k] < max_voxels) {
-      slot0[k] = lists + (int64_t)(base + vid[k]) * LS;
-      head[k] = ld_cg_i4(slot0[k]);                       // (padding words beyond max_points stay 0)
-      last[k] = ld_cg_i32(slot0[k] + (max_points - 1));
+    const int w = kVoxIdxBias - (i0 + 256 * k);
+    const bool over = row[k] >= 0 && pos[k] >= (uint32_t)max_points;
+    if (row[k] >= 0 && !over) lists[(int64_t)row[k] * LS + pos[k]] = w;
+    const unsigned bal = __ballot_sync(0xffffffffu, over);
+    if (bal) {
+      uint32_t at = 0;
+      if (lane == __ffs(bal) - 1) at = atomicAdd(num_overflow, (uint32_t)__popc(bal));
+      at = __shfl_sync(0xffffffffu, at, __ffs(bal) - 1);
+      if (over) overflow[at + __popc(bal & ((1u << lane) - 1u))] = make_int2(row[k], w);
     }
   }
-  // stage 2: first atomic of every point
-  int old[kVcPer];
+}
+
+// slot holding the row's smallest word (= latest point); rows here are full (no empty slots)
+template <int LQ>
+__device__ __forceinline__ int vox_pick_victim(const int4 (&q)[LQ], int max_points, int &minw) {
+  int mw = 0x7fffffff, ms = 0;
 #pragma unroll
-  for (int k = 0; k < kVcPer; ++k) {
-    pos[k] = max_points;                                  // "cannot enter" (out of range, voxel cap, list full of earlier points)
-    old[k] = 0;
-    if (vid[k] < max_voxels && !(last[k] > v[k])) {
-      int p = (head[k].x > v[k]) + (head[k].y > v[k]) + (head[k].z > v[k]) + (head[k].w > v[k]);
-      p = p < max_points ? p : max_points;
-      pos[k] = p;
-      if (p < max_points) old[k] = atomicMax(slot0[k] + p, v[k]);
+  for (int t = 0; t < 4 * LQ; ++t) {
+    const int4 qq = q[t >> 2];
+    const int w = (t & 3) == 0 ? qq.x : (t & 3) == 1 ? qq.y : (t & 3) == 2 ? qq.z : qq.w;
+    if (t < max_points && w < mw) { mw = w; ms = t; }
+  }
+  minw = mw;
+  return ms;
+}
+
+template <int LQ>                                        // row = 4 * LQ words (max_points <= 16); LQ = 0: any length
+__global__ void __launch_bounds__(256)
+vox_evict_kernel(const int2 *__restrict__ overflow, const uint32_t *__restrict__ num_overflow, int max_points,
+                 int32_t *__restrict__ lists) {
+  const uint32_t n = *num_overflow;
+  const int LS = vox_list_stride(max_points);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int2 ent = overflow[e];
+    int *row = lists + (int64_t)ent.x * LS;
+    const int w = ent.y;
+    while (true) {
+      int mw = 0x7fffffff, ms = 0;
+      if constexpr (LQ > 0) {
+        int4 q[LQ];
+#pragma unroll
+        for (int j = 0; j < LQ; ++j) q[j] = ld_cg_i4(row + 4 * j);
+        ms = vox_pick_victim<LQ>(q, max_points, mw);
+      } else {
+        for (int t4 = 0; t4 < LS; t4 += 4) {
+          const int4 qq = ld_cg_i4(row + t4);
+          const int ww[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (t4 + j < max_points && ww[j] < mw) { mw = ww[j]; ms = t4 + j; }
+        }
+      }
+      if (w < mw) break;                                  // the row is full of earlier points
+      if (atomicCAS(row + ms, mw, w) == mw) break;
     }
   }
-  // stage 3: carry the displaced (later) point down the list -- voxels with several points arriving out of order
+}
+
+// Batcher's merge-exchange network on 16 registers (63 compare-exchanges, every index a compile-time constant)
+__device__ __forceinline__ void vox_sort16_desc(int (&w)[16]) {
 #pragma unroll
-  for (int k = 0; k < kVcPer; ++k) {
-    if (old[k] == 0) continue;
-    int carry = old[k] < v[k] ? old[k] : v[k];
-    for (int t = pos[k] + 1; t < max_points; ++t) {
-      const int o = atomicMax(slot0[k] + t, carry);
-      if (o == 0) break;
-      carry = o < carry ? o : carry;
+  for (int p = 1; p < 16; p <<= 1) {
+#pragma unroll
+    for (int k = p; k >= 1; k >>= 1) {
+#pragma unroll
+      for (int j = k % p; j <= 16 - 1 - k; j += 2 * k) {
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+          if (i <= 16 - j - k - 1 && (i + j) / (p * 2) == (i + j + k) / (p * 2)) {
+            const int a = w[i + j], c = w[i + j + k];
+            w[i + j] = max(a, c);
+            w[i + j + k] = min(a, c);
+          }
+        }
+      }
     }
   }
 }
@@ -518,8 +587,8 @@ constexpr int kFinWarps = 4;
 template <int FM>                                       // FM >= F: bound of the per-point register arrays (8 or 16)
 __global__ void __launch_bounds__(kFinWarps * 32)
 vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
-                    const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists, int batch, int max_voxels,
-                    int max_points, float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
+                    const int32_t *__restrict__ cell_of_vid, int32_t *__restrict__ lists, const uint32_t *__restrict__ arrivals,
+                    int batch, int max_voxels, int max_points, float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
                     const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
                     float *__restrict__ canvas) {
   extern __shared__ __align__(16) float s_fin[];          // [kFinWarps][32][TF] floats, then voxel_base (batch + 1 ints)
@@ -545,14 +614,31 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
       const int b = lo;
       const int begin = offsets[b];
       const int LS = vox_list_stride(max_points);
-      const int32_t *list = lists + row * LS;
+      int32_t *list = lists + row * LS;
       // the row's slot words first (16-byte loads of the padded row: one round trip), then its points four at a time
       int words[16];
 #pragma unroll
       for (int t4 = 0; t4 < 4; ++t4) {
         int4 w4 = make_int4(0, 0, 0, 0);
-        if (4 * t4 < LS) w4 = __ldg(reinterpret_cast<const int4 *>(list) + t4);      // (padding words are 0)
+        if (4 * t4 < LS) w4 = reinterpret_cast<const int4 *>(list)[t4];               // (padding words are 0)
         words[4 * t4 + 0] = w4.x; words[4 * t4 + 1] = w4.y; words[4 * t4 + 2] = w4.z; words[4 * t4 + 3] = w4.w;
+      }
+      // the claim kernels leave an unsorted set in the first `filled` slots (the rest was never written):
+      // descending words = ascending point index, empty slots (0) last
+      const int filled = (int)min(arrivals[row], (uint32_t)max_points);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) words[t] = t < filled ? words[t] : 0;
+      if (max_points <= 16) {
+        vox_sort16_desc(words);
+      } else {                                             // long rows: insertion sort in place (this lane owns the row)
+        for (int t = 1; t < filled; ++t) {
+          const int w = list[t];
+          int u = t - 1;
+          while (u >= 0 && list[u] < w) { list[u + 1] = list[u]; --u; }
+          list[u + 1] = w;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) words[t] = t < filled ? list[t] : 0;
       }
       const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
       const int64_t c = (int64_t)gc - (int64_t)b * cells;
@@ -562,7 +648,7 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
       float sum[FM];
 #pragma unroll
       for (int k = 0; k < FM; ++k) sum[k] = 0.f;
-      auto word_at = [&](int t) { return t < 16 ? words[t & 15] : (t < max_points ? __ldg(list + t) : 0); };
+      auto word_at = [&](int t) { return t < 16 ? words[t & 15] : (t < filled ? list[t] : 0); };
       for (int t0 = 0; t0 < max_points; t0 += 4) {
         int wq[4];
 #pragma unroll
@@ -661,9 +747,10 @@ static VoxTemp vox_temp_layout(int batch, int64_t total_points, int max_voxels, 
 
 // dense mode: first-point table + voxel-number table over all cells of the batch (int32 each), point -> global cell ids
 struct VoxDenseTemp {
-  size_t off_status, off_tickets, off_lists, zero_bytes;   // [0, zero_bytes) memset 0 (scan status words, tickets, slot lists)
+  size_t off_status, off_tickets, off_arrivals, off_num_overflow, zero_bytes;   // [0, zero_bytes) memset 0 (scan status words, tickets, arrival counters)
+  size_t off_lists, off_overflow;
   size_t off_first, first_bytes;                // memset 0x7f
-  size_t off_vid, off_gcell, off_cell_of_vid, off_totals, bytes;
+  size_t off_gcell, off_cell_of_vid, off_totals, bytes;
   int tiles_per_sample;
 };
 constexpr int64_t kVoxDenseMaxCells = 1ll << 26;          // cells of the whole batch (2 x 256 MB of tables); larger grids hash
@@ -680,10 +767,12 @@ static VoxDenseTemp vox_dense_layout(int batch, int64_t total_points, int max_vo
   size_t o = 0;
   L.off_status = o;  o = align_up(o + (size_t)batch * L.tiles_per_sample * 8, 256);
   L.off_tickets = o; o = align_up(o + (size_t)batch * 4, 256);
-  L.off_lists = o;   o = align_up(o + (size_t)batch * max_voxels * vox_list_stride(max_points) * 4, 256);
+  L.off_arrivals = o; o = align_up(o + (size_t)batch * max_voxels * 4, 256);
+  L.off_num_overflow = o; o += 256;
   L.zero_bytes = o;
+  L.off_lists = o;   o = align_up(o + (size_t)batch * max_voxels * vox_list_stride(max_points) * 4, 256);   // (never read beyond a row's arrival count)
+  L.off_overflow = o; o = align_up(o + (size_t)total_points * 8, 256);
   L.off_first = o;  L.first_bytes = align_up((size_t)batch * cells * 4, 256); o += L.first_bytes;
-  L.off_vid = o;    o += align_up((size_t)batch * cells * 4, 256);
   L.off_gcell = o;  o = align_up(o + (size_t)total_points * 4, 256);
   L.off_cell_of_vid = o; o = align_up(o + (size_t)batch * max_voxels * 4, 256);
   L.off_totals = o; o = align_up(o + (size_t)batch * 4, 256);
@@ -753,7 +842,7 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   const int tps = (int)scan_num_tiles(max_sample_points > 0 ? max_sample_points : 1);   // <= L.tiles_per_sample
   char *tb = static_cast<char *>(temp);
   int32_t *first = reinterpret_cast<int32_t *>(tb + L.off_first);
-  int32_t *vid_of_cell = reinterpret_cast<int32_t *>(tb + L.off_vid);
+  const int32_t *vid_of_cell = first;                   // after the scan: ~(voxel number of the cell)
   int32_t *gcell = reinterpret_cast<int32_t *>(tb + L.off_gcell);
   int32_t *cell_of_vid = reinterpret_cast<int32_t *>(tb + L.off_cell_of_vid);
   uint32_t *totals = reinterpret_cast<uint32_t *>(tb + L.off_totals);
@@ -788,14 +877,27 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     BEVPOOL_LAUNCH_CHECK();
   }
   vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(
-      sample_offsets, gcell, first, vid_of_cell, cell_of_vid, max_voxels, totals,
+      sample_offsets, gcell, first, cell_of_vid, max_voxels, totals,
       reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
       L.tiles_per_sample);
   BEVPOOL_LAUNCH_CHECK();
   vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, batch, max_voxels, voxel_base);
   BEVPOOL_LAUNCH_CHECK();
   if (total_points > 0) {
-    vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists);
+    uint32_t *arrivals = reinterpret_cast<uint32_t *>(tb + L.off_arrivals);
+    int2 *overflow = reinterpret_cast<int2 *>(tb + L.off_overflow);
+    uint32_t *num_overflow = reinterpret_cast<uint32_t *>(tb + L.off_num_overflow);
+    vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
+                                                arrivals, overflow, num_overflow);
+    BEVPOOL_LAUNCH_CHECK();
+    const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div64(total_points, 256), (int64_t)kSMs * 8);
+    switch (max_points <= 16 ? vox_list_stride(max_points) / 4 : 0) {
+      case 1: vox_evict_kernel<1><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
+      case 2: vox_evict_kernel<2><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
+      case 3: vox_evict_kernel<3><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
+      case 4: vox_evict_kernel<4><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
+      default: vox_evict_kernel<0><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
+    }
     BEVPOOL_LAUNCH_CHECK();
   }
   const size_t fin_smem = (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
@@ -809,13 +911,15 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     if (fin_smem > 48 * 1024)
       BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     vox_finalize_kernel<8><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
-        pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
+        pts, sample_offsets, F, g, cells, cell_of_vid, lists, reinterpret_cast<const uint32_t *>(tb + L.off_arrivals), batch, max_voxels,
+        max_points, voxels, num_points, coors, voxel_base,
         voxel_mean, mean_features, canvas);
   } else {
     if (fin_smem > 48 * 1024)
       BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
     vox_finalize_kernel<16><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
-        pts, sample_offsets, F, g, cells, cell_of_vid, lists, batch, max_voxels, max_points, voxels, num_points, coors, voxel_base,
+        pts, sample_offsets, F, g, cells, cell_of_vid, lists, reinterpret_cast<const uint32_t *>(tb + L.off_arrivals), batch, max_voxels,
+        max_points, voxels, num_points, coors, voxel_base,
         voxel_mean, mean_features, canvas);
   }
   BEVPOOL_LAUNCH_CHECK();

@@ -109,6 +109,19 @@ def test_adversarial_sets():
     assert c.tolist() == [[0, 0, 0, 0]] and n.tolist() == [1]                      # NaN / inf dropped (documented)
 
 
+@pytest.mark.parametrize('T', [1, 3, 4, 8, 15, 16, 20, 35])
+def test_slot_lists_under_contention(T):
+    # every row length of the claim kernel (1..4 quads in registers, longer rows in a loop): 120 k points shuffled over
+    # 60 cells (2000 points per voxel arriving in random order) plus a sparse background
+    rng = np.random.default_rng(100 + T)
+    hot = np.stack([rng.integers(0, 10, 120000) + rng.random(120000) * 0.999,
+                    rng.integers(0, 6, 120000) + rng.random(120000) * 0.999, np.full(120000, 0.5)], 1)
+    cold = np.stack([rng.uniform(0, 64, 30000), rng.uniform(0, 64, 30000), np.full(30000, 0.5)], 1)
+    pts = np.concatenate([hot, cold]).astype(np.float32)
+    pts = np.concatenate([pts[rng.permutation(len(pts))], np.arange(len(pts), dtype=np.float32)[:, None]], 1)
+    _check_batch([pts, pts[::-1].copy()], [1, 1, 1], [0, 0, 0, 64, 64, 1], T, 3000, mean_features=4)
+
+
 @pytest.mark.parametrize('hash_path', [False, True])
 def test_dense_and_hash_tables_agree(hash_path, monkeypatch):
     # grids up to 2^26 cells use a dense first-point table, larger ones a hash table: same outputs
