@@ -136,6 +136,33 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   return p;
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// 4-byte accesses carrying an L2 eviction-priority policy (tables that several kernels of one call re-visit at random)
+__device__ __forceinline__ int ld_l2hint_i32(const int *p, uint64_t pol) {
+  int v;
+  asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_l2hint_i32(int *p, int v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_min_l2hint_i32(int *p, int v, uint64_t pol) {
+  asm volatile("red.global.min.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_l2hint_u32(uint32_t *p, uint32_t v, uint64_t pol) {
+  uint32_t r;
+  asm volatile("atom.global.add.L2::cache_hint.u32 %0, [%1], %2, %3;" : "=r"(r) : "l"(p), "r"(v), "l"(pol) : "memory");
+  return r;
+}
+__device__ __forceinline__ void tma_load_1d_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }

@@ -271,7 +271,7 @@ struct VoxPoints {                                   // point i of sample b (i g
 constexpr int kVcPer = 4;                          // points per thread: independent chains in flight, 4x fewer CTAs
 __global__ void __launch_bounds__(kVcThreads)
 vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
-                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell) {
+                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell, int l2_hints) {
   extern __shared__ __align__(16) float s_pts[];   // kVcPer * kVcThreads * F floats
   __shared__ __align__(8) uint64_t s_bar;
   const int b = blockIdx.y;
@@ -289,7 +289,8 @@ vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGe
       mbar_init(&s_bar, 1);
       fence_mbar_init();
       mbar_expect_tx(&s_bar, bytes);
-      tma_load_1d(s_pts, src, bytes, &s_bar);
+      if (l2_hints & 4) tma_load_1d_hint(s_pts, src, bytes, &s_bar, l2_policy_evict_first());   // (re-read by the gather, much later)
+      else tma_load_1d(s_pts, src, bytes, &s_bar);
     }
     __syncthreads();                               // (the barrier is initialised before anybody polls it)
     mbar_wait(&s_bar, 0);
@@ -308,11 +309,15 @@ vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGe
       point_gcell[tile0 + p] = gcell[k];
     }
   }
-  // one atomic per distinct cell of the warp: the lowest lane of a match group holds the lowest index
+  // one atomic per distinct cell of the warp: the lowest lane of a match group holds the lowest index.  The table is
+  // visited at random by three kernels of the call: its lines are marked evict_last so that the streams in between
+  // (points in, cell ids out) do not push them out of L2.
+  const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
     const unsigned peers = __match_any_sync(0xffffffffu, gcell[k]);
-    if (gcell[k] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicMin(first + gcell[k], tile0 + k * kVcThreads + (int)threadIdx.x);
+    if (gcell[k] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
+      red_min_l2hint_i32(first + gcell[k], tile0 + k * kVcThreads + (int)threadIdx.x, pol);
   }
 }
 
@@ -325,8 +330,9 @@ static __global__ void __launch_bounds__(kScanThreads)
 vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                 int32_t *first, int32_t *__restrict__ cell_of_vid,
                 int max_voxels, uint32_t *__restrict__ totals, unsigned long long *status, unsigned int *tickets,
-                int tiles_per_sample) {
+                int tiles_per_sample, int l2_hints) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
+  const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   __shared__ uint32_t s_tile, s_prefix;
   const int b = blockIdx.y;
   const int begin = offsets[b], n = offsets[b + 1] - begin;
@@ -356,7 +362,7 @@ vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__
     const int idx = warp_base + r * 128 + lane * 4;
     uint32_t f[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) f[k] = (gcs[r][k] >= 0 && first[gcs[r][k]] == begin + idx + k) ? 1u : 0u;
+    for (int k = 0; k < 4; ++k) f[k] = (gcs[r][k] >= 0 && ld_l2hint_i32(first + gcs[r][k], pol) == begin + idx + k) ? 1u : 0u;
     v[r] = make_uint4(f[0], f[1], f[2], f[3]);
     const uint32_t s = f[0] + f[1] + f[2] + f[3];
     uint32_t incl = s;
@@ -421,7 +427,7 @@ vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (fl[k]) {                                        // a creating point: o[k] is its cell's voxel number
-        first[gcs[r][k]] = ~(int32_t)o[k];                // (readers compare with their own index: either value differs)
+        st_l2hint_i32(first + gcs[r][k], ~(int32_t)o[k], pol);   // (readers compare with their own index: either value differs)
         if (o[k] < (uint32_t)max_voxels) cell_of_vid[(int64_t)b * max_voxels + o[k]] = gcs[r][k];
       }
     }
@@ -475,7 +481,9 @@ __global__ void __launch_bounds__(256)
 vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                  const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base, int max_voxels,
                  int max_points, int32_t *__restrict__ lists, uint32_t *__restrict__ arrivals,
-                 int2 *__restrict__ overflow, uint32_t *__restrict__ num_overflow) {
+                 int2 *__restrict__ overflow, uint32_t *__restrict__ num_overflow, int l2_hints) {
+  const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+  const uint64_t pol_lists = (l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
   const int b = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
   const int i0 = begin + blockIdx.x * (256 * kVcPer) + threadIdx.x;
@@ -489,16 +497,16 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
   for (int k = 0; k < kVcPer; ++k) gc[k] = i0 + 256 * k < end ? point_gcell[i0 + 256 * k] : -1;
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
-    const int vid = gc[k] >= 0 ? ~vid_of_cell[gc[k]] : max_voxels;
+    const int vid = gc[k] >= 0 ? ~ld_l2hint_i32(vid_of_cell + gc[k], pol) : max_voxels;
     row[k] = vid < max_voxels ? base + vid : -1;                 // (voxel cap: the whole cell is dropped)
   }
 #pragma unroll
-  for (int k = 0; k < kVcPer; ++k) pos[k] = row[k] >= 0 ? atomicAdd(arrivals + row[k], 1u) : 0u;
+  for (int k = 0; k < kVcPer; ++k) pos[k] = row[k] >= 0 ? atom_add_l2hint_u32(arrivals + row[k], 1u, pol_lists) : 0u;
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
     const int w = kVoxIdxBias - (i0 + 256 * k);
     const bool over = row[k] >= 0 && pos[k] >= (uint32_t)max_points;
-    if (row[k] >= 0 && !over) lists[(int64_t)row[k] * LS + pos[k]] = w;
+    if (row[k] >= 0 && !over) st_l2hint_i32(lists + (int64_t)row[k] * LS + pos[k], w, pol_lists);
     const unsigned bal = __ballot_sync(0xffffffffu, over);
     if (bal) {
       uint32_t at = 0;
@@ -509,18 +517,11 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
   }
 }
 
-// slot holding the row's smallest word (= latest point); rows here are full (no empty slots)
+// word of slot t of a row held as LQ quads (t a compile-time constant after unrolling)
 template <int LQ>
-__device__ __forceinline__ int vox_pick_victim(const int4 (&q)[LQ], int max_points, int &minw) {
-  int mw = 0x7fffffff, ms = 0;
-#pragma unroll
-  for (int t = 0; t < 4 * LQ; ++t) {
-    const int4 qq = q[t >> 2];
-    const int w = (t & 3) == 0 ? qq.x : (t & 3) == 1 ? qq.y : (t & 3) == 2 ? qq.z : qq.w;
-    if (t < max_points && w < mw) { mw = w; ms = t; }
-  }
-  minw = mw;
-  return ms;
+__device__ __forceinline__ int vox_quad_word(const int4 (&q)[LQ], int t) {
+  const int4 qq = q[t >> 2];
+  return (t & 3) == 0 ? qq.x : (t & 3) == 1 ? qq.y : (t & 3) == 2 ? qq.z : qq.w;
 }
 
 template <int LQ>                                        // row = 4 * LQ words (max_points <= 16); LQ = 0: any length
@@ -532,15 +533,57 @@ vox_evict_kernel(const int2 *__restrict__ overflow, const uint32_t *__restrict__
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     const int2 ent = overflow[e];
     int *row = lists + (int64_t)ent.x * LS;
-    const int w = ent.y;
-    while (true) {
-      int mw = 0x7fffffff, ms = 0;
-      if constexpr (LQ > 0) {
+    int w = ent.y;
+    if constexpr (LQ > 0) {
+      // The victim is the slot holding the LATEST point (then the displaced point is later than the 14 others and the
+      // new one: dropped at once).  On a near-range row hundreds of entries race for that one slot and every swap sends
+      // all the others back to re-read the row: the rounds, not the work, were this kernel's time.  An entry that lost
+      // a race therefore picks a pseudo-random slot among those holding later points and CARRIES the point it displaces
+      // (which may still belong to the result) as its new candidate.  Invariant: row + candidates in flight contain the
+      // max_points earliest points; slot words only grow, so a candidate that finds every slot earlier than itself can
+      // never enter and is dropped.  Every swap raises the sum of the row's words: the loop ends.
+      bool spread = false;
+      uint32_t rnd = e * 2654435761u + 12345u;
+      while (true) {
         int4 q[LQ];
 #pragma unroll
         for (int j = 0; j < LQ; ++j) q[j] = ld_cg_i4(row + 4 * j);
-        ms = vox_pick_victim<LQ>(q, max_points, mw);
-      } else {
+        int mw = 0x7fffffff, ms = 0, later = 0;
+#pragma unroll
+        for (int t = 0; t < 4 * LQ; ++t) {
+          const int ww = vox_quad_word<LQ>(q, t);
+          if (t < max_points) {
+            later += ww < w;
+            if (ww < mw) { mw = ww; ms = t; }
+          }
+        }
+        if (later == 0) break;                              // the row is full of earlier points
+        bool is_min = true;
+        if (spread && later > 1) {
+          rnd = rnd * 1664525u + 1013904223u;
+          const int pick = (int)((rnd >> 16) % (uint32_t)later);
+          const int min_slot = ms;
+          int seen = 0;
+#pragma unroll
+          for (int t = 0; t < 4 * LQ; ++t) {
+            const int ww = vox_quad_word<LQ>(q, t);
+            if (t < max_points && ww < w) {
+              if (seen == pick) { mw = ww; ms = t; }
+              ++seen;
+            }
+          }
+          is_min = ms == min_slot;
+        }
+        if (atomicCAS(row + ms, mw, w) == mw) {
+          if (is_min) break;                                // (others only grew since the read: it still was the minimum)
+          w = mw;                                           // carry the displaced point
+        } else {
+          spread = true;
+        }
+      }
+    } else {
+      while (true) {
+        int mw = 0x7fffffff, ms = 0;
         for (int t4 = 0; t4 < LS; t4 += 4) {
           const int4 qq = ld_cg_i4(row + t4);
           const int ww[4] = {qq.x, qq.y, qq.z, qq.w};
@@ -548,9 +591,9 @@ vox_evict_kernel(const int2 *__restrict__ overflow, const uint32_t *__restrict__
           for (int j = 0; j < 4; ++j)
             if (t4 + j < max_points && ww[j] < mw) { mw = ww[j]; ms = t4 + j; }
         }
+        if (w < mw) break;                                  // the row is full of earlier points
+        if (atomicCAS(row + ms, mw, w) == mw) break;
       }
-      if (w < mw) break;                                  // the row is full of earlier points
-      if (atomicCAS(row + ms, mw, w) == mw) break;
     }
   }
 }
@@ -584,6 +627,9 @@ __device__ __forceinline__ void vox_sort16_desc(int (&w)[16]) {
 // exactly once, coalesced (no memset of the 93 %-padding tensor, no 20-byte scattered stores).  Rows beyond the voxel
 // count are written as zeros with num_points = 0.
 constexpr int kFinWarps = 4;
+__host__ __device__ inline size_t vox_fin_coop_warp_bytes(int max_points, int F) {   // tile + words + pair map + row sources
+  return (size_t)128 * max_points * F + 2048 + 1024 + 256;
+}
 template <int FM>                                       // FM >= F: bound of the per-point register arrays (8 or 16)
 __global__ void __launch_bounds__(kFinWarps * 32)
 vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
@@ -704,6 +750,139 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
   for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
 }
 
+// Rows of at most 16 slots (every pillar / voxel configuration of the reference): the same output, but the gather is
+// shared by the warp.  With one lane walking its own row the warp runs as long as its fullest row (13 % of the rows of a
+// long-range sweep are full, so practically every warp went through all max_points slots) while the mean row holds 1.7
+// points -- 8.6x more gather rounds than points.  Here a lane only reads, masks and sorts its row's words; the warp then
+// lists its (row, slot) pairs behind an exclusive scan of the counts and lane p fetches pair p: every point row of the
+// 32 voxels is in flight at once (two rounds for a typical warp), and nobody idles behind a full row.  The mean is summed
+// by the row's lane from the shared-memory tile in slot order (bit-identical to the serial sum).
+template <int FM>
+__global__ void __launch_bounds__(kFinWarps * 32)
+vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
+                         const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists,
+                         const uint32_t *__restrict__ arrivals, int batch, int max_voxels, int max_points,
+                         float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
+                         const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
+                         float *__restrict__ canvas) {
+  extern __shared__ __align__(128) unsigned char s_finc[];
+  const int TF = max_points * F;
+  const size_t warp_bytes = vox_fin_coop_warp_bytes(max_points, F);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wb = s_finc + (size_t)warp * warp_bytes;
+  float *tile = reinterpret_cast<float *>(wb);                                         // [32][TF]
+  int (*s_words)[16] = reinterpret_cast<int (*)[16]>(wb + (size_t)128 * TF);           // sorted slot words of the 32 rows
+  uint16_t *s_map = reinterpret_cast<uint16_t *>(wb + (size_t)128 * TF + 2048);        // pair p -> row * 16 + slot
+  const float **s_src = reinterpret_cast<const float **>(wb + (size_t)128 * TF + 3072); // row -> address of point 0 of its cloud
+  int *s_vb = reinterpret_cast<int *>(s_finc + (size_t)kFinWarps * warp_bytes);
+  for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
+  for (int e = lane; e < 32 * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int64_t total_rows = (int64_t)batch * max_voxels;
+  const int64_t row0 = ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
+  if (row0 >= total_rows) return;
+  const int64_t row = row0 + lane;
+  int cnt = 0, b = 0, x = 0, y = 0, z = 0;
+  int words[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) words[t] = 0;
+  if (row < total_rows && row < s_vb[batch]) {
+    int lo = 0, hi = batch;                               // sample b: s_vb[b] <= row < s_vb[b + 1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_vb[mid] <= row) lo = mid; else hi = mid;
+    }
+    b = lo;
+    const int LS = vox_list_stride(max_points);
+    const int4 *list = reinterpret_cast<const int4 *>(lists + row * LS);
+    const int filled = (int)min(arrivals[row], (uint32_t)max_points);
+    const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
+#pragma unroll
+    for (int t4 = 0; t4 < 4; ++t4) {
+      if (4 * t4 < LS) {
+        const int4 w4 = ldg_stream_i4(list + t4);          // (last use of the row)
+        words[4 * t4 + 0] = w4.x; words[4 * t4 + 1] = w4.y; words[4 * t4 + 2] = w4.z; words[4 * t4 + 3] = w4.w;
+      }
+    }
+    // the claim kernels leave an unsorted set in the first `filled` slots (the rest was never written):
+    // descending words = ascending point index, empty slots (0) last
+#pragma unroll
+    for (int t = 0; t < 16; ++t) words[t] = t < filled ? words[t] : 0;
+    cnt = filled;
+    const int64_t c = (int64_t)gc - (int64_t)b * cells;
+    x = (int)(c % g.gx); y = (int)((c / g.gx) % g.gy); z = (int)(c / ((int64_t)g.gx * g.gy));
+    reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
+    const int begin = offsets[b];
+    s_src[lane] = pts.per_sample ? pts.per_sample[b] - (int64_t)begin * F : pts.cat;
+  }
+  if (__any_sync(0xffffffffu, cnt > 1)) vox_sort16_desc(words);
+  if (row < total_rows) num_points[row] = cnt;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+#pragma unroll
+  for (int t4 = 0; t4 < 4; ++t4)
+    *reinterpret_cast<int4 *>(&s_words[lane][4 * t4]) = make_int4(words[4 * t4], words[4 * t4 + 1], words[4 * t4 + 2], words[4 * t4 + 3]);
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+    if (t < cnt) s_map[off + t] = (uint16_t)(lane * 16 + t);
+  __syncwarp();
+  for (int p0 = 0; p0 < total; p0 += 64) {                 // two point rows per lane in flight
+    float val[2][FM];
+    int dst[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int p = p0 + 32 * j + lane;
+      dst[j] = -1;
+      if (p < total) {
+        const int m = s_map[p], r = m >> 4, t = m & 15;
+        const float *src = s_src[r] + (int64_t)(kVoxIdxBias - s_words[r][t]) * F;
+#pragma unroll
+        for (int k = 0; k < FM; ++k)
+          if (k < F) val[j][k] = __ldg(src + k);
+        dst[j] = r * TF + t * F;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (dst[j] >= 0) {
+#pragma unroll
+        for (int k = 0; k < FM; ++k)
+          if (k < F) tile[dst[j] + k] = val[j][k];
+      }
+    }
+  }
+  __syncwarp();
+  if (cnt > 0 && (voxel_mean || canvas)) {
+    float sum[FM];
+#pragma unroll
+    for (int k = 0; k < FM; ++k) sum[k] = 0.f;
+    const float *trow = tile + (size_t)lane * TF;
+    for (int t = 0; t < cnt; ++t) {
+#pragma unroll
+      for (int k = 0; k < FM; ++k)
+        if (k < mean_features) sum[k] += trow[t * F + k];
+    }
+#pragma unroll
+    for (int k = 0; k < FM; ++k) {
+      if (k >= mean_features) break;
+      const float m = sum[k] / (float)cnt;
+      if (voxel_mean) voxel_mean[row * mean_features + k] = m;
+      if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
+    }
+  }
+  // the warp's 32 rows are one contiguous span of the output
+  const int64_t nrows = min((int64_t)32, total_rows - row0);
+  float *out = voxels + row0 * TF;
+  const int n4 = (int)(nrows * TF / 4);                    // row0 * TF * 4 bytes is a multiple of 16 (row0 % 32 == 0)
+  for (int e = lane; e < n4; e += 32) stg_stream_f4(reinterpret_cast<float4 *>(out) + e, reinterpret_cast<const float4 *>(tile)[e]);
+  for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
+}
+
 // pillar scatter for UNIQUE coordinates (what hard voxelization produces): canvas pre-zeroed, one thread per element
 template <typename T>
 __global__ void scatter_unique_kernel(const T *__restrict__ feats, const int32_t *__restrict__ coors, int64_t M, int C,
@@ -808,6 +987,15 @@ extern "C" int bevvox_temp_bytes(int batch, int64_t total_points, const int *gri
   return BEVPOOL_OK;
 }
 
+// bit 0: first-point / voxel-number table evict_last, bit 1: slot lists + arrival counters evict_last, bit 2: point stream
+// evict_first (BEVVOX_L2_HINTS, read once; default below)
+static int vox_l2_hints() {
+  static const int v = [] {
+    const char *e = std::getenv("BEVVOX_L2_HINTS");
+    return e && e[0] ? std::atoi(e) : 5;
+  }();
+  return v;
+}
 static bool vox_overlap_enabled() {
   static const bool on = [] {
     const char *e = std::getenv("BEVVOX_CANVAS_OVERLAP");
@@ -873,13 +1061,13 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   const dim3 pgrid((unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer), (unsigned)batch);
   if (total_points > 0) {
     vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(pts, sample_offsets, F, g,
-                                                                                                 cells, first, gcell);
+                                                                                                 cells, first, gcell, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
   }
   vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(
       sample_offsets, gcell, first, cell_of_vid, max_voxels, totals,
       reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
-      L.tiles_per_sample);
+      L.tiles_per_sample, vox_l2_hints());
   BEVPOOL_LAUNCH_CHECK();
   vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, batch, max_voxels, voxel_base);
   BEVPOOL_LAUNCH_CHECK();
@@ -888,7 +1076,7 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     int2 *overflow = reinterpret_cast<int2 *>(tb + L.off_overflow);
     uint32_t *num_overflow = reinterpret_cast<uint32_t *>(tb + L.off_num_overflow);
     vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
-                                                arrivals, overflow, num_overflow);
+                                                arrivals, overflow, num_overflow, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
     const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div64(total_points, 256), (int64_t)kSMs * 8);
     switch (max_points <= 16 ? vox_list_stride(max_points) / 4 : 0) {
@@ -900,28 +1088,32 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     }
     BEVPOOL_LAUNCH_CHECK();
   }
-  const size_t fin_smem = (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
+  const bool coop = max_points <= 16;
+  const size_t fin_smem = coop ? (size_t)kFinWarps * vox_fin_coop_warp_bytes(max_points, F) + (size_t)(batch + 1) * sizeof(int)
+                               : (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
   if (fin_smem > 200 * 1024) return BEVPOOL_E_RANGE;       // max_points * F beyond ~390 floats: not a pillar configuration
   if (ev_join) {
     BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     cudaEventDestroy(ev_join);
   }
   const unsigned fin_grid = (unsigned)ceil_div64((int64_t)rows, kFinWarps * 32);
-  if (F <= 8) {
-    if (fin_smem > 48 * 1024)
-      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    vox_finalize_kernel<8><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
-        pts, sample_offsets, F, g, cells, cell_of_vid, lists, reinterpret_cast<const uint32_t *>(tb + L.off_arrivals), batch, max_voxels,
-        max_points, voxels, num_points, coors, voxel_base,
-        voxel_mean, mean_features, canvas);
+#define BEVVOX_FIN_ARGS pts, sample_offsets, F, g, cells, cell_of_vid, lists, reinterpret_cast<const uint32_t *>(tb + L.off_arrivals), batch, \
+                        max_voxels, max_points, voxels, num_points, coors, voxel_base, voxel_mean, mean_features, canvas
+#define BEVVOX_FIN_LAUNCH(KERNEL)                                                                                          \
+  do {                                                                                                                     \
+    if (fin_smem > 48 * 1024)                                                                                              \
+      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));    \
+    KERNEL<<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(BEVVOX_FIN_ARGS);                                               \
+  } while (0)
+  if (coop) {
+    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<8>);
+    else BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<16>);
   } else {
-    if (fin_smem > 48 * 1024)
-      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    vox_finalize_kernel<16><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
-        pts, sample_offsets, F, g, cells, cell_of_vid, lists, reinterpret_cast<const uint32_t *>(tb + L.off_arrivals), batch, max_voxels,
-        max_points, voxels, num_points, coors, voxel_base,
-        voxel_mean, mean_features, canvas);
+    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>);
+    else BEVVOX_FIN_LAUNCH(vox_finalize_kernel<16>);
   }
+#undef BEVVOX_FIN_LAUNCH
+#undef BEVVOX_FIN_ARGS
   BEVPOOL_LAUNCH_CHECK();
   return BEVPOOL_OK;
 }
