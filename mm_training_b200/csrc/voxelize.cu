@@ -271,10 +271,10 @@ struct VoxPoints {                                   // point i of sample b (i g
 constexpr int kVcPer = 4;                          // points per thread: independent chains in flight, 4x fewer CTAs
 __global__ void __launch_bounds__(kVcThreads)
 vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
-                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell, int l2_hints) {
+                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell, int l2_hints, int b0) {
   extern __shared__ __align__(16) float s_pts[];   // kVcPer * kVcThreads * F floats
   __shared__ __align__(8) uint64_t s_bar;
-  const int b = blockIdx.y;
+  const int b = b0 + blockIdx.y;                   // (the batch may be processed in groups of samples: b0 = first of the group)
   const int begin = offsets[b], end = offsets[b + 1];
   const int tile0 = begin + blockIdx.x * (kVcThreads * kVcPer);
   if (tile0 >= end) return;
@@ -330,11 +330,11 @@ static __global__ void __launch_bounds__(kScanThreads)
 vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                 int32_t *first, int32_t *__restrict__ cell_of_vid,
                 int max_voxels, uint32_t *__restrict__ totals, unsigned long long *status, unsigned int *tickets,
-                int tiles_per_sample, int l2_hints) {
+                int tiles_per_sample, int l2_hints, int b0) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   __shared__ uint32_t s_tile, s_prefix;
-  const int b = blockIdx.y;
+  const int b = b0 + blockIdx.y;
   const int begin = offsets[b], n = offsets[b + 1] - begin;
   if (n == 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) totals[b] = 0u;
@@ -481,13 +481,17 @@ __global__ void __launch_bounds__(256)
 vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                  const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base, int max_voxels,
                  int max_points, int32_t *__restrict__ lists, uint32_t *__restrict__ arrivals,
-                 int2 *__restrict__ overflow, uint32_t *__restrict__ num_overflow, int l2_hints) {
+                 int2 *__restrict__ overflow, uint32_t *__restrict__ tile_overflow, int tiles_cap, int l2_hints, int b0) {
+  __shared__ uint32_t s_over;                                     // overflow entries of this tile so far
   const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   const uint64_t pol_lists = (l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
-  const int b = blockIdx.y;
+  const int b = b0 + blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
-  const int i0 = begin + blockIdx.x * (256 * kVcPer) + threadIdx.x;
-  if (i0 - (int)threadIdx.x >= end) return;
+  const int tile0 = begin + blockIdx.x * (256 * kVcPer);
+  if (tile0 >= end) return;
+  const int i0 = tile0 + threadIdx.x;
+  if (threadIdx.x == 0) s_over = 0u;
+  __syncthreads();
   const int base = voxel_base[b];
   const int LS = vox_list_stride(max_points);
   const int lane = threadIdx.x & 31;
@@ -502,6 +506,9 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
   }
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) pos[k] = row[k] >= 0 ? atom_add_l2hint_u32(arrivals + row[k], 1u, pol_lists) : 0u;
+  // Late arrivals go to the TILE's segment of the overflow list (the tile's own points bound its length): positions come
+  // from a shared-memory counter.  One global counter for the whole batch -- the first version -- made every second warp
+  // wait for the return value of an atomic on a single address (75 % of this kernel's stall samples).
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
     const int w = kVoxIdxBias - (i0 + 256 * k);
@@ -510,11 +517,13 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
     const unsigned bal = __ballot_sync(0xffffffffu, over);
     if (bal) {
       uint32_t at = 0;
-      if (lane == __ffs(bal) - 1) at = atomicAdd(num_overflow, (uint32_t)__popc(bal));
+      if (lane == __ffs(bal) - 1) at = atomicAdd(&s_over, (uint32_t)__popc(bal));
       at = __shfl_sync(0xffffffffu, at, __ffs(bal) - 1);
-      if (over) overflow[at + __popc(bal & ((1u << lane) - 1u))] = make_int2(row[k], w);
+      if (over) overflow[(int64_t)tile0 + at + __popc(bal & ((1u << lane) - 1u))] = make_int2(row[k], w);
     }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) tile_overflow[(int64_t)b * tiles_cap + blockIdx.x] = s_over;
 }
 
 // word of slot t of a row held as LQ quads (t a compile-time constant after unrolling)
@@ -525,12 +534,18 @@ __device__ __forceinline__ int vox_quad_word(const int4 (&q)[LQ], int t) {
 }
 
 template <int LQ>                                        // row = 4 * LQ words (max_points <= 16); LQ = 0: any length
-__global__ void __launch_bounds__(256)
-vox_evict_kernel(const int2 *__restrict__ overflow, const uint32_t *__restrict__ num_overflow, int max_points,
-                 int32_t *__restrict__ lists) {
-  const uint32_t n = *num_overflow;
+__global__ void __launch_bounds__(128)
+vox_evict_kernel(const int32_t *__restrict__ offsets, const int2 *__restrict__ overflow_all,
+                 const uint32_t *__restrict__ tile_overflow, int tiles_cap, int max_points, int32_t *__restrict__ lists) {
+  // one CTA per tile of the claim kernel: its overflow entries sit at the tile's first point index
+  const int b = blockIdx.y;
+  const int begin = offsets[b], end = offsets[b + 1];
+  const int tile0 = begin + blockIdx.x * (256 * kVcPer);
+  if (tile0 >= end) return;
+  const uint32_t n = tile_overflow[(int64_t)b * tiles_cap + blockIdx.x];
+  const int2 *overflow = overflow_all + tile0;
   const int LS = vox_list_stride(max_points);
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     const int2 ent = overflow[e];
     int *row = lists + (int64_t)ent.x * LS;
     int w = ent.y;
@@ -543,7 +558,7 @@ vox_evict_kernel(const int2 *__restrict__ overflow, const uint32_t *__restrict__
       // max_points earliest points; slot words only grow, so a candidate that finds every slot earlier than itself can
       // never enter and is dropped.  Every swap raises the sum of the row's words: the loop ends.
       bool spread = false;
-      uint32_t rnd = e * 2654435761u + 12345u;
+      uint32_t rnd = ((uint32_t)tile0 + e) * 2654435761u + 12345u;
       while (true) {
         int4 q[LQ];
 #pragma unroll
@@ -627,9 +642,6 @@ __device__ __forceinline__ void vox_sort16_desc(int (&w)[16]) {
 // exactly once, coalesced (no memset of the 93 %-padding tensor, no 20-byte scattered stores).  Rows beyond the voxel
 // count are written as zeros with num_points = 0.
 constexpr int kFinWarps = 4;
-__host__ __device__ inline size_t vox_fin_coop_warp_bytes(int max_points, int F) {   // tile + words + pair map + row sources
-  return (size_t)128 * max_points * F + 2048 + 1024 + 256;
-}
 template <int FM>                                       // FM >= F: bound of the per-point register arrays (8 or 16)
 __global__ void __launch_bounds__(kFinWarps * 32)
 vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
@@ -750,137 +762,38 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
   for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
 }
 
-// Rows of at most 16 slots (every pillar / voxel configuration of the reference): the same output, but the gather is
-// shared by the warp.  With one lane walking its own row the warp runs as long as its fullest row (13 % of the rows of a
-// long-range sweep are full, so practically every warp went through all max_points slots) while the mean row holds 1.7
-// points -- 8.6x more gather rounds than points.  Here a lane only reads, masks and sorts its row's words; the warp then
-// lists its (row, slot) pairs behind an exclusive scan of the counts and lane p fetches pair p: every point row of the
-// 32 voxels is in flight at once (two rounds for a typical warp), and nobody idles behind a full row.  The mean is summed
-// by the row's lane from the shared-memory tile in slot order (bit-identical to the serial sum).
+// Dense canvas of the fused HardSimpleVFE mean, written ONCE and in order: a thread owns 4 consecutive cells, reads their
+// entries of the voxel-number table (16 bytes), fetches the mean row of the occupied ones (5 % of the cells of a
+// long-range sweep) and writes mean_features coalesced 16-byte streaming stores.  This replaces a DRAM-speed zero fill of
+// the canvas plus mean_features scattered 4-byte stores per voxel from the finalize kernel -- each of those a
+// read-modify-write of a 32-byte sector at a random address, 40 % of that kernel's sector traffic -- by one sequential
+// read of the table.
 template <int FM>
-__global__ void __launch_bounds__(kFinWarps * 32)
-vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
-                         const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists,
-                         const uint32_t *__restrict__ arrivals, int batch, int max_voxels, int max_points,
-                         float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
-                         const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
-                         float *__restrict__ canvas) {
-  extern __shared__ __align__(128) unsigned char s_finc[];
-  const int TF = max_points * F;
-  const size_t warp_bytes = vox_fin_coop_warp_bytes(max_points, F);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wb = s_finc + (size_t)warp * warp_bytes;
-  float *tile = reinterpret_cast<float *>(wb);                                         // [32][TF]
-  int (*s_words)[16] = reinterpret_cast<int (*)[16]>(wb + (size_t)128 * TF);           // sorted slot words of the 32 rows
-  uint16_t *s_map = reinterpret_cast<uint16_t *>(wb + (size_t)128 * TF + 2048);        // pair p -> row * 16 + slot
-  const float **s_src = reinterpret_cast<const float **>(wb + (size_t)128 * TF + 3072); // row -> address of point 0 of its cloud
-  int *s_vb = reinterpret_cast<int *>(s_finc + (size_t)kFinWarps * warp_bytes);
-  for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
-  for (int e = lane; e < 32 * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  const int64_t total_rows = (int64_t)batch * max_voxels;
-  const int64_t row0 = ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
-  if (row0 >= total_rows) return;
-  const int64_t row = row0 + lane;
-  int cnt = 0, b = 0, x = 0, y = 0, z = 0;
-  int words[16];
+__global__ void __launch_bounds__(256)
+vox_canvas_dense_kernel(const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base,
+                        const float *__restrict__ voxel_mean, int mean_features, int max_voxels, int64_t cells,
+                        float *__restrict__ canvas) {
+  const int b = blockIdx.y;
+  const int64_t c4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c4 >= cells) return;
+  const int4 e4 = ldg_stream_i4(reinterpret_cast<const int4 *>(vid_of_cell + (int64_t)b * cells + c4));
+  const int e[4] = {e4.x, e4.y, e4.z, e4.w};
+  const int base = voxel_base[b];
+  float m[4][FM];
 #pragma unroll
-  for (int t = 0; t < 16; ++t) words[t] = 0;
-  if (row < total_rows && row < s_vb[batch]) {
-    int lo = 0, hi = batch;                               // sample b: s_vb[b] <= row < s_vb[b + 1]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_vb[mid] <= row) lo = mid; else hi = mid;
-    }
-    b = lo;
-    const int LS = vox_list_stride(max_points);
-    const int4 *list = reinterpret_cast<const int4 *>(lists + row * LS);
-    const int filled = (int)min(arrivals[row], (uint32_t)max_points);
-    const int gc = cell_of_vid[(int64_t)b * max_voxels + (row - s_vb[b])];
+  for (int j = 0; j < 4; ++j) {
+    const int vid = e[j] < 0 ? ~e[j] : max_voxels;           // (empty cells hold 0x7f7f7f7f; cells beyond the cap are dropped)
+    const bool ok = vid < max_voxels;
+    const float *src = voxel_mean + (int64_t)(base + (ok ? vid : 0)) * mean_features;
 #pragma unroll
-    for (int t4 = 0; t4 < 4; ++t4) {
-      if (4 * t4 < LS) {
-        const int4 w4 = ldg_stream_i4(list + t4);          // (last use of the row)
-        words[4 * t4 + 0] = w4.x; words[4 * t4 + 1] = w4.y; words[4 * t4 + 2] = w4.z; words[4 * t4 + 3] = w4.w;
-      }
-    }
-    // the claim kernels leave an unsorted set in the first `filled` slots (the rest was never written):
-    // descending words = ascending point index, empty slots (0) last
-#pragma unroll
-    for (int t = 0; t < 16; ++t) words[t] = t < filled ? words[t] : 0;
-    cnt = filled;
-    const int64_t c = (int64_t)gc - (int64_t)b * cells;
-    x = (int)(c % g.gx); y = (int)((c / g.gx) % g.gy); z = (int)(c / ((int64_t)g.gx * g.gy));
-    reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
-    const int begin = offsets[b];
-    s_src[lane] = pts.per_sample ? pts.per_sample[b] - (int64_t)begin * F : pts.cat;
+    for (int k = 0; k < FM; ++k) m[j][k] = (ok && k < mean_features) ? __ldg(src + k) : 0.f;
   }
-  if (__any_sync(0xffffffffu, cnt > 1)) vox_sort16_desc(words);
-  if (row < total_rows) num_points[row] = cnt;
-  int incl = cnt;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
+  for (int k = 0; k < FM; ++k) {
+    if (k >= mean_features) break;
+    stg_stream_f4(reinterpret_cast<float4 *>(canvas + ((int64_t)b * mean_features + k) * cells + c4),
+                  make_float4(m[0][k], m[1][k], m[2][k], m[3][k]));
   }
-  const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
-#pragma unroll
-  for (int t4 = 0; t4 < 4; ++t4)
-    *reinterpret_cast<int4 *>(&s_words[lane][4 * t4]) = make_int4(words[4 * t4], words[4 * t4 + 1], words[4 * t4 + 2], words[4 * t4 + 3]);
-#pragma unroll
-  for (int t = 0; t < 16; ++t)
-    if (t < cnt) s_map[off + t] = (uint16_t)(lane * 16 + t);
-  __syncwarp();
-  for (int p0 = 0; p0 < total; p0 += 64) {                 // two point rows per lane in flight
-    float val[2][FM];
-    int dst[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int p = p0 + 32 * j + lane;
-      dst[j] = -1;
-      if (p < total) {
-        const int m = s_map[p], r = m >> 4, t = m & 15;
-        const float *src = s_src[r] + (int64_t)(kVoxIdxBias - s_words[r][t]) * F;
-#pragma unroll
-        for (int k = 0; k < FM; ++k)
-          if (k < F) val[j][k] = __ldg(src + k);
-        dst[j] = r * TF + t * F;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (dst[j] >= 0) {
-#pragma unroll
-        for (int k = 0; k < FM; ++k)
-          if (k < F) tile[dst[j] + k] = val[j][k];
-      }
-    }
-  }
-  __syncwarp();
-  if (cnt > 0 && (voxel_mean || canvas)) {
-    float sum[FM];
-#pragma unroll
-    for (int k = 0; k < FM; ++k) sum[k] = 0.f;
-    const float *trow = tile + (size_t)lane * TF;
-    for (int t = 0; t < cnt; ++t) {
-#pragma unroll
-      for (int k = 0; k < FM; ++k)
-        if (k < mean_features) sum[k] += trow[t * F + k];
-    }
-#pragma unroll
-    for (int k = 0; k < FM; ++k) {
-      if (k >= mean_features) break;
-      const float m = sum[k] / (float)cnt;
-      if (voxel_mean) voxel_mean[row * mean_features + k] = m;
-      if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
-    }
-  }
-  // the warp's 32 rows are one contiguous span of the output
-  const int64_t nrows = min((int64_t)32, total_rows - row0);
-  float *out = voxels + row0 * TF;
-  const int n4 = (int)(nrows * TF / 4);                    // row0 * TF * 4 bytes is a multiple of 16 (row0 % 32 == 0)
-  for (int e = lane; e < n4; e += 32) stg_stream_f4(reinterpret_cast<float4 *>(out) + e, reinterpret_cast<const float4 *>(tile)[e]);
-  for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
 }
 
 // pillar scatter for UNIQUE coordinates (what hard voxelization produces): canvas pre-zeroed, one thread per element
@@ -926,7 +839,9 @@ static VoxTemp vox_temp_layout(int batch, int64_t total_points, int max_voxels, 
 
 // dense mode: first-point table + voxel-number table over all cells of the batch (int32 each), point -> global cell ids
 struct VoxDenseTemp {
-  size_t off_status, off_tickets, off_arrivals, off_num_overflow, zero_bytes;   // [0, zero_bytes) memset 0 (scan status words, tickets, arrival counters)
+  size_t off_status, off_tickets, off_arrivals, zero_bytes;   // [0, zero_bytes) memset 0 (scan status words, tickets, arrival counters)
+  size_t off_tile_overflow;                     // per (sample, claim tile) overflow counts (written by every live tile)
+  int tiles_cap;
   size_t off_lists, off_overflow;
   size_t off_first, first_bytes;                // memset 0x7f
   size_t off_gcell, off_cell_of_vid, off_totals, bytes;
@@ -947,8 +862,9 @@ static VoxDenseTemp vox_dense_layout(int batch, int64_t total_points, int max_vo
   L.off_status = o;  o = align_up(o + (size_t)batch * L.tiles_per_sample * 8, 256);
   L.off_tickets = o; o = align_up(o + (size_t)batch * 4, 256);
   L.off_arrivals = o; o = align_up(o + (size_t)batch * max_voxels * 4, 256);
-  L.off_num_overflow = o; o += 256;
   L.zero_bytes = o;
+  L.tiles_cap = (int)ceil_div64(total_points > 0 ? total_points : 1, kVcThreads * kVcPer);   // (bounds every sample's tile count)
+  L.off_tile_overflow = o; o = align_up(o + (size_t)batch * L.tiles_cap * 4, 256);
   L.off_lists = o;   o = align_up(o + (size_t)batch * max_voxels * vox_list_stride(max_points) * 4, 256);   // (never read beyond a row's arrival count)
   L.off_overflow = o; o = align_up(o + (size_t)total_points * 8, 256);
   L.off_first = o;  L.first_bytes = align_up((size_t)batch * cells * 4, 256); o += L.first_bytes;
@@ -996,6 +912,14 @@ static int vox_l2_hints() {
   }();
   return v;
 }
+// samples per group of the dense pipeline: BEVVOX_GROUP (default 0 = the whole batch at once)
+static int vox_group_samples(int batch) {
+  static const int env = [] {
+    const char *e = std::getenv("BEVVOX_GROUP");
+    return e && e[0] ? std::atoi(e) : 0;
+  }();
+  return env > 0 && env < batch ? env : batch;
+}
 static bool vox_overlap_enabled() {
   static const bool on = [] {
     const char *e = std::getenv("BEVVOX_CANVAS_OVERLAP");
@@ -1039,8 +963,12 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   // The canvas fill (335 MB per 32 sweeps of pure DRAM-write work) does not depend on anything the first four kernels do,
   // and those are latency bound: it runs on a side stream (fork here, join before the kernel that scatters into it).
   // Event fork / join is legal under stream capture; the side stream is created once per device.
+  // With a mean output to read from (and 16-byte aligned cell rows) the canvas is written densely by its own kernel after
+  // the finalize kernel; otherwise it is zero-filled here, on the side stream, and the finalize kernel scatters into it.
+  const bool dense_canvas = canvas && fill_canvas && voxel_mean && mean_features > 0 && (cells & 3) == 0 &&
+                            ((reinterpret_cast<uintptr_t>(canvas) | reinterpret_cast<uintptr_t>(first)) & 15u) == 0;
   cudaEvent_t ev_join = nullptr;
-  if (canvas && fill_canvas) {
+  if (canvas && fill_canvas && !dense_canvas) {
     const size_t cbytes = (size_t)batch * mean_features * g.gx * g.gy * g.gz * sizeof(float);
     cudaStream_t side = vox_overlap_enabled() ? vox_side_stream() : nullptr;
     if (side) {
@@ -1057,64 +985,79 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     }
   }
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, L.zero_bytes, stream));
-  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
-  const dim3 pgrid((unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer), (unsigned)batch);
-  if (total_points > 0) {
-    vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(pts, sample_offsets, F, g,
-                                                                                                 cells, first, gcell, vox_l2_hints());
+  // Groups of samples.  The first-point / voxel-number table (4 bytes per cell: 2 MB per sample of the aiMotive pillar grid)
+  // is visited at random by the cell, scan and claim kernels; at 32 sweeps it is 64 MB and every visit of the later kernels
+  // missed L2 (ncu: the claim kernel waits 130 cycles per issued instruction on 32-byte DRAM reads).  Running
+  // fill -> cell -> scan -> base -> claim per group of samples keeps a group's table in L2 from its fill to its last use.
+  const int group = vox_group_samples(batch);
+  uint32_t *arrivals = reinterpret_cast<uint32_t *>(tb + L.off_arrivals);
+  int2 *overflow = reinterpret_cast<int2 *>(tb + L.off_overflow);
+  uint32_t *tile_overflow = reinterpret_cast<uint32_t *>(tb + L.off_tile_overflow);
+  const unsigned ptiles = (unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer);
+  for (int b0 = 0; b0 < batch; b0 += group) {
+    const int nb = std::min(group, batch - b0);
+    BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first + (size_t)b0 * cells, 0x7f, (size_t)nb * cells * 4, stream));
+    const dim3 pgrid(ptiles, (unsigned)nb);
+    if (total_points > 0) {
+      vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(
+          pts, sample_offsets, F, g, cells, first, gcell, vox_l2_hints(), b0);
+      BEVPOOL_LAUNCH_CHECK();
+    }
+    vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)nb), kScanThreads, 0, stream>>>(
+        sample_offsets, gcell, first, cell_of_vid, max_voxels, totals,
+        reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
+        L.tiles_per_sample, vox_l2_hints(), b0);
     BEVPOOL_LAUNCH_CHECK();
+    vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, b0 + nb, max_voxels, voxel_base);   // (prefix over the samples so far)
+    BEVPOOL_LAUNCH_CHECK();
+    if (total_points > 0) {
+      vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
+                                                  arrivals, overflow, tile_overflow, L.tiles_cap, vox_l2_hints(), b0);
+      BEVPOOL_LAUNCH_CHECK();
+    }
   }
-  vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(
-      sample_offsets, gcell, first, cell_of_vid, max_voxels, totals,
-      reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
-      L.tiles_per_sample, vox_l2_hints());
-  BEVPOOL_LAUNCH_CHECK();
-  vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, batch, max_voxels, voxel_base);
-  BEVPOOL_LAUNCH_CHECK();
   if (total_points > 0) {
-    uint32_t *arrivals = reinterpret_cast<uint32_t *>(tb + L.off_arrivals);
-    int2 *overflow = reinterpret_cast<int2 *>(tb + L.off_overflow);
-    uint32_t *num_overflow = reinterpret_cast<uint32_t *>(tb + L.off_num_overflow);
-    vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
-                                                arrivals, overflow, num_overflow, vox_l2_hints());
-    BEVPOOL_LAUNCH_CHECK();
-    const unsigned egrid = (unsigned)std::min<int64_t>(ceil_div64(total_points, 256), (int64_t)kSMs * 8);
+    const dim3 egrid(ptiles, (unsigned)batch);
     switch (max_points <= 16 ? vox_list_stride(max_points) / 4 : 0) {
-      case 1: vox_evict_kernel<1><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
-      case 2: vox_evict_kernel<2><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
-      case 3: vox_evict_kernel<3><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
-      case 4: vox_evict_kernel<4><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
-      default: vox_evict_kernel<0><<<egrid, 256, 0, stream>>>(overflow, num_overflow, max_points, lists); break;
+      case 1: vox_evict_kernel<1><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
+      case 2: vox_evict_kernel<2><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
+      case 3: vox_evict_kernel<3><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
+      case 4: vox_evict_kernel<4><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
+      default: vox_evict_kernel<0><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
     }
     BEVPOOL_LAUNCH_CHECK();
   }
-  const bool coop = max_points <= 16;
-  const size_t fin_smem = coop ? (size_t)kFinWarps * vox_fin_coop_warp_bytes(max_points, F) + (size_t)(batch + 1) * sizeof(int)
-                               : (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
+  const size_t fin_smem = (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
   if (fin_smem > 200 * 1024) return BEVPOOL_E_RANGE;       // max_points * F beyond ~390 floats: not a pillar configuration
   if (ev_join) {
     BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     cudaEventDestroy(ev_join);
   }
-  const unsigned fin_grid = (unsigned)ceil_div64((int64_t)rows, kFinWarps * 32);
+  float *fin_canvas = dense_canvas ? nullptr : canvas;
 #define BEVVOX_FIN_ARGS pts, sample_offsets, F, g, cells, cell_of_vid, lists, reinterpret_cast<const uint32_t *>(tb + L.off_arrivals), batch, \
-                        max_voxels, max_points, voxels, num_points, coors, voxel_base, voxel_mean, mean_features, canvas
-#define BEVVOX_FIN_LAUNCH(KERNEL)                                                                                          \
+                        max_voxels, max_points, voxels, num_points, coors, voxel_base, voxel_mean, mean_features, fin_canvas
+#define BEVVOX_FIN_LAUNCH(KERNEL, GRID, THREADS)                                                                           \
   do {                                                                                                                     \
     if (fin_smem > 48 * 1024)                                                                                              \
       BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));    \
-    KERNEL<<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(BEVVOX_FIN_ARGS);                                               \
+    KERNEL<<<GRID, THREADS, fin_smem, stream>>>(BEVVOX_FIN_ARGS);                                                          \
   } while (0)
-  if (coop) {
-    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<8>);
-    else BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<16>);
-  } else {
-    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>);
-    else BEVVOX_FIN_LAUNCH(vox_finalize_kernel<16>);
+  {
+    const unsigned fin_grid = (unsigned)ceil_div64((int64_t)rows, kFinWarps * 32);
+    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>, fin_grid, kFinWarps * 32);
+    else BEVVOX_FIN_LAUNCH(vox_finalize_kernel<16>, fin_grid, kFinWarps * 32);
   }
 #undef BEVVOX_FIN_LAUNCH
 #undef BEVVOX_FIN_ARGS
   BEVPOOL_LAUNCH_CHECK();
+  if (dense_canvas) {
+    const dim3 cgrid((unsigned)ceil_div64(cells / 4, 256), (unsigned)batch);
+    if (mean_features <= 8)
+      vox_canvas_dense_kernel<8><<<cgrid, 256, 0, stream>>>(vid_of_cell, voxel_base, voxel_mean, mean_features, max_voxels, cells, canvas);
+    else
+      vox_canvas_dense_kernel<16><<<cgrid, 256, 0, stream>>>(vid_of_cell, voxel_base, voxel_mean, mean_features, max_voxels, cells, canvas);
+    BEVPOOL_LAUNCH_CHECK();
+  }
   return BEVPOOL_OK;
 }
 
