@@ -409,10 +409,6 @@ def main():
                     help="where the plan's cell indices come from: 'rig' = built on the device from sensor2ego @ inv(intrin) "
                          "(no geom_xyz tensor; needs an accumulation order proven bit-exact on this device), 'geom' = from the "
                          "reference's int32 geom_xyz tensor, 'auto' = rig when proven")
-    ap.add_argument('--lanes', type=int, default=1,
-                    help='split the batch into this many groups of frames, each on its own stream inside the step '
-                         '(samples are independent: the latency-bound plan chain of one group overlaps the other '
-                         "group's bandwidth- and issue-bound kernels)")
     ap.add_argument('--no-graph', action='store_true', help='launch eagerly instead of replaying a CUDA graph')
     ap.add_argument('--no-extras', action='store_true', help='skip e2e / cpu / reference-CUDA side measurements')
     ap.add_argument('--sweep', default='mini', choices=['mini', 'full'],
@@ -519,61 +515,13 @@ def main():
 
     from mm_training_b200.ops.voxel_pooling import fused_forward_cold
 
-    def step_whole():
+    def step():
         # cold call: plan build, then forward (BEVPOOL_COLD_OVERLAP=1: zero fill on a side stream behind the plan build)
         plan, out = fused_forward_cold(make_plan, B, vn, depth, ctx)      # NCHW context read through a TMA tensor map
         gd, gc = fused_backward(plan, go, depth, ctx)  # NCHW incoming gradient; grad_context written NCHW like ctx
         return plan, out, gd, gc
 
-    lanes = max(1, args.lanes)
-    if lanes > 1:
-        assert B % lanes == 0, '--lanes must divide --batch'
-        Bk, Nc = B // lanes, cfg.num_cams
-        lane_streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
-        lane_in = []
-        for k in range(lanes):
-            sl, slN = slice(k * Bk, (k + 1) * Bk), slice(k * Bk * Nc, (k + 1) * Bk * Nc)
-            pk = build_plan(geom[sl], vn, frustum=frustum)     # eager, once: the group's run count sizes its scratch rows
-            lane_in.append(dict(geom=geom[sl], depth=depth[slN], ctx=ctx[slN], go=go[sl],
-                                combine=combine[sl] if combine is not None else None,
-                                max_runs=pk.num_sorted if pk.mode == 'runs' else None))
-            del pk
-
-        def lane_plan(L):
-            if variant is not None:
-                return PoolingPlan.from_rig(lsg, L['combine'], variant, L['max_runs'])
-            return build_plan(L['geom'], vn, frustum=frustum, max_runs=L['max_runs'])
-
-        def step():
-            # the same cold call per group of frames, the groups on concurrent streams (fork / join: graph capturable)
-            cur = torch.cuda.current_stream()
-            res = []
-            for st, L in zip(lane_streams, lane_in):
-                st.wait_stream(cur)
-                with torch.cuda.stream(st):
-                    p, o = fused_forward_cold(lambda: lane_plan(L), Bk, vn, L['depth'], L['ctx'])
-                    g_d, g_c = fused_backward(p, L['go'], L['depth'], L['ctx'])
-                    res.append((p, o, g_d, g_c))
-            for st in lane_streams:
-                cur.wait_stream(st)
-            return res
-    else:
-        step = step_whole
-
-    plan, out, gd, gc = step_whole()
-    if lanes > 1:
-        lane_res = step()
-        torch.cuda.synchronize()
-        # (stage B cuts the sorted run list into equal slices of the WHOLE call: a group's partial sums are grouped
-        # differently -> rounding-level differences in the pooled output; the gradients are per pixel and bit-equal)
-        l_out, l_gd, l_gc = (torch.cat([r[i] for r in lane_res]) for i in (1, 2, 3))
-        assert torch.allclose(l_out, out, rtol=1e-5, atol=1e-6), 'lane outputs differ from the whole-batch call'
-        assert torch.allclose(l_gd, gd, rtol=1e-5, atol=1e-6) and torch.allclose(l_gc, gc, rtol=1e-5, atol=1e-6), \
-            'lane gradients differ from the whole-batch call'
-        lanes_bit_equal = {'out': bool(torch.equal(l_out, out)), 'grad_depth': bool(torch.equal(l_gd, gd)),
-                           'grad_context': bool(torch.equal(l_gc, gc))}
-        del l_out, l_gd, l_gc
-        del lane_res
+    plan, out, gd, gc = step()
     torch.cuda.synchronize()
     kept_per_frame = int((plan.cell_of_point >= 0).sum().item()) / B
     bytes_ = algorithmic_bytes(cfg, kept_per_frame)
@@ -756,8 +704,7 @@ def main():
             'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': dict(workload, launch='cuda_graph_replay' if graph is not None else 'eager',
-                           kept_points_per_frame=kept_per_frame, plan=plan_mode, lanes=lanes,
-                           **({'lanes_bit_equal_to_whole_batch': lanes_bit_equal} if lanes > 1 else {}),
+                           kept_points_per_frame=kept_per_frame, plan=plan_mode,
                            geometry=('rig: cell indices derived on the device from sensor2ego @ inv(intrin), variant %d, bit-exact '
                                      'vs the reference ops (checked in this run)' % variant) if variant is not None
                            else 'geom_xyz: int32 tensor made by the reference ops',

@@ -237,7 +237,7 @@ __global__ void scatter_backward_kernel(const T *__restrict__ grad_canvas, const
 
 // ==== dense-grid path (grids that fit a per-cell table: the aiMotive pillar grid is 2048 x 256 x 1) =================
 // The hash table is replaced by what mmcv's own CPU kernel uses, a dense cell -> first-point table, and the
-// pipeline shrinks to 4 kernels with no per-voxel index lists and no per-point prefix array:
+// pipeline is 6 kernels for the whole batch, with no per-voxel index lists and no per-point prefix array:
 //   A vox_cell_kernel      a tile of 1024 points = one contiguous span of the cloud brought into shared memory by ONE
 //                          TMA bulk copy (a point row is F*4 = 20 bytes: no wider aligned per-thread access exists),
 //                          global cell id per point, warp-aggregated atomicMin -> first point of every cell
@@ -245,17 +245,20 @@ __global__ void scatter_backward_kernel(const T *__restrict__ grad_canvas, const
 //                          = voxel numbering in point order; the creating point overwrites its cell's entry of the
 //                          first-point table with ~vid (one table serves both lookups) and publishes
 //                          cell_of_vid[sample][vid]
-//   C vox_claim_kernel     per kept point: cell -> voxel number -> the voxel's slot list (max_points words holding
-//                          0x7fffffff - index, zero = empty), an unsorted set that converges to the max_points
-//                          smallest indices by compare-and-swap eviction of the latest point (see the kernel).  The
-//                          lists are a compact array that stays in L2 -- atomics on the padded voxel tensor itself
-//                          (15 x F floats per row, far larger than L2) ran at DRAM random-access speed, 4x slower
-//   D vox_finalize_kernel  one lane per voxel row, one warp per 32 rows: slot list sorted in registers -> point rows gathered into a
+//   C vox_claim_kernel     per kept point: cell -> voxel number -> a ticket from the voxel's arrival counter; tickets
+//     vox_evict_kernel     below max_points are slots of the voxel's list (words = 0x7fffffff - index), later arrivals go
+//                          to the tile's overflow segment and are swapped in by compare-and-swap when they are earlier
+//                          than the row's latest point (see the kernels).  The lists are a compact array that stays in
+//                          L2 -- atomics on the padded voxel tensor itself (15 x F floats per row, far larger than L2)
+//                          ran at DRAM random-access speed, 4x slower
+//   D vox_finalize_*       one warp per 32 voxel rows: slot words sorted in registers -> point rows gathered into a
 //                          shared-memory tile that leaves as one contiguous, coalesced span of the padded voxel
 //                          tensor (93 % of it is zeros: written once, by this kernel, at streaming-store speed);
-//                          count, coordinates, HardSimpleVFE mean in slot order and, optionally, its pillar scatter
-// The canvas is zeroed by cudaMemsetAsync (a DRAM-speed fill; the pillars then overwrite their cells).  The clouds may
-// be given as one concatenated tensor or as a device array of per-sample pointers (no torch.cat of the batch).
+//                          count, coordinates, HardSimpleVFE mean in slot order
+//   E vox_canvas_dense_kernel  the pillar scatter of that mean as ONE in-order pass over the canvas (no zero fill, no
+//                          scattered stores); without a mean output the canvas is zero-filled on a side stream and the
+//                          finalize kernel scatters into it
+// The clouds may be given as one concatenated tensor or as a device array of per-sample pointers (no torch.cat).
 constexpr int kVcThreads = 256;
 constexpr int kVoxMaxF = 16;
 constexpr int32_t kVoxIdxBias = 0x7fffffff;          // slot word = kVoxIdxBias - point index  (> 0; 0 = empty)
@@ -271,10 +274,10 @@ struct VoxPoints {                                   // point i of sample b (i g
 constexpr int kVcPer = 4;                          // points per thread: independent chains in flight, 4x fewer CTAs
 __global__ void __launch_bounds__(kVcThreads)
 vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
-                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell, int l2_hints, int b0) {
+                int32_t *__restrict__ first, int32_t *__restrict__ point_gcell, int l2_hints) {
   extern __shared__ __align__(16) float s_pts[];   // kVcPer * kVcThreads * F floats
   __shared__ __align__(8) uint64_t s_bar;
-  const int b = b0 + blockIdx.y;                   // (the batch may be processed in groups of samples: b0 = first of the group)
+  const int b = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
   const int tile0 = begin + blockIdx.x * (kVcThreads * kVcPer);
   if (tile0 >= end) return;
@@ -330,11 +333,11 @@ static __global__ void __launch_bounds__(kScanThreads)
 vox_scan_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                 int32_t *first, int32_t *__restrict__ cell_of_vid,
                 int max_voxels, uint32_t *__restrict__ totals, unsigned long long *status, unsigned int *tickets,
-                int tiles_per_sample, int l2_hints, int b0) {
+                int tiles_per_sample, int l2_hints) {
   __shared__ uint32_t s_warp[kScanThreads / 32];
   const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   __shared__ uint32_t s_tile, s_prefix;
-  const int b = b0 + blockIdx.y;
+  const int b = blockIdx.y;
   const int begin = offsets[b], n = offsets[b + 1] - begin;
   if (n == 0) {
     if (blockIdx.x == 0 && threadIdx.x == 0) totals[b] = 0u;
@@ -481,11 +484,11 @@ __global__ void __launch_bounds__(256)
 vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ point_gcell,
                  const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base, int max_voxels,
                  int max_points, int32_t *__restrict__ lists, uint32_t *__restrict__ arrivals,
-                 int2 *__restrict__ overflow, uint32_t *__restrict__ tile_overflow, int tiles_cap, int l2_hints, int b0) {
+                 int2 *__restrict__ overflow, uint32_t *__restrict__ tile_overflow, int tiles_cap, int l2_hints) {
   __shared__ uint32_t s_over;                                     // overflow entries of this tile so far
   const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   const uint64_t pol_lists = (l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
-  const int b = b0 + blockIdx.y;
+  const int b = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
   const int tile0 = begin + blockIdx.x * (256 * kVcPer);
   if (tile0 >= end) return;
@@ -762,6 +765,147 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
   for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
 }
 
+// Rows of at most 16 slots (every pillar / voxel configuration of the reference): same output as vox_finalize_kernel, but
+// the point gather is shared by the warp.  With one lane walking its own row the warp runs as long as its fullest row
+// (13 % of the rows of a long-range sweep are full: practically every warp went through all four rounds of four slots)
+// while the mean row holds 1.7 points.  Here a lane reads, masks and sorts its row's words; the warp lists its (row, slot)
+// pairs behind an exclusive scan of the counts and lane p fetches pair p -- every point row of the 32 voxels is in flight
+// within two rounds for a typical warp.  The mean is summed by the row's lane from the shared-memory tile in slot order
+// (bit-identical to the serial sum).
+__host__ __device__ inline size_t vox_fin_coop_warp_bytes(int max_points, int F) {   // tile + words + pair map + row sources
+  return (size_t)128 * max_points * F + 2048 + 1024 + 256;
+}
+template <int FM>
+__global__ void __launch_bounds__(kFinWarps * 32)
+vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
+                         const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists,
+                         const uint32_t *__restrict__ arrivals, int batch, int max_voxels, int max_points,
+                         float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
+                         const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
+                         float *__restrict__ canvas) {
+  extern __shared__ __align__(128) unsigned char s_finc[];
+  const int TF = max_points * F;
+  const size_t warp_bytes = vox_fin_coop_warp_bytes(max_points, F);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wb = s_finc + (size_t)warp * warp_bytes;
+  float *tile = reinterpret_cast<float *>(wb);                                          // [32][TF]
+  int *s_words = reinterpret_cast<int *>(wb + (size_t)128 * TF);                        // [32][16] sorted slot words
+  uint16_t *s_map = reinterpret_cast<uint16_t *>(wb + (size_t)128 * TF + 2048);         // pair p -> row * 16 + slot
+  const float **s_src = reinterpret_cast<const float **>(wb + (size_t)128 * TF + 3072); // row -> point 0 of its cloud
+  int *s_vb = reinterpret_cast<int *>(s_finc + (size_t)kFinWarps * warp_bytes);
+  for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
+  for (int e = lane; e < 32 * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int64_t total_rows = (int64_t)batch * max_voxels;
+  const int64_t row0 = ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
+  if (row0 >= total_rows) return;
+  const int64_t row = row0 + lane;
+  const bool live = row < total_rows && row < s_vb[batch];
+  const int64_t lrow = live ? row : 0;                       // (dead lanes read row 0: no divergence around the sort)
+  int lo = 0, hi = batch;                                    // sample b: s_vb[b] <= row < s_vb[b + 1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (s_vb[mid] <= lrow) lo = mid; else hi = mid;
+  }
+  const int b = lo;
+  const int LS = vox_list_stride(max_points);
+  const int4 *list = reinterpret_cast<const int4 *>(lists + lrow * LS);
+  const int cnt = live ? (int)min(arrivals[lrow], (uint32_t)max_points) : 0;
+  const int gc = cell_of_vid[(int64_t)b * max_voxels + (lrow - s_vb[b])];
+  const int begin = offsets[b];
+  int4 q[4];
+#pragma unroll
+  for (int t4 = 0; t4 < 4; ++t4) {
+    q[t4] = make_int4(0, 0, 0, 0);
+    if (4 * t4 < cnt) q[t4] = ldg_stream_i4(list + t4);     // (last use of the row; cnt <= max_points <= LS)
+  }
+  int words[16];
+#pragma unroll
+  for (int t4 = 0; t4 < 4; ++t4) {
+    words[4 * t4 + 0] = 4 * t4 + 0 < cnt ? q[t4].x : 0;
+    words[4 * t4 + 1] = 4 * t4 + 1 < cnt ? q[t4].y : 0;
+    words[4 * t4 + 2] = 4 * t4 + 2 < cnt ? q[t4].z : 0;
+    words[4 * t4 + 3] = 4 * t4 + 3 < cnt ? q[t4].w : 0;
+  }
+  // the claim kernels leave an unsorted set in the first `cnt` slots: descending words = ascending point index
+  vox_sort16_desc(words);
+  int x = 0, y = 0, z = 0;
+  if (live) {
+    const uint32_t c = (uint32_t)((int64_t)gc - (int64_t)b * cells);      // (dense mode: a sample has < 2^26 cells)
+    const uint32_t cy = c / (uint32_t)g.gx;
+    x = (int)(c - cy * (uint32_t)g.gx);
+    z = (int)(cy / (uint32_t)g.gy);
+    y = (int)(cy - (uint32_t)z * (uint32_t)g.gy);
+    reinterpret_cast<int4 *>(coors)[row] = make_int4(b, z, y, x);
+  }
+  if (row < total_rows) num_points[row] = cnt;
+  s_src[lane] = pts.per_sample ? pts.per_sample[b] - (int64_t)begin * F : pts.cat;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+#pragma unroll
+  for (int t4 = 0; t4 < 4; ++t4)
+    *reinterpret_cast<int4 *>(s_words + lane * 16 + 4 * t4) = make_int4(words[4 * t4], words[4 * t4 + 1], words[4 * t4 + 2], words[4 * t4 + 3]);
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+    if (t < cnt) s_map[off + t] = (uint16_t)(lane * 16 + t);
+  __syncwarp();
+  for (int p0 = 0; p0 < total; p0 += 64) {                   // two point rows per lane in flight
+    float val[2][FM];
+    int dst[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int p = p0 + 32 * j + lane;
+      dst[j] = -1;
+      if (p < total) {
+        const int m = s_map[p], r = m >> 4;
+        const float *src = s_src[r] + (int64_t)(kVoxIdxBias - s_words[m]) * F;
+#pragma unroll
+        for (int k = 0; k < FM; ++k)
+          if (k < F) val[j][k] = __ldg(src + k);
+        dst[j] = r * TF + (m & 15) * F;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (dst[j] >= 0) {
+#pragma unroll
+        for (int k = 0; k < FM; ++k)
+          if (k < F) tile[dst[j] + k] = val[j][k];
+      }
+    }
+  }
+  __syncwarp();
+  if (cnt > 0 && (voxel_mean || canvas)) {
+    float sum[FM];
+#pragma unroll
+    for (int k = 0; k < FM; ++k) sum[k] = 0.f;
+    const float *trow = tile + (size_t)lane * TF;
+    for (int t = 0; t < cnt; ++t) {
+#pragma unroll
+      for (int k = 0; k < FM; ++k)
+        if (k < mean_features) sum[k] += trow[t * F + k];
+    }
+#pragma unroll
+    for (int k = 0; k < FM; ++k) {
+      if (k >= mean_features) break;
+      const float m = sum[k] / (float)cnt;
+      if (voxel_mean) voxel_mean[row * mean_features + k] = m;
+      if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
+    }
+  }
+  // the warp's 32 rows are one contiguous span of the output
+  const int64_t nrows = min((int64_t)32, total_rows - row0);
+  float *out = voxels + row0 * TF;
+  const int n4 = (int)(nrows * TF / 4);                      // row0 * TF * 4 bytes is a multiple of 16 (row0 % 32 == 0)
+  for (int e = lane; e < n4; e += 32) stg_stream_f4(reinterpret_cast<float4 *>(out) + e, reinterpret_cast<const float4 *>(tile)[e]);
+  for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
+}
+
 // Dense canvas of the fused HardSimpleVFE mean, written ONCE and in order: a thread owns 4 consecutive cells, reads their
 // entries of the voxel-number table (16 bytes), fetches the mean row of the occupied ones (5 % of the cells of a
 // long-range sweep) and writes mean_features coalesced 16-byte streaming stores.  This replaces a DRAM-speed zero fill of
@@ -912,14 +1056,6 @@ static int vox_l2_hints() {
   }();
   return v;
 }
-// samples per group of the dense pipeline: BEVVOX_GROUP (default 0 = the whole batch at once)
-static int vox_group_samples(int batch) {
-  static const int env = [] {
-    const char *e = std::getenv("BEVVOX_GROUP");
-    return e && e[0] ? std::atoi(e) : 0;
-  }();
-  return env > 0 && env < batch ? env : batch;
-}
 static bool vox_overlap_enabled() {
   static const bool on = [] {
     const char *e = std::getenv("BEVVOX_CANVAS_OVERLAP");
@@ -985,36 +1121,31 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     }
   }
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(tb, 0, L.zero_bytes, stream));
-  // Groups of samples.  The first-point / voxel-number table (4 bytes per cell: 2 MB per sample of the aiMotive pillar grid)
-  // is visited at random by the cell, scan and claim kernels; at 32 sweeps it is 64 MB and every visit of the later kernels
-  // missed L2 (ncu: the claim kernel waits 130 cycles per issued instruction on 32-byte DRAM reads).  Running
-  // fill -> cell -> scan -> base -> claim per group of samples keeps a group's table in L2 from its fill to its last use.
-  const int group = vox_group_samples(batch);
+  // (Tried: running fill -> cell -> scan -> base -> claim per group of 8 or 16 samples so that a group's 2 MB-per-sample
+  // first-point table stays in L2 between the three kernels that visit it at random -- no gain at 16, slower at 8: the
+  // extra launches and tails cost more than the L2 hits return.)
   uint32_t *arrivals = reinterpret_cast<uint32_t *>(tb + L.off_arrivals);
   int2 *overflow = reinterpret_cast<int2 *>(tb + L.off_overflow);
   uint32_t *tile_overflow = reinterpret_cast<uint32_t *>(tb + L.off_tile_overflow);
   const unsigned ptiles = (unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer);
-  for (int b0 = 0; b0 < batch; b0 += group) {
-    const int nb = std::min(group, batch - b0);
-    BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first + (size_t)b0 * cells, 0x7f, (size_t)nb * cells * 4, stream));
-    const dim3 pgrid(ptiles, (unsigned)nb);
-    if (total_points > 0) {
-      vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(
-          pts, sample_offsets, F, g, cells, first, gcell, vox_l2_hints(), b0);
-      BEVPOOL_LAUNCH_CHECK();
-    }
-    vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)nb), kScanThreads, 0, stream>>>(
-        sample_offsets, gcell, first, cell_of_vid, max_voxels, totals,
-        reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
-        L.tiles_per_sample, vox_l2_hints(), b0);
+  const dim3 pgrid(ptiles, (unsigned)batch);
+  BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
+  if (total_points > 0) {
+    vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(
+        pts, sample_offsets, F, g, cells, first, gcell, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
-    vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, b0 + nb, max_voxels, voxel_base);   // (prefix over the samples so far)
+  }
+  vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(
+      sample_offsets, gcell, first, cell_of_vid, max_voxels, totals,
+      reinterpret_cast<unsigned long long *>(tb + L.off_status), reinterpret_cast<unsigned int *>(tb + L.off_tickets),
+      L.tiles_per_sample, vox_l2_hints());
+  BEVPOOL_LAUNCH_CHECK();
+  vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, batch, max_voxels, voxel_base);
+  BEVPOOL_LAUNCH_CHECK();
+  if (total_points > 0) {
+    vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
+                                                arrivals, overflow, tile_overflow, L.tiles_cap, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
-    if (total_points > 0) {
-      vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
-                                                  arrivals, overflow, tile_overflow, L.tiles_cap, vox_l2_hints(), b0);
-      BEVPOOL_LAUNCH_CHECK();
-    }
   }
   if (total_points > 0) {
     const dim3 egrid(ptiles, (unsigned)batch);
@@ -1027,7 +1158,10 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
     }
     BEVPOOL_LAUNCH_CHECK();
   }
-  const size_t fin_smem = (size_t)kFinWarps * 32 * max_points * F * sizeof(float) + (size_t)(batch + 1) * sizeof(int);
+  static const bool coop_on = [] { const char *e = std::getenv("BEVVOX_FIN_COOP"); return !(e && e[0] == '0'); }();
+  const bool coop = coop_on && max_points <= 16;
+  const size_t fin_smem = (coop ? (size_t)kFinWarps * vox_fin_coop_warp_bytes(max_points, F)
+                                : (size_t)kFinWarps * 32 * max_points * F * sizeof(float)) + (size_t)(batch + 1) * sizeof(int);
   if (fin_smem > 200 * 1024) return BEVPOOL_E_RANGE;       // max_points * F beyond ~390 floats: not a pillar configuration
   if (ev_join) {
     BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
@@ -1044,7 +1178,10 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   } while (0)
   {
     const unsigned fin_grid = (unsigned)ceil_div64((int64_t)rows, kFinWarps * 32);
-    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>, fin_grid, kFinWarps * 32);
+    if (coop) {
+      if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<8>, fin_grid, kFinWarps * 32);
+      else BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<16>, fin_grid, kFinWarps * 32);
+    } else if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>, fin_grid, kFinWarps * 32);
     else BEVVOX_FIN_LAUNCH(vox_finalize_kernel<16>, fin_grid, kFinWarps * 32);
   }
 #undef BEVVOX_FIN_LAUNCH
