@@ -1,4 +1,5 @@
-"""Per-kernel table of the LAST bench step in an ncu launch list (csv with gpu__time_duration / dram bytes)."""
+"""Per-kernel table of one step in an ncu launch list (csv with gpu__time_duration / dram bytes).
+usage: python scripts/launch_table.py <launches.csv> [name of the kernel that opens a step]"""
 import collections
 import csv
 import sys
@@ -15,8 +16,10 @@ for r in rows[hi + 1:]:
     d[r[mi]] = float(r[vi].replace(',', ''))
 ls = list(launch.values())
 # one step = from a plan key kernel to the next; the timed loop comes first, per-stage timing loops after it
-starts = [i for i, l in enumerate(ls) if 'plan_key' in l['name']]
-a, b = starts[3], starts[4]          # a warm-up step of the main loop (earlier ones are the probe / set-up steps)
+key = sys.argv[2] if len(sys.argv) > 2 else 'plan_key'          # kernel that opens a step ('vox_cell' for the LiDAR branch)
+starts = [i for i, l in enumerate(ls) if key in l['name']]
+a, b = (starts[3], starts[4]) if key == 'plan_key' else (starts[-2], starts[-1])   # camera: a warm-up step of the main loop
+# (earlier ones are the probe / set-up steps); other probes: the last complete step (the timed loop comes last)
 tot = sum(l.get('gpu__time_duration.sum', 0) for l in ls[a:b])
 print(f'one step = {b - a} launches, {tot / 1e3:.1f} us (ncu: cold caches, serialised)')
 for l in ls[a:b]:
