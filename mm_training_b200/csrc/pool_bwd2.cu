@@ -33,6 +33,8 @@
 #include "pool_g8.cuh"
 #include "tma.cuh"
 
+#include <cstdlib>
+
 namespace bevpool {
 
 constexpr int kBcTW = 4;                            // image columns per CTA = warps per CTA
@@ -79,7 +81,7 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int NV2, bool kNchw>
+template <int NV2, bool kNchw, bool kStaticBins>
 __global__ void __launch_bounds__(kBcThreads, (NV2 <= 5 ? 3 : 2))
 fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __grid_constant__ CUtensorMap gctx_map,
                           const int32_t *__restrict__ cell_of_point, const int4 *__restrict__ pair_rec,
@@ -269,10 +271,12 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
           }
           dp4 = lds_f4(d_addr + (uint32_t)b * (kBcDepStride * 4));
         };
-        auto phase_b = [&]() {
+        // phase B: the parked partial sums of up to 4 bins -> grad_depth values.  `bins`: the bin of every slot, packed 4 bits
+        // each; `nb`: slots in use.
+        auto phase_b = [&](uint32_t bins, int nb) {
           __syncwarp();
           const int pair = lane >> 1, half = lane & 1, kk = pair >> 2, prg = pair & 3;
-          const int bq = (int)((binpack >> (4 * kk)) & 0xfu);
+          const int bq = (int)((bins >> (4 * kk)) & 0xfu);
           const uint32_t mq = __shfl_sync(kFull, m_lane, bq);
           const float4 *pp = reinterpret_cast<const float4 *>(part_w + pair * kBcPartStride + 16 * half);
           const float4 p0 = pp[0], p1 = pp[1], p2 = pp[2], p3 = pp[3];
@@ -285,7 +289,7 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
           t.y += __shfl_xor_sync(kFull, t.y, 1);
           t.z += __shfl_xor_sync(kFull, t.z, 1);
           t.w += __shfl_xor_sync(kFull, t.w, 1);
-          if (half == 0 && kk < nslot) {
+          if (half == 0 && kk < nb && (mq & 0xffffu)) {            // (a slot of a dead bin holds stale sums: never stored)
             const uint32_t keep = (mq >> (4 * prg)) & 0xfu;         // rows of this group lying in the bin's primary cell
             t.x = (keep & 1u) ? t.x : 0.f;
             t.y = (keep & 2u) ? t.y : 0.f;
@@ -294,12 +298,11 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
             *reinterpret_cast<float4 *>(s_res + bq * kBcDepStride + wl * kBcTH + 4 * prg) = t;
           }
           __syncwarp();
-          binpack = 0u;
-          nslot = 0;
         };
-        // body: reduce bin b.  Branch-free over the rows: dot products of rows outside the primary cell are computed
-        // and never stored, and their staged depth is 0, so their accumulators receive +-0 (exact for finite gradients).
-        auto body = [&](int b, const float (&g)[NREG], const float4 &dp4) {
+        // body: reduce bin b into partial-sum slot `slot`.  Branch-free over the rows: dot products of rows outside the
+        // primary cell are computed and never stored, and their staged depth is 0, so their accumulators receive +-0
+        // (exact for finite gradients).
+        auto body = [&](int slot, const float (&g)[NREG], const float4 &dp4) {
           const float dp[4] = {dp4.x, dp4.y, dp4.z, dp4.w};
           float sv[4];
 #pragma unroll
@@ -314,35 +317,56 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
             const float2 dab = __fadd2_rn(da, db);
             sv[j] = dab.x + dab.y;
           }
-          sts_f4(p_addr + (uint32_t)nslot * (4 * kBcPartStride * 4), make_float4(sv[0], sv[1], sv[2], sv[3]));
-          binpack |= (uint32_t)b << (4 * nslot);
-          ++nslot;
+          sts_f4(p_addr + (uint32_t)slot * (4 * kBcPartStride * 4), make_float4(sv[0], sv[1], sv[2], sv[3]));
         };
         const uint32_t slow_bins = __ballot_sync(kFull, (m_lane >> 16) != 0u);
         float ga[NREG], gb[NREG];
         float4 da4, db4;
-        int ba = __ffs(live) - 1, bb = ba;
-        live &= live - 1u;
-        fetch(ba, ga, da4);
-        while (true) {                                                // warp-uniform; two roles, no register rotation
-          const bool more_a = live != 0u;
-          if (more_a) {
-            bb = __ffs(live) - 1;
-            live &= live - 1u;
-            fetch(bb, gb, db4);
+        if constexpr (kStaticBins) {
+          // All 16 bins of the chunk in program order, dead ones skipped by a warp-uniform branch: every shared-memory
+          // address is base + immediate, a bin's partial-sum slot is (bin & 3), phase B runs after bins 3, 7, 11, 15 --
+          // no find-first-set chain, address arithmetic or slot bookkeeping per bin (the searching loop below spends 47
+          // instructions per bin beside its 40 FFMA2, and its FLO -> IMAD -> LDS chain shows up in the stall samples).
+          if (live & 1u) fetch(0, ga, da4);
+#pragma unroll
+          for (int b = 0; b < kBcDC; ++b) {
+            if (b + 1 < kBcDC && ((live >> (b + 1)) & 1u)) {
+              if (b & 1) fetch(b + 1, ga, da4); else fetch(b + 1, gb, db4);
+            }
+            if ((live >> b) & 1u) {
+              if (b & 1) body(b & 3, gb, db4); else body(b & 3, ga, da4);
+            }
+            if ((b & 3) == 3 && ((live >> (b - 3)) & 0xfu))
+              phase_b((uint32_t)(b - 3) | ((uint32_t)(b - 2) << 4) | ((uint32_t)(b - 1) << 8) | ((uint32_t)b << 12), 4);
           }
-          body(ba, ga, da4);
-          if (nslot == kBcMC || !more_a) phase_b();
-          if (!more_a) break;
-          const bool more_b = live != 0u;
-          if (more_b) {
-            ba = __ffs(live) - 1;
-            live &= live - 1u;
-            fetch(ba, ga, da4);
+        } else {
+          int ba = __ffs(live) - 1, bb = ba;
+          live &= live - 1u;
+          fetch(ba, ga, da4);
+          while (true) {                                                // warp-uniform; two roles, no register rotation
+            const bool more_a = live != 0u;
+            if (more_a) {
+              bb = __ffs(live) - 1;
+              live &= live - 1u;
+              fetch(bb, gb, db4);
+            }
+            body(nslot, ga, da4);
+            binpack |= (uint32_t)ba << (4 * nslot);
+            ++nslot;
+            if (nslot == kBcMC || !more_a) { phase_b(binpack, nslot); binpack = 0u; nslot = 0; }
+            if (!more_a) break;
+            const bool more_b = live != 0u;
+            if (more_b) {
+              ba = __ffs(live) - 1;
+              live &= live - 1u;
+              fetch(ba, ga, da4);
+            }
+            body(nslot, gb, db4);
+            binpack |= (uint32_t)bb << (4 * nslot);
+            ++nslot;
+            if (nslot == kBcMC || !more_b) { phase_b(binpack, nslot); binpack = 0u; nslot = 0; }
+            if (!more_b) break;
           }
-          body(bb, gb, db4);
-          if (nslot == kBcMC || !more_b) phase_b();
-          if (!more_b) break;
         }
         // ---- kept rows outside their pair's primary cell (tilted cameras, random geometry; none for a level
         // camera): every such row gathers its own gradient row from global memory.  After the loop above, so that
@@ -414,15 +438,15 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
   }
 }
 
-template <int NV2, bool kNchw>
+template <int NV2, bool kNchw, bool kStaticBins>
 static int launch_bc(const CUtensorMap &ctx_map, const CUtensorMap &gctx_map, const int32_t *cell_of_point,
                      const int4 *pair_rec, const float *grad_rows, const float *depth, const float *ctx_nhwc, float *grad_depth,
                      float *grad_ctx_nhwc, int num_cams, int D, int H, int W, int64_t cells_per_sample, int64_t ctas,
                      int tiles_h, int tiles_w, int64_t g_stride, cudaStream_t s) {
   constexpr size_t smem = BcSmem<NV2>::bytes;
-  BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_col_kernel<NV2, kNchw>,
+  BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(fused_backward_col_kernel<NV2, kNchw, kStaticBins>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BEVPOOL_RETURN_IF_CUDA(launch_pdl(fused_backward_col_kernel<NV2, kNchw>, dim3((unsigned)ctas), dim3(kBcThreads), smem, s,
+  BEVPOOL_RETURN_IF_CUDA(launch_pdl(fused_backward_col_kernel<NV2, kNchw, kStaticBins>, dim3((unsigned)ctas), dim3(kBcThreads), smem, s,
                                     ctx_map, gctx_map, cell_of_point, pair_rec, grad_rows, depth, ctx_nhwc, grad_depth, grad_ctx_nhwc,
                                     num_cams, D, H, W, cells_per_sample, tiles_h, tiles_w, g_stride));
   BEVPOOL_LAUNCH_CHECK();
@@ -453,8 +477,14 @@ int launch_fused_backward_col(const int32_t *cell_of_point, const int4 *pair_rec
   int rc = BEVPOOL_OK;
 #define BEVPOOL_BC_ARGS ctx_map, gctx_map, cell_of_point, pair_rec, grad_rows, depth, ctx, grad_depth, grad_ctx, num_cams, D, H, W, \
                         cells_per_sample, ctas, (int)tiles_h, (int)tiles_w, grad_row_stride, s
-  if (nchw) { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, true>(BEVPOOL_BC_ARGS))); }
-  else { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, false>(BEVPOOL_BC_ARGS))); }
+  static const bool static_bins = [] { const char *e = std::getenv("BEVPOOL_BW_STATIC"); return !(e && e[0] == '0'); }();
+  if (static_bins) {
+    if (nchw) { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, true, true>(BEVPOOL_BC_ARGS))); }
+    else { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, false, true>(BEVPOOL_BC_ARGS))); }
+  } else {
+    if (nchw) { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, true, false>(BEVPOOL_BC_ARGS))); }
+    else { BEVPOOL_G8_DISPATCH(C, (rc = launch_bc<NV2, false, false>(BEVPOOL_BC_ARGS))); }
+  }
 #undef BEVPOOL_BC_ARGS
   return rc;
 }
