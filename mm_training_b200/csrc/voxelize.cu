@@ -782,7 +782,7 @@ vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int
                          const uint32_t *__restrict__ arrivals, int batch, int max_voxels, int max_points,
                          float *__restrict__ voxels, int32_t *__restrict__ num_points, int32_t *__restrict__ coors,
                          const int32_t *__restrict__ voxel_base, float *__restrict__ voxel_mean, int mean_features,
-                         float *__restrict__ canvas, int64_t row_begin, int64_t row_end) {
+                         float *__restrict__ canvas) {
   extern __shared__ __align__(128) unsigned char s_finc[];
   const int TF = max_points * F;
   const size_t warp_bytes = vox_fin_coop_warp_bytes(max_points, F);
@@ -796,8 +796,8 @@ vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int
   for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
   for (int e = lane; e < 32 * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const int64_t total_rows = row_end;                        // this launch covers rows [row_begin, row_end), row_begin % 32 == 0
-  const int64_t row0 = row_begin + ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
+  const int64_t total_rows = (int64_t)batch * max_voxels;
+  const int64_t row0 = ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
   if (row0 >= total_rows) return;
   const int64_t row = row0 + lane;
   const bool live = row < total_rows && row < s_vb[batch];
@@ -916,13 +916,8 @@ template <int FM>
 __global__ void __launch_bounds__(256)
 vox_canvas_dense_kernel(const int32_t *__restrict__ vid_of_cell, const int32_t *__restrict__ voxel_base,
                         const float *__restrict__ voxel_mean, int mean_features, int max_voxels, int64_t cells,
-                        float *__restrict__ canvas, int64_t rows_lo, int64_t rows_hi) {
-  // this launch writes the samples whose LAST row became final in the finalize launch that covered rows [rows_lo, rows_hi)
-  // (rows_lo = -1: from the start): the finalize kernel runs in parts and each part's samples are written behind it, on a
-  // side stream, beside the next part
+                        float *__restrict__ canvas) {
   const int b = blockIdx.y;
-  const int64_t last = voxel_base[b + 1];
-  if (last <= rows_lo || last > rows_hi) return;
   const int64_t c4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (c4 >= cells) return;
   const int4 e4 = ldg_stream_i4(reinterpret_cast<const int4 *>(vid_of_cell + (int64_t)b * cells + c4));
@@ -1175,61 +1170,15 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   float *fin_canvas = dense_canvas ? nullptr : canvas;
   const uint32_t *arrivals_c = reinterpret_cast<const uint32_t *>(tb + L.off_arrivals);
   const dim3 cgrid((unsigned)ceil_div64(cells / 4, 256), (unsigned)batch);
-  auto launch_canvas = [&](cudaStream_t cs, int64_t lo, int64_t hi) {
+  auto launch_canvas = [&](cudaStream_t cs) {
     if (mean_features <= 8)
-      vox_canvas_dense_kernel<8><<<cgrid, 256, 0, cs>>>(vid_of_cell, voxel_base, voxel_mean, mean_features, max_voxels, cells, canvas, lo, hi);
+      vox_canvas_dense_kernel<8><<<cgrid, 256, 0, cs>>>(vid_of_cell, voxel_base, voxel_mean, mean_features, max_voxels, cells, canvas);
     else
-      vox_canvas_dense_kernel<16><<<cgrid, 256, 0, cs>>>(vid_of_cell, voxel_base, voxel_mean, mean_features, max_voxels, cells, canvas, lo, hi);
+      vox_canvas_dense_kernel<16><<<cgrid, 256, 0, cs>>>(vid_of_cell, voxel_base, voxel_mean, mean_features, max_voxels, cells, canvas);
   };
-  if (coop) {
-    // The finalize kernel is issue-bound (42 % of the DRAM bandwidth) and the canvas pass is a pure DRAM-write stream that
-    // needs a sample's means: the rows are cut into `parts` launches and every part's samples are written to the canvas on
-    // the side stream while the next part runs (fork / join by events: capturable).
-    static const int parts_env = [] { const char *e = std::getenv("BEVVOX_FIN_PARTS"); return e && e[0] ? std::atoi(e) : 3; }();
-    cudaStream_t side = (dense_canvas && parts_env > 1 && vox_overlap_enabled()) ? vox_side_stream() : nullptr;
-    const int parts = side ? std::min(parts_env, 8) : 1;
-    const int64_t part_rows = (ceil_div64(ceil_div64((int64_t)rows, parts), kFinWarps * 32)) * (kFinWarps * 32);
-    if (fin_smem > 48 * 1024) {
-      if (F <= 8) BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_coop_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-      else BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_finalize_coop_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem));
-    }
-    for (int p = 0; p < parts; ++p) {
-      const int64_t r0 = (int64_t)p * part_rows, r1 = std::min<int64_t>((int64_t)rows, r0 + part_rows);
-      if (r0 >= r1) break;
-      const unsigned fin_grid = (unsigned)ceil_div64(r1 - r0, kFinWarps * 32);
-      if (F <= 8)
-        vox_finalize_coop_kernel<8><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
-            pts, sample_offsets, F, g, cells, cell_of_vid, lists, arrivals_c, batch, max_voxels, max_points, voxels, num_points, coors,
-            voxel_base, voxel_mean, mean_features, fin_canvas, r0, r1);
-      else
-        vox_finalize_coop_kernel<16><<<fin_grid, kFinWarps * 32, fin_smem, stream>>>(
-            pts, sample_offsets, F, g, cells, cell_of_vid, lists, arrivals_c, batch, max_voxels, max_points, voxels, num_points, coors,
-            voxel_base, voxel_mean, mean_features, fin_canvas, r0, r1);
-      BEVPOOL_LAUNCH_CHECK();
-      if (dense_canvas) {
-        const int64_t lo = p == 0 ? -1 : r0, hi = r1 >= (int64_t)rows ? INT64_MAX : r1;
-        if (side) {
-          cudaEvent_t ev = nullptr;
-          BEVPOOL_RETURN_IF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-          BEVPOOL_RETURN_IF_CUDA(cudaEventRecord(ev, stream));
-          BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(side, ev, 0));
-          cudaEventDestroy(ev);
-          launch_canvas(side, lo, hi);
-        } else {
-          launch_canvas(stream, lo, hi);
-        }
-        BEVPOOL_LAUNCH_CHECK();
-      }
-    }
-    if (side) {
-      cudaEvent_t ev = nullptr;
-      BEVPOOL_RETURN_IF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-      BEVPOOL_RETURN_IF_CUDA(cudaEventRecord(ev, side));
-      BEVPOOL_RETURN_IF_CUDA(cudaStreamWaitEvent(stream, ev, 0));
-      cudaEventDestroy(ev);
-    }
-    return BEVPOOL_OK;
-  }
+  // (Tried: the finalize kernel in 2-4 launches over row ranges, each range's samples written to the canvas on a side
+  // stream beside the next range -- 359 / 373 / 385 us per 32 sweeps against 344 us back to back: the DRAM-write stream
+  // slows the finalize kernel's own streaming stores by more than the overlap returns.)
 #define BEVVOX_FIN_ARGS pts, sample_offsets, F, g, cells, cell_of_vid, lists, arrivals_c, batch, \
                         max_voxels, max_points, voxels, num_points, coors, voxel_base, voxel_mean, mean_features, fin_canvas
 #define BEVVOX_FIN_LAUNCH(KERNEL, GRID, THREADS)                                                                           \
@@ -1240,14 +1189,17 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   } while (0)
   {
     const unsigned fin_grid = (unsigned)ceil_div64((int64_t)rows, kFinWarps * 32);
-    if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>, fin_grid, kFinWarps * 32);
+    if (coop) {
+      if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<8>, fin_grid, kFinWarps * 32);
+      else BEVVOX_FIN_LAUNCH(vox_finalize_coop_kernel<16>, fin_grid, kFinWarps * 32);
+    } else if (F <= 8) BEVVOX_FIN_LAUNCH(vox_finalize_kernel<8>, fin_grid, kFinWarps * 32);
     else BEVVOX_FIN_LAUNCH(vox_finalize_kernel<16>, fin_grid, kFinWarps * 32);
   }
 #undef BEVVOX_FIN_LAUNCH
 #undef BEVVOX_FIN_ARGS
   BEVPOOL_LAUNCH_CHECK();
   if (dense_canvas) {
-    launch_canvas(stream, -1, INT64_MAX);
+    launch_canvas(stream);
     BEVPOOL_LAUNCH_CHECK();
   }
   return BEVPOOL_OK;
