@@ -307,15 +307,12 @@ fused_backward_col_kernel(const __grid_constant__ CUtensorMap ctx_map, const __g
           float sv[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
+            float2 da = make_float2(0.f, 0.f);                      // (one chain per row: the four rows interleave)
 #pragma unroll
-            for (int r = 0; r < NREG; r += 4) {
+            for (int r = 0; r < NREG; r += 2)
               da = __ffma2_rn(make_float2(g[r], g[r + 1]), make_float2(cx[j][r], cx[j][r + 1]), da);
-              if (r + 2 < NREG) db = __ffma2_rn(make_float2(g[r + 2], g[r + 3]), make_float2(cx[j][r + 2], cx[j][r + 3]), db);
-            }
             axpy_row<NREG>(gacc[j], dp[j], g);
-            const float2 dab = __fadd2_rn(da, db);
-            sv[j] = dab.x + dab.y;
+            sv[j] = da.x + da.y;
           }
           sts_f4(p_addr + (uint32_t)slot * (4 * kBcPartStride * 4), make_float4(sv[0], sv[1], sv[2], sv[3]));
         };

@@ -167,6 +167,40 @@ def test_padded_no_sync_and_fused_scatter():
     assert torch.equal(cap[0], voxels) and torch.equal(cap[5], canvas) and torch.equal(cap[3], base)
 
 
+def test_canvas_without_a_mean_output_takes_the_fill_and_scatter_path():
+    # C ABI with voxel_mean == NULL and a canvas: no mean rows to read the dense canvas pass from -> the canvas is
+    # zero-filled on the side stream and the finalize kernel scatters into it; same bits as the dense pass
+    import ctypes
+    from mm_training_b200 import _lib
+    from mm_training_b200.ops import voxelize as vzmod
+    clouds = [torch.from_numpy(synthetic.lidar_sweep(n, 5, seed=40 + i)).to(DEV) for i, n in enumerate([30000, 52000])]
+    T, M, mf = 15, 25000, 5
+    ref = hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, T, M, mean_features=mf, padded=True, scatter=True)
+    B, F = len(clouds), 5
+    counts = [int(c.shape[0]) for c in clouds]
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    grid = vzmod._grid_size(CFG_3.voxel_size, CFG_3.point_cloud_range)
+    gx, gy, gz = grid
+    L = _lib.lib()
+    tb = ctypes.c_size_t()
+    _lib.check(L.bevvox_temp_bytes(B, int(offs[-1]), vzmod._i32_array(grid), M, T, ctypes.byref(tb)), 'bevvox_temp_bytes')
+    pts = torch.cat(clouds, 0).contiguous()
+    offsets = torch.from_numpy(offs).to(DEV)
+    voxels = torch.empty(B * M, T, F, device=DEV)
+    coors = torch.empty(B * M, 4, dtype=torch.int32, device=DEV)
+    num = torch.empty(B * M, dtype=torch.int32, device=DEV)
+    base = torch.empty(B + 1, dtype=torch.int32, device=DEV)
+    canvas = torch.full((B, mf * gz, gy, gx), 7.0, device=DEV)             # (garbage: the call must fill it)
+    temp = torch.empty(tb.value, dtype=torch.uint8, device=DEV)
+    _lib.check(L.bevvox_hard_voxelize_scatter(
+        pts.data_ptr(), None, offsets.data_ptr(), B, int(offs[-1]), max(counts), F, vzmod._f32_array(CFG_3.voxel_size),
+        vzmod._f32_array(CFG_3.point_cloud_range), vzmod._i32_array(grid), T, M, voxels.data_ptr(), coors.data_ptr(),
+        num.data_ptr(), base.data_ptr(), None, mf, canvas.data_ptr(), 0, temp.data_ptr(), _lib.stream_ptr(torch.device(DEV))),
+        'bevvox_hard_voxelize_scatter')
+    torch.cuda.synchronize()
+    assert torch.equal(canvas, ref[5]) and torch.equal(voxels, ref[0]) and torch.equal(num, ref[1]) and torch.equal(base, ref[3])
+
+
 def test_dynamic_voxelize():
     pts = synthetic.lidar_sweep(50000, 5, seed=3)
     coors = dynamic_voxelize(torch.from_numpy(pts).to(DEV), CFG_3.voxel_size, CFG_3.point_cloud_range)
