@@ -296,6 +296,37 @@ def run_dropin_op(dev, peak_gbs, cfg=CFG_2, B=8, seed=5):
     return res
 
 
+def run_half_precision_side(dev, cfg=CFG_2, B=8, seed=5):
+    """fp16 / bf16 inputs (north star: features and gradients within 1e-2): the fused op on half-precision depth, context and
+    incoming gradient, cold POINT plan + forward + backward (the run-plan fast path is fp32 only; the generic kernels
+    accumulate in fp32), CUDA events, beside the fp32 step on the same frames and the worst relative error against it."""
+    from mm_training_b200.ops.voxel_pooling import build_plan, fused_backward, fused_forward
+    geom, vn_t = synthetic.camera_rig(cfg, B, device=dev, yaw_jitter_deg=5.0, seed=seed)
+    vn = tuple(int(v) for v in vn_t.tolist())
+    depth, ctx, go = synthetic.camera_features(cfg, B, device=dev, seed=seed)
+    fr = tuple(geom.shape[1:5])
+
+    def step32():
+        plan = build_plan(geom, vn, frustum=fr)
+        return fused_forward(plan, depth, ctx), fused_backward(plan, go, depth, ctx)
+    out32, (gd32, gc32) = step32()
+    res = {'workload': cfg.name, 'frames_per_step': B, 'fp32_run_plan_ms_per_step': time_cuda(step32, 10, 3)[0],
+           'what': 'cold plan + fused forward + fused backward through the functional API, eager'}
+    for name, dt in (('bf16', torch.bfloat16), ('fp16', torch.float16)):
+        d16, c16, g16 = depth.to(dt), ctx.to(dt), go.to(dt)
+
+        def step16():
+            plan = build_plan(geom, vn)
+            return fused_forward(plan, d16, c16), fused_backward(plan, g16, d16, c16)
+        out16, (gd16, gc16) = step16()
+        rel = lambda a, b: float((a.float() - b).abs().max() / b.abs().max())
+        res[name] = {'ms_per_step': time_cuda(step16, 10, 3)[0],
+                     'max_err_over_max_abs': {'out': rel(out16, out32), 'grad_depth': rel(gd16, gd32), 'grad_context': rel(gc16, gc32)}}
+        res[name]['frames_per_s'] = B / (res[name]['ms_per_step'] * 1e-3)
+        del d16, c16, g16, out16, gd16, gc16
+    return res
+
+
 def run_depth_labels_side(dev, peak_gbs, B=4):
     """Side measurement: depth labels for the depth loss at the shipped shape (704 x 1280 images, 2
     cameras, 200 k LiDAR points per frame, 16 x 16 min-pool, 409 bins): the native two-launch path beside the
@@ -760,6 +791,12 @@ def main():
             line['dropin_op'] = run_dropin_op(dev, peak_gbs)
         except Exception as e:                                  # pragma: no cover
             line['dropin_op'] = {'error': repr(e)}
+
+        # ---- fp16 / bf16 inputs (generic kernels, fp32 accumulation)
+        try:
+            line['half_precision'] = run_half_precision_side(dev)
+        except Exception as e:                                  # pragma: no cover
+            line['half_precision'] = {'error': repr(e)}
 
         # ---- depth labels for the depth loss
         try:

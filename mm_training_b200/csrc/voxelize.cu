@@ -772,11 +772,15 @@ vox_finalize_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, V
 // pairs behind an exclusive scan of the counts and lane p fetches pair p -- every point row of the 32 voxels is in flight
 // within two rounds for a typical warp.  The mean is summed by the row's lane from the shared-memory tile in slot order
 // (bit-identical to the serial sum).
+// The tile holds 16 rows: the warp's 32 rows leave in two passes (gather, mean, write-out per half) -- 8 KB of shared
+// memory per warp instead of 13 KB at the pillar shape, 28 resident warps per SM instead of 16 (the kernel is bound by
+// instruction issue and latency, not by DRAM).
+constexpr int kFinTileRows = 16;
 __host__ __device__ inline size_t vox_fin_coop_warp_bytes(int max_points, int F) {   // tile + words + pair map + row sources
-  return (size_t)128 * max_points * F + 2048 + 1024 + 256;
+  return (size_t)kFinTileRows * 4 * max_points * F + 2048 + 1024 + 256;
 }
 template <int FM>
-__global__ void __launch_bounds__(kFinWarps * 32)
+__global__ void __launch_bounds__(kFinWarps * 32, FM <= 8 ? 6 : 3)
 vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
                          const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists,
                          const uint32_t *__restrict__ arrivals, int batch, int max_voxels, int max_points,
@@ -786,15 +790,15 @@ vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int
   extern __shared__ __align__(128) unsigned char s_finc[];
   const int TF = max_points * F;
   const size_t warp_bytes = vox_fin_coop_warp_bytes(max_points, F);
+  const size_t tile_bytes = (size_t)kFinTileRows * 4 * TF;                              // (a multiple of 64)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char *wb = s_finc + (size_t)warp * warp_bytes;
-  float *tile = reinterpret_cast<float *>(wb);                                          // [32][TF]
-  int *s_words = reinterpret_cast<int *>(wb + (size_t)128 * TF);                        // [32][16] sorted slot words
-  uint16_t *s_map = reinterpret_cast<uint16_t *>(wb + (size_t)128 * TF + 2048);         // pair p -> row * 16 + slot
-  const float **s_src = reinterpret_cast<const float **>(wb + (size_t)128 * TF + 3072); // row -> point 0 of its cloud
+  float *tile = reinterpret_cast<float *>(wb);                                          // [16][TF]
+  int *s_words = reinterpret_cast<int *>(wb + tile_bytes);                              // [32][16] sorted slot words
+  uint16_t *s_map = reinterpret_cast<uint16_t *>(wb + tile_bytes + 2048);               // pair p -> row * 16 + slot
+  const float **s_src = reinterpret_cast<const float **>(wb + tile_bytes + 3072);       // row -> point 0 of its cloud
   int *s_vb = reinterpret_cast<int *>(s_finc + (size_t)kFinWarps * warp_bytes);
   for (int k = threadIdx.x; k <= batch; k += blockDim.x) s_vb[k] = voxel_base[k];
-  for (int e = lane; e < 32 * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   const int64_t total_rows = (int64_t)batch * max_voxels;
   const int64_t row0 = ((int64_t)blockIdx.x * kFinWarps + warp) * 32;
@@ -847,63 +851,84 @@ vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int
     if (lane >= o) incl += t;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31), off = incl - cnt;
+  const int split = __shfl_sync(0xffffffffu, off, kFinTileRows);           // pairs of rows 0..15 come first
 #pragma unroll
   for (int t4 = 0; t4 < 4; ++t4)
     *reinterpret_cast<int4 *>(s_words + lane * 16 + 4 * t4) = make_int4(words[4 * t4], words[4 * t4 + 1], words[4 * t4 + 2], words[4 * t4 + 3]);
 #pragma unroll
   for (int t = 0; t < 16; ++t)
     if (t < cnt) s_map[off + t] = (uint16_t)(lane * 16 + t);
-  __syncwarp();
-  for (int p0 = 0; p0 < total; p0 += 64) {                   // two point rows per lane in flight
-    float val[2][FM];
-    int dst[2];
+  // canvas coordinates of the other half-warp's rows are needed by the lanes that share their mean work (below)
+  const int64_t canvas_cell = (((int64_t)b * mean_features * g.gz + z) * g.gy + y) * g.gx + x;   // channel 0 of the row's cell
+  const int64_t canvas_plane = (int64_t)g.gz * g.gy * g.gx;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int64_t hrow0 = row0 + half * kFinTileRows;
+    if (hrow0 >= total_rows) break;
+    for (int e = lane; e < kFinTileRows * TF / 4; e += 32) reinterpret_cast<float4 *>(tile)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    const int pbeg = half ? split : 0, pend = half ? total : split;
+    for (int p0 = pbeg; p0 < pend; p0 += 64) {                // two point rows per lane in flight
+      float val[2][FM];
+      int dst[2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int p = p0 + 32 * j + lane;
-      dst[j] = -1;
-      if (p < total) {
-        const int m = s_map[p], r = m >> 4;
-        const float *src = s_src[r] + (int64_t)(kVoxIdxBias - s_words[m]) * F;
+      for (int j = 0; j < 2; ++j) {
+        const int p = p0 + 32 * j + lane;
+        dst[j] = -1;
+        if (p < pend) {
+          const int m = s_map[p], r = m >> 4;
+          const float *src = s_src[r] + (int64_t)(kVoxIdxBias - s_words[m]) * F;
 #pragma unroll
-        for (int k = 0; k < FM; ++k)
-          if (k < F) val[j][k] = __ldg(src + k);
-        dst[j] = r * TF + (m & 15) * F;
+          for (int k = 0; k < FM; ++k)
+            if (k < F) val[j][k] = __ldg(src + k);
+          dst[j] = (r & (kFinTileRows - 1)) * TF + (m & 15) * F;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (dst[j] >= 0) {
+#pragma unroll
+          for (int k = 0; k < FM; ++k)
+            if (k < F) tile[dst[j] + k] = val[j][k];
+        }
       }
     }
+    __syncwarp();
+    if (voxel_mean || canvas) {
+      // HardSimpleVFE mean of the half's 16 rows, summed in slot order from the tile.  Both half-warps work: lane l and
+      // lane l + 16 share row (l & 15) of the half, the first takes the even features, the second the odd ones.
+      const int rl = lane & (kFinTileRows - 1), owner = half * kFinTileRows + rl, par = lane >> 4;
+      const int rcnt = __shfl_sync(0xffffffffu, cnt, owner);
+      const int64_t rcell = __shfl_sync(0xffffffffu, canvas_cell, owner);
+      if (rcnt > 0) {
+        float sum[(FM + 1) / 2];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (dst[j] >= 0) {
+        for (int k = 0; k < (FM + 1) / 2; ++k) sum[k] = 0.f;
+        const float *trow = tile + (size_t)rl * TF + par;
+        for (int t = 0; t < rcnt; ++t) {
 #pragma unroll
-        for (int k = 0; k < FM; ++k)
-          if (k < F) tile[dst[j] + k] = val[j][k];
+          for (int k = 0; k < (FM + 1) / 2; ++k)
+            if (2 * k + par < mean_features) sum[k] += trow[t * F + 2 * k];
+        }
+        const int64_t orow = hrow0 + rl;
+#pragma unroll
+        for (int k = 0; k < (FM + 1) / 2; ++k) {
+          const int f = 2 * k + par;
+          if (f >= mean_features) break;
+          const float m = sum[k] / (float)rcnt;
+          if (voxel_mean) voxel_mean[orow * mean_features + f] = m;
+          if (canvas) canvas[rcell + (int64_t)f * canvas_plane] = m;
+        }
       }
     }
+    // the half's 16 rows are one contiguous span of the output
+    const int64_t nrows = min((int64_t)kFinTileRows, total_rows - hrow0);
+    float *out = voxels + hrow0 * TF;
+    const int n4 = (int)(nrows * TF / 4);                    // hrow0 * TF * 4 bytes is a multiple of 16 (hrow0 % 16 == 0)
+    for (int e = lane; e < n4; e += 32) stg_stream_f4(reinterpret_cast<float4 *>(out) + e, reinterpret_cast<const float4 *>(tile)[e]);
+    for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
+    __syncwarp();
   }
-  __syncwarp();
-  if (cnt > 0 && (voxel_mean || canvas)) {
-    float sum[FM];
-#pragma unroll
-    for (int k = 0; k < FM; ++k) sum[k] = 0.f;
-    const float *trow = tile + (size_t)lane * TF;
-    for (int t = 0; t < cnt; ++t) {
-#pragma unroll
-      for (int k = 0; k < FM; ++k)
-        if (k < mean_features) sum[k] += trow[t * F + k];
-    }
-#pragma unroll
-    for (int k = 0; k < FM; ++k) {
-      if (k >= mean_features) break;
-      const float m = sum[k] / (float)cnt;
-      if (voxel_mean) voxel_mean[row * mean_features + k] = m;
-      if (canvas) canvas[((((int64_t)b * mean_features + k) * g.gz + z) * g.gy + y) * g.gx + x] = m;
-    }
-  }
-  // the warp's 32 rows are one contiguous span of the output
-  const int64_t nrows = min((int64_t)32, total_rows - row0);
-  float *out = voxels + row0 * TF;
-  const int n4 = (int)(nrows * TF / 4);                      // row0 * TF * 4 bytes is a multiple of 16 (row0 % 32 == 0)
-  for (int e = lane; e < n4; e += 32) stg_stream_f4(reinterpret_cast<float4 *>(out) + e, reinterpret_cast<const float4 *>(tile)[e]);
-  for (int e = n4 * 4 + lane; e < nrows * TF; e += 32) out[e] = tile[e];
 }
 
 // Dense canvas of the fused HardSimpleVFE mean, written ONCE and in order: a thread owns 4 consecutive cells, reads their
