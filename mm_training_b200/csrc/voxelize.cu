@@ -31,6 +31,7 @@ constexpr int32_t kEmptyIdx = 0x7f7f7f7f;   // what cudaMemset(0x7f) writes
 struct VoxGeom {
   float vx, vy, vz, xmin, ymin, zmin;
   int gx, gy, gz;
+  float ivx, ivy, ivz;                       // 1 / voxel size, rounded to float (point_to_cell_fast)
 };
 
 // IEEE float32 subtract, true division, floor -- exactly mmcv's `floor((p - min) / voxel_size)`.
@@ -39,6 +40,28 @@ __device__ __forceinline__ bool point_to_cell(const float *p, const VoxGeom &g, 
   const float fx = floorf(__fdiv_rn(__fsub_rn(p[0], g.xmin), g.vx));
   const float fy = floorf(__fdiv_rn(__fsub_rn(p[1], g.ymin), g.vy));
   const float fz = floorf(__fdiv_rn(__fsub_rn(p[2], g.zmin), g.vz));
+  const bool ok = fx >= 0.f && fx < (float)g.gx && fy >= 0.f && fy < (float)g.gy && fz >= 0.f && fz < (float)g.gz;
+  x = ok ? (int)fx : -1;
+  y = ok ? (int)fy : -1;
+  z = ok ? (int)fz : -1;
+  return ok;
+}
+
+// The same result with ONE rare branch instead of three IEEE divisions.  q' = (p - min) * (1 / v) differs from the
+// correctly rounded quotient by less than 7.3e-4 while |q'| < 4096 (two roundings of 2^-24 on q', one on the quotient):
+// when q' is farther than 1e-3 from every integer both floor to the same value; otherwise -- and for huge or NaN
+// coordinates, which compare false -- the exact expression decides.
+__device__ __forceinline__ bool point_to_cell_fast(const float *p, const VoxGeom &g, int &x, int &y, int &z) {
+  const float tx = __fsub_rn(p[0], g.xmin), ty = __fsub_rn(p[1], g.ymin), tz = __fsub_rn(p[2], g.zmin);
+  const float qx = __fmul_rn(tx, g.ivx), qy = __fmul_rn(ty, g.ivy), qz = __fmul_rn(tz, g.ivz);
+  const float dx = fabsf(qx - rintf(qx)), dy = fabsf(qy - rintf(qy)), dz = fabsf(qz - rintf(qz));
+  const float big = fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz));
+  float fx, fy, fz;
+  if (fminf(fminf(dx, dy), dz) > 1e-3f && big < 4096.f) {
+    fx = floorf(qx); fy = floorf(qy); fz = floorf(qz);
+  } else {
+    fx = floorf(__fdiv_rn(tx, g.vx)); fy = floorf(__fdiv_rn(ty, g.vy)); fz = floorf(__fdiv_rn(tz, g.vz));
+  }
   const bool ok = fx >= 0.f && fx < (float)g.gx && fy >= 0.f && fy < (float)g.gy && fz >= 0.f && fz < (float)g.gz;
   x = ok ? (int)fx : -1;
   y = ok ? (int)fy : -1;
@@ -272,16 +295,20 @@ struct VoxPoints {                                   // point i of sample b (i g
 };
 
 constexpr int kVcPer = 4;                          // points per thread: independent chains in flight, 4x fewer CTAs
+constexpr int kVcTile = kVcThreads * kVcPer;       // points per tile (the claim / evict kernels use the same tiles)
+// One tile per CTA, 8 resident CTAs per SM at the pillar shape.  (Tried: persistent CTAs over the tiles with two buffers,
+// the bulk copy of the next tile in flight behind the current one -- the same 48-50 us: with one tile of prefetch per
+// CTA the copy latency is no better hidden than by the neighbouring CTAs.)
 __global__ void __launch_bounds__(kVcThreads)
 vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
                 int32_t *__restrict__ first, int32_t *__restrict__ point_gcell, int l2_hints) {
-  extern __shared__ __align__(16) float s_pts[];   // kVcPer * kVcThreads * F floats
+  extern __shared__ __align__(16) float s_pts[];   // kVcTile * F floats
   __shared__ __align__(8) uint64_t s_bar;
   const int b = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
-  const int tile0 = begin + blockIdx.x * (kVcThreads * kVcPer);
+  const int tile0 = begin + blockIdx.x * kVcTile;
   if (tile0 >= end) return;
-  const int npts = min(kVcThreads * kVcPer, end - tile0);
+  const int npts = min(kVcTile, end - tile0);
   const float *src = pts.row(b, begin, tile0, F);
   // the tile is one contiguous span of the cloud: ONE bulk copy (TMA, SASS UBLKCP) when its address and size are
   // multiples of 16 bytes (always for full tiles of a 16-byte aligned cloud), else 4-byte loads (a point row is F*4 = 20
@@ -301,27 +328,25 @@ vox_cell_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGe
     for (int e = threadIdx.x; e < npts * F; e += kVcThreads) s_pts[e] = ldg_stream_f32(src + e);
     __syncthreads();
   }
+  // the table is visited at random by three kernels of the call: evict_last keeps its lines ahead of the streams
+  const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   int gcell[kVcPer];
 #pragma unroll
   for (int k = 0; k < kVcPer; ++k) {
-    const int p = k * kVcThreads + threadIdx.x;     // consecutive lanes = consecutive points (index order inside a warp)
+    const int p = k * kVcThreads + threadIdx.x;     // consecutive lanes = consecutive points
     gcell[k] = -1;
     if (p < npts) {
       int x, y, z;
-      if (point_to_cell(s_pts + p * F, g, x, y, z)) gcell[k] = (int)((int64_t)b * cells + ((int64_t)z * g.gy + y) * g.gx + x);
+      if (point_to_cell_fast(s_pts + p * F, g, x, y, z)) gcell[k] = (int)((int64_t)b * cells + ((int64_t)z * g.gy + y) * g.gx + x);
       point_gcell[tile0 + p] = gcell[k];
     }
   }
-  // one atomic per distinct cell of the warp: the lowest lane of a match group holds the lowest index.  The table is
-  // visited at random by three kernels of the call: its lines are marked evict_last so that the streams in between
-  // (points in, cell ids out) do not push them out of L2.
-  const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+  // first point of every cell: one fire-and-forget red.min per kept point.  (Aggregating the points of a warp that share
+  // a cell with __match_any_sync first saved few atomics -- a sweep is sparse -- and cost four MATCH round trips per
+  // thread: a quarter of the kernel's stall samples.)
 #pragma unroll
-  for (int k = 0; k < kVcPer; ++k) {
-    const unsigned peers = __match_any_sync(0xffffffffu, gcell[k]);
-    if (gcell[k] >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
-      red_min_l2hint_i32(first + gcell[k], tile0 + k * kVcThreads + (int)threadIdx.x, pol);
-  }
+  for (int k = 0; k < kVcPer; ++k)
+    if (gcell[k] >= 0) red_min_l2hint_i32(first + gcell[k], tile0 + k * kVcThreads + (int)threadIdx.x, pol);
 }
 
 // Per SAMPLE (blockIdx.y) exclusive scan, in point order, of flag(i) = "i is the first point of its cell" = the voxel
@@ -1055,6 +1080,7 @@ static VoxGeom make_geom(const float *vs, const float *range, const int *grid) {
   g.vx = vs[0]; g.vy = vs[1]; g.vz = vs[2];
   g.xmin = range[0]; g.ymin = range[1]; g.zmin = range[2];
   g.gx = grid[0]; g.gy = grid[1]; g.gz = grid[2];
+  g.ivx = 1.0f / g.vx; g.ivy = 1.0f / g.vy; g.ivz = 1.0f / g.vz;
   return g;
 }
 
@@ -1156,8 +1182,8 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   const dim3 pgrid(ptiles, (unsigned)batch);
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
   if (total_points > 0) {
-    vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcPer * kVcThreads * F * sizeof(float), stream>>>(
-        pts, sample_offsets, F, g, cells, first, gcell, vox_l2_hints());
+    vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcTile * F * sizeof(float), stream>>>(pts, sample_offsets, F, g, cells, first,
+                                                                                        gcell, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
   }
   vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(

@@ -201,6 +201,26 @@ def test_canvas_without_a_mean_output_takes_the_fill_and_scatter_path():
     assert torch.equal(canvas, ref[5]) and torch.equal(voxels, ref[0]) and torch.equal(num, ref[1]) and torch.equal(base, ref[3])
 
 
+@pytest.mark.parametrize('F,mf,T', [(12, 12, 5), (9, 7, 16), (16, 3, 2)])
+def test_wide_point_rows_and_odd_mean_widths(F, mf, T):
+    # point rows beyond 8 floats take the 16-wide instantiations of the finalize and canvas kernels; odd mean widths
+    # split unevenly between the two half-warps that share a row's sums
+    rng = np.random.default_rng(F * 100 + mf)
+    clouds = []
+    for n in (4000, 0, 2500):
+        p = rng.uniform(-0.5, 8.5, size=(n, F)).astype(np.float32)
+        p[:, 2] = rng.uniform(0.0, 1.0, n)
+        clouds.append(p)
+    vs, rg, M = [0.5, 0.5, 1.0], [0, 0, 0, 8, 8, 1], 200
+    gpu = _check_batch(clouds, vs, rg, T, M, mean_features=mf)
+    out = hard_voxelize_batch([torch.from_numpy(p).to(DEV) for p in clouds], vs, rg, T, M, mean_features=mf, padded=True,
+                              scatter=True)
+    n = int(out[3][-1])
+    assert torch.equal(out[0][:n], gpu[0]) and torch.equal(out[4][:n], gpu[4])
+    ref = vz.pillar_scatter_ref(gpu[4].cpu().numpy(), gpu[2].cpu().numpy(), 3, (1, 16, 16))
+    assert np.array_equal(out[5].cpu().numpy(), ref)
+
+
 def test_dynamic_voxelize():
     pts = synthetic.lidar_sweep(50000, 5, seed=3)
     coors = dynamic_voxelize(torch.from_numpy(pts).to(DEV), CFG_3.voxel_size, CFG_3.point_cloud_range)
