@@ -1182,8 +1182,10 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   const dim3 pgrid(ptiles, (unsigned)batch);
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
   if (total_points > 0) {
-    vox_cell_kernel<<<pgrid, kVcThreads, (size_t)kVcTile * F * sizeof(float), stream>>>(pts, sample_offsets, F, g, cells, first,
-                                                                                        gcell, vox_l2_hints());
+    const size_t cell_smem = (size_t)kVcTile * F * sizeof(float);
+    if (cell_smem + 64 > 48 * 1024)                       // point rows of 12 floats and more: beyond the default limit
+      BEVPOOL_RETURN_IF_CUDA(cudaFuncSetAttribute(vox_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cell_smem));
+    vox_cell_kernel<<<pgrid, kVcThreads, cell_smem, stream>>>(pts, sample_offsets, F, g, cells, first, gcell, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
   }
   vox_scan_kernel<<<dim3((unsigned)tps, (unsigned)batch), kScanThreads, 0, stream>>>(
