@@ -258,8 +258,10 @@ int bevpool_transpose(const void *in, void *out, int dtype, int batch, int64_t r
  * bevvox_hard_voxelize_scatter (dense path only) takes the clouds either concatenated or as a DEVICE array of `batch`
  * per-sample base pointers (points == NULL; the reference passes a list of tensors: no concatenation pass) and, with
  * canvas != NULL, also writes the dense canvas (batch, mean_features, gz, gy, gx) of the fused HardSimpleVFE mean --
- * voxelize -> VFE -> scatter of models/bev_depth.py:181-183 in one call.  canvas_is_zeroed != 0: the caller zero-filled
- * the canvas already (e.g. on a side stream while the voxelizer's first kernels run); else the call fills it.          */
+ * voxelize -> VFE -> scatter of models/bev_depth.py:181-183 in one call.  canvas_is_zeroed == 0: the call writes every
+ * element of the canvas (with a voxel_mean output: one in-order pass over the canvas after the voxels are final, no
+ * fill; without: a zero fill on a side stream + scattered stores); != 0: the caller zero-filled it already and only the
+ * occupied cells are stored.                                                                                          */
 int bevvox_temp_bytes(int batch, int64_t total_points, const int *grid_host, int max_voxels, int max_points,
                       size_t *temp_bytes);
 int bevvox_hard_voxelize(const float *points, const int32_t *sample_offsets, int batch,
