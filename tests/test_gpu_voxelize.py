@@ -221,6 +221,16 @@ def test_wide_point_rows_and_odd_mean_widths(F, mf, T):
     assert np.array_equal(out[5].cpu().numpy(), ref)
 
 
+def test_all_samples_empty():
+    # no point at all: zero voxels, zero canvas, nothing launched over an empty range
+    clouds = [torch.zeros(0, 5, device=DEV), torch.zeros(0, 5, device=DEV)]
+    out = hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, 15, 100, mean_features=5, padded=True, scatter=True)
+    assert out[3].tolist() == [0, 0, 0] and int(out[1].abs().sum()) == 0 and float(out[0].abs().sum()) == 0.0
+    assert float(out[5].abs().sum()) == 0.0 and out[5].shape == (2, 5, 256, 2048)
+    v, n, c, base, mean = hard_voxelize_batch(clouds, CFG_3.voxel_size, CFG_3.point_cloud_range, 15, 100, mean_features=5)
+    assert v.shape[0] == 0 and n.shape[0] == 0 and c.shape == (0, 4)
+
+
 def test_dynamic_voxelize():
     pts = synthetic.lidar_sweep(50000, 5, seed=3)
     coors = dynamic_voxelize(torch.from_numpy(pts).to(DEV), CFG_3.voxel_size, CFG_3.point_cloud_range)
