@@ -90,9 +90,12 @@ class LiftSplatGeometry:
     @staticmethod
     def combine(sensor2ego_mat: torch.Tensor, intrin_mat: torch.Tensor) -> torch.Tensor:
         """``sensor2ego @ inverse(intrin)`` (B, N, 4, 4) -- ``lss_fpn.py:354``, left in torch (B*N tiny matrices); always
-        float32 (autocast off)."""
+        float32 (autocast off).  ``inv_ex(check_errors=False)`` runs the LU kernels of ``torch.inverse`` (same values)
+        without its singularity check, which is a host synchronisation per call; a singular intrinsic matrix gives inf / nan
+        coordinates here and every point of that image is dropped (the reference raises)."""
         with torch.autocast(device_type=sensor2ego_mat.device.type, enabled=False):
-            return sensor2ego_mat.float().matmul(torch.inverse(intrin_mat.float())).contiguous()
+            inv = torch.linalg.inv_ex(intrin_mat.float(), check_errors=False).inverse
+            return sensor2ego_mat.float().matmul(inv).contiguous()
 
     # ---- device path ---------------------------------------------------------------------------------
     def rig_geom(self, combine: torch.Tensor, variant: int) -> torch.Tensor:
