@@ -513,9 +513,12 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
   __shared__ uint32_t s_over;                                     // overflow entries of this tile so far
   const uint64_t pol = (l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
   const uint64_t pol_lists = (l2_hints & 2) ? l2_policy_evict_last() : l2_policy_evict_normal();
-  const int b = blockIdx.y;
+  // grid = (samples, tiles): CTAs are dispatched tile-major, so the tiles of a sample take their tickets roughly in point
+  // order -- a near-range voxel's slots are then mostly taken by its earliest points already and the late arrivals in
+  // its overflow list lose at their first look at the row (no compare-and-swap rounds)
+  const int b = blockIdx.x, tile = blockIdx.y;
   const int begin = offsets[b], end = offsets[b + 1];
-  const int tile0 = begin + blockIdx.x * (256 * kVcPer);
+  const int tile0 = begin + tile * (256 * kVcPer);
   if (tile0 >= end) return;
   const int i0 = tile0 + threadIdx.x;
   if (threadIdx.x == 0) s_over = 0u;
@@ -551,7 +554,7 @@ vox_claim_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict_
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) tile_overflow[(int64_t)b * tiles_cap + blockIdx.x] = s_over;
+  if (threadIdx.x == 0) tile_overflow[(int64_t)b * tiles_cap + tile] = s_over;
 }
 
 // word of slot t of a row held as LQ quads (t a compile-time constant after unrolling)
@@ -566,11 +569,11 @@ __global__ void __launch_bounds__(128)
 vox_evict_kernel(const int32_t *__restrict__ offsets, const int2 *__restrict__ overflow_all,
                  const uint32_t *__restrict__ tile_overflow, int tiles_cap, int max_points, int32_t *__restrict__ lists) {
   // one CTA per tile of the claim kernel: its overflow entries sit at the tile's first point index
-  const int b = blockIdx.y;
+  const int b = blockIdx.x, tile = blockIdx.y;              // (tile-major like the claim kernel: the earliest candidates first)
   const int begin = offsets[b], end = offsets[b + 1];
-  const int tile0 = begin + blockIdx.x * (256 * kVcPer);
+  const int tile0 = begin + tile * (256 * kVcPer);
   if (tile0 >= end) return;
-  const uint32_t n = tile_overflow[(int64_t)b * tiles_cap + blockIdx.x];
+  const uint32_t n = tile_overflow[(int64_t)b * tiles_cap + tile];
   const int2 *overflow = overflow_all + tile0;
   const int LS = vox_list_stride(max_points);
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
@@ -1180,6 +1183,7 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   uint32_t *tile_overflow = reinterpret_cast<uint32_t *>(tb + L.off_tile_overflow);
   const unsigned ptiles = (unsigned)ceil_div64(max_sample_points > 0 ? max_sample_points : 1, kVcThreads * kVcPer);
   const dim3 pgrid(ptiles, (unsigned)batch);
+  if (ptiles > 65535u) return BEVPOOL_E_RANGE;            // (the claim kernel walks the tiles in grid.y: 67 M points per sample)
   BEVPOOL_RETURN_IF_CUDA(cudaMemsetAsync(first, 0x7f, L.first_bytes, stream));
   if (total_points > 0) {
     const size_t cell_smem = (size_t)kVcTile * F * sizeof(float);
@@ -1196,12 +1200,12 @@ static int hard_voxelize_dense(VoxPoints pts, const int32_t *sample_offsets, int
   vox_dense_base_kernel<<<1, 32, 0, stream>>>(totals, batch, max_voxels, voxel_base);
   BEVPOOL_LAUNCH_CHECK();
   if (total_points > 0) {
-    vox_claim_kernel<<<pgrid, 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
+    vox_claim_kernel<<<dim3((unsigned)batch, ptiles), 256, 0, stream>>>(sample_offsets, gcell, vid_of_cell, voxel_base, max_voxels, max_points, lists,
                                                 arrivals, overflow, tile_overflow, L.tiles_cap, vox_l2_hints());
     BEVPOOL_LAUNCH_CHECK();
   }
   if (total_points > 0) {
-    const dim3 egrid(ptiles, (unsigned)batch);
+    const dim3 egrid((unsigned)batch, ptiles);
     switch (max_points <= 16 ? vox_list_stride(max_points) / 4 : 0) {
       case 1: vox_evict_kernel<1><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
       case 2: vox_evict_kernel<2><<<egrid, 128, 0, stream>>>(sample_offsets, overflow, tile_overflow, L.tiles_cap, max_points, lists); break;
