@@ -730,6 +730,18 @@ def main():
                 'unit': 'GB/s', 'frac': achieved / peak_gbs, 'peak_source': peak_src, 'traffic': traffic,
                 'algorithmic_bytes_per_frame': bytes_[dom_name], 'kernel_ms': dom[0],
                 'frac_of_nominal_8TBps': achieved / 8000.0}
+    # both fused kernels against the same peak (the dominant one above is whichever is slower in this run)
+    roofline['kernels'] = []
+    for nm, kt in (('fused_forward', k_fwd), ('fused_backward', k_bwd)):
+        gbs = bytes_[nm] * B / (kt[0] * 1e-3) / 1e9
+        ent = None
+        try:
+            ent = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get(nm + '_kernel')
+        except (OSError, ValueError):
+            pass
+        roofline['kernels'].append({'kernel': nm + '_kernel', 'kernel_ms': kt[0], 'algorithmic_bytes_per_frame': bytes_[nm],
+                                    'achieved': gbs, 'frac': gbs / peak_gbs,
+                                    'traffic': ent['dram_bytes_per_launch'] if ent and ent.get('frames_per_launch') == B else None})
     step_gbs = bytes_['step'] * B / (ms_per_step * 1e-3) / 1e9
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
