@@ -105,3 +105,31 @@ def test_vfe_and_pillar_scatter_oracle():
     g = rng.random(canvas.shape).astype(np.float32)
     gb = vz.pillar_scatter_backward_ref(g, coors, (1, 256, 2048))
     assert np.array_equal(gb[m], g[b, :, y, x])
+
+
+def test_reciprocal_cell_index_rule_equals_the_exact_division():
+    """csrc/voxelize.cu::point_to_cell_fast in numpy float32: q' = (p - min) * fl(1 / v) decides floor(fl((p - min) / v))
+    whenever q' is farther than 1e-3 from every integer and |q'| < 4096; otherwise the exact expression is used.  Checked
+    on random coordinates, on coordinates placed within a few ulps of every cell boundary, and for awkward voxel sizes."""
+    rng = np.random.default_rng(0)
+    for v in (0.2, 0.1, 0.05, 0.075, 0.8, 1.0 / 3.0, 0.16, 2.5):
+        v32 = np.float32(v)
+        inv = np.float32(1.0) / v32
+        lo = np.float32(-204.8 if v < 1 else -37.3)
+        cells = np.arange(0, 4096, dtype=np.float64)
+        edges = (np.float64(lo) + cells * np.float64(v32)).astype(np.float32)
+        near = np.concatenate([np.nextafter(edges, np.float32(np.inf)), np.nextafter(edges, np.float32(-np.inf)), edges])
+        for k in range(1, 6):                                        # a few more ulps around every boundary
+            up = near.copy()
+            for _ in range(k):
+                up = np.nextafter(up, np.float32(np.inf))
+            near = np.concatenate([near, up])
+        p = np.concatenate([near, rng.uniform(float(lo) - 5, float(lo) + 4096 * v + 5, 2_000_000).astype(np.float32)])
+        t = (p - lo).astype(np.float32)
+        exact = np.floor((t / v32).astype(np.float32))
+        q = (t * inv).astype(np.float32)
+        fast_ok = (np.abs(q - np.rint(q)) > np.float32(1e-3)) & (np.abs(q) < np.float32(4096.0))
+        assert np.array_equal(np.floor(q)[fast_ok], exact[fast_ok]), v
+        ordinary = np.arange(p.size) >= near.size                    # the uniformly drawn coordinates
+        ordinary &= (q > 0) & (q < 4000)
+        assert fast_ok[ordinary].mean() > 0.99                       # (the exact path is the rare one on ordinary data)
