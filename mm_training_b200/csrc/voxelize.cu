@@ -6,7 +6,10 @@
 // first in-range point of its cell, at most max_voxels voxels exist (later cells are dropped
 // entirely), and the first max_points points of a voxel are kept in order.
 //
-// Parallel formulation with bit-identical results:
+// Two pipelines with identical outputs: grids of up to 2^26 cells per batch (every pillar / voxel grid of the reference) take
+// the DENSE-TABLE path further down (first-point table, tickets + eviction, cooperative finalize, dense canvas); larger grids
+// take the hash path described here.
+// Parallel formulation with bit-identical results (hash path):
 //   1. warp-cooperative hash insert of (sample, cell) keys; per slot atomicMin of the point
 //      index  -> first-occurrence point of every cell (order independent)
 //   2. flag "point is the first of its cell" -> exclusive scan in point order = voxel id
