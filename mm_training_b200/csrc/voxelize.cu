@@ -811,7 +811,7 @@ __host__ __device__ inline size_t vox_fin_coop_warp_bytes(int max_points, int F)
   return (size_t)kFinTileRows * 4 * max_points * F + 2048 + 1024 + 256;
 }
 template <int FM>
-__global__ void __launch_bounds__(kFinWarps * 32, FM <= 8 ? 6 : 3)
+__global__ void __launch_bounds__(kFinWarps * 32, FM <= 8 ? 5 : 3)
 vox_finalize_coop_kernel(VoxPoints pts, const int32_t *__restrict__ offsets, int F, VoxGeom g, int64_t cells,
                          const int32_t *__restrict__ cell_of_vid, const int32_t *__restrict__ lists,
                          const uint32_t *__restrict__ arrivals, int batch, int max_voxels, int max_points,
